@@ -1,0 +1,232 @@
+/*
+ * infur_b200 -- C ABI of the B200-native `Scale -> Model -> ColorCode` hot path of ahirner/infur.
+ *
+ * The reference has no FFI today: its plug-in surface is the Rust trait `Processor`
+ * (infur/src/processing.rs:23-60: control / advance / is_dirty / generate) and the three
+ * implementations sequenced by `ProcessingApp::advance` (infur/src/app.rs:107-153).  Every entry
+ * point below names the reference item it replaces; INTEGRATION.md shows the Rust binding
+ * (`impl Processor for GpuPipeline`) a maintainer would add.
+ *
+ * Conventions: C99, `int32_t` status (0 = OK; nothing throws or aborts across the boundary),
+ * opaque handle, caller-owned buffers with explicit capacities, no callbacks.  One owner thread per
+ * handle (the reference creates its ORT session on the "Proc" thread because it cannot be sent,
+ * infur/src/main.rs:38-40).  All work runs on one CUDA device chosen at create(); multi-GPU is one
+ * handle (one process) per GPU with frames sharded by id (DESIGN.md "Multi-GPU").
+ *
+ * There is NO CPU fallback: without a CUDA device create() returns INFUR_E_NO_DEVICE.
+ */
+#ifndef INFUR_B200_H
+#define INFUR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INFUR_B200_ABI_VERSION 1
+
+typedef struct infur_b200_handle infur_b200_handle;
+
+/* ---- status codes (mirror the reference's error enums) ---------------------------------- */
+enum {
+  INFUR_OK = 0,
+  INFUR_E_INVALID_ARG = 1,
+  INFUR_E_SCALE_NONPOSITIVE = 2,  /* ValidScaleError "Cannot scale by negative number" processing.rs:159-168 */
+  INFUR_E_ZERO_SIZE_IN = 3,       /* ScaleProcError::ZeroSizeIn   processing.rs:203-204 */
+  INFUR_E_ZERO_SIZE_OUT = 4,      /* ScaleProcError::ZeroSizeOut  processing.rs:205-206 */
+  INFUR_E_MODEL_LOAD = 5,         /* ModelCmdError::OrtError      predict_onnx.rs:43-46 (unreadable / unparsable / unsupported file) */
+  INFUR_E_MODEL_INPUT_FORMAT = 6, /* ModelInputFormatError::Infer predict_onnx.rs:50-54,223-265 */
+  INFUR_E_SHAPE = 7,              /* ModelProcError::ShapeError   predict_onnx.rs:35-36 */
+  INFUR_E_RUNTIME = 8,            /* ModelProcError::RuntimeError predict_onnx.rs:37-38 (here: CUDA errors) */
+  INFUR_E_BUFFER_TOO_SMALL = 9,   /* C analogue of "stage re-allocates Out on size change" (processing.rs:260-268) */
+  INFUR_E_NO_DEVICE = 10,
+  INFUR_E_UNSUPPORTED = 11,
+  INFUR_E_TICKET = 12
+};
+
+enum { INFUR_RESIZE_NEAREST = 0 /* fr::ResizeAlg::Nearest, processing.rs:189 (the reference's only mode) */ };
+enum { INFUR_CONV_TCGEN05 = 0, INFUR_CONV_VALIDATE = 1 /* slow CUDA-core kernel, validation only; never selected implicitly */ };
+
+typedef struct infur_b200_config {
+  uint32_t struct_size;  /* sizeof(infur_b200_config) */
+  int32_t device;        /* CUDA ordinal */
+  int32_t max_batch;     /* frames per ring slot (default 8) */
+  int32_t ring_depth;    /* pinned ring slots (default 3) */
+  int32_t resize_mode;   /* INFUR_RESIZE_NEAREST */
+  int32_t compute_aux;   /* also evaluate the `aux` head (the reference's caller discards it, app.rs:116) */
+  int32_t blend;         /* also produce blended_rgba (new feature; gui.rs:324-329 "todo: blend somehow?") */
+  int32_t conv_impl;     /* INFUR_CONV_TCGEN05 */
+  int32_t use_cuda_graph;/* capture the per-shape forward into a CUDA graph */
+} infur_b200_config;
+
+/* Fills *cfg with the defaults of the three stages: factor 1.0, dirty, no model
+ * (processing.rs:185-193, predict_onnx.rs:151-155). */
+void infur_b200_default_config(infur_b200_config* cfg);
+
+int32_t infur_b200_abi_version(void);
+
+/* `Default::default()` of Scale + Model + ColorCode and the process-wide ENVIRONMENT
+ * (predict_onnx.rs:19-30). */
+int32_t infur_b200_create(const infur_b200_config* cfg, infur_b200_handle** out);
+void infur_b200_destroy(infur_b200_handle* h);
+
+/* thiserror Display strings (processing.rs:203-210, predict_onnx.rs:33-54); handle-local, valid until
+ * the next call on the handle.  h == NULL returns the message of the last failed create(). */
+const char* infur_b200_last_error(const infur_b200_handle* h);
+
+/* ---- control ------------------------------------------------------------------------------ */
+
+/* Scale::control (processing.rs:220-226): f <= 0 -> INFUR_E_SCALE_NONPOSITIVE, state unchanged;
+ * else dirty = (f != old factor). NaN passes, as in the reference. */
+int32_t infur_b200_scale_control(infur_b200_handle* h, float factor);
+
+/* Model::control(ModelCmd::Load(path)) (predict_onnx.rs:283-315): "" unloads.  On any failure the
+ * previously loaded model stays active (:289-308). */
+int32_t infur_b200_model_load(infur_b200_handle* h, const char* utf8_path);
+
+/* Same, from an in-memory copy of the .onnx file (used after a rank-0 broadcast of the file). */
+int32_t infur_b200_model_load_bytes(infur_b200_handle* h, const void* onnx, size_t size);
+
+/* ModelInfo / Model::get_info (predict_onnx.rs:56-62,341-345).  Writes a NUL-terminated text
+ * "input0_name\tinput0_dtype\tout0,out1,...".  Returns INFUR_E_INVALID_ARG when no model is loaded
+ * (get_info() == None), INFUR_E_BUFFER_TOO_SMALL (with *required set) when cap is too small. */
+int32_t infur_b200_model_info(const infur_b200_handle* h, char* buf, size_t cap, size_t* required);
+
+/* Weight arena in device memory (packed fp16 weights + f32 biases), for an NCCL broadcast from the
+ * rank that parsed the file; *dptr is a CUDA device pointer. */
+int32_t infur_b200_model_weights(const infur_b200_handle* h, void** dptr, size_t* bytes);
+
+/* Scale::is_dirty (processing.rs:228-230); Model and ColorCode are never dirty
+ * (predict_onnx.rs:336-338, decode_predict.rs:81-83). */
+int32_t infur_b200_is_dirty(const infur_b200_handle* h);
+
+/* ---- advance ------------------------------------------------------------------------------- */
+
+typedef struct infur_b200_out {
+  uint32_t struct_size; /* sizeof(infur_b200_out) */
+  /* caller-owned HOST buffers; NULL = output not wanted; *_cap in bytes */
+  uint8_t* scaled_bgr;   size_t scaled_bgr_cap;   /* Scale output, [out_h][out_w][3] u8 */
+  uint8_t* frame_rgba;   size_t frame_rgba_cap;   /* GUIFrame.buffer, app.rs:132-144: (r,g,b,255) */
+  uint8_t* class_map;    size_t class_map_cap;    /* k_max per pixel, decode_predict.rs:67-77, u8 */
+  uint8_t* decoded_rgba; size_t decoded_rgba_cap; /* GUIFrame.decoded_buffer: premultiplied Color32 */
+  uint8_t* blended_rgba; size_t blended_rgba_cap; /* mask "over" frame (cfg.blend) */
+  float* logits_f32;     size_t logits_cap;       /* Model::advance out[0]: [K][out_h][out_w] f32 (debug path) */
+  float* aux_logits_f32; size_t aux_logits_cap;   /* Model::advance out[1] (cfg.compute_aux) */
+  /* written by the library */
+  uint32_t out_w, out_h;     /* (w as f32 * factor) as u32, processing.rs:253-254 */
+  uint32_t num_classes;      /* K */
+  int32_t has_decoded;       /* 0 when no model is loaded: decoded_img = None, app.rs:127-129 */
+  uint64_t id;               /* Frame.id passes through, processing.rs:239,264 */
+  size_t required[7];        /* bytes needed for each buffer above, in declaration order */
+} infur_b200_out;
+
+/* Scale::advance -> Model::advance -> ColorCode::advance as sequenced in app.rs:109-149.
+ * Synchronous.  `bgr` is a caller-owned tight HWC B,G,R u8 image of w*h*3 bytes
+ * (image-ext/src/image_bgr.rs:7-11), only read during the call.  Clears the dirty flag
+ * (processing.rs:233).  Errors: INFUR_E_ZERO_SIZE_IN / _OUT, INFUR_E_BUFFER_TOO_SMALL (required[]
+ * filled, nothing written), INFUR_E_RUNTIME. */
+int32_t infur_b200_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, uint64_t id,
+                           infur_b200_out* out);
+
+/* Batched synchronous variant: n frames of identical size, stored back to back. outs[i] as above. */
+int32_t infur_b200_advance_batch(infur_b200_handle* h, const uint8_t* bgr, uint32_t n, uint32_t w, uint32_t hgt,
+                                 const uint64_t* ids, infur_b200_out* outs);
+
+/* ---- pinned ring: asynchronous batches (new; configs "batch=8, pinned ring buffer") ------- */
+
+typedef struct infur_b200_slot {
+  uint64_t ticket;
+  uint32_t n, w, h;          /* frames in the slot, input size */
+  uint32_t out_w, out_h;     /* valid after ring_wait */
+  uint32_t num_classes;
+  int32_t has_decoded;
+  uint8_t* bgr_in;           /* PINNED host memory: the frame source writes n*w*h*3 bytes here */
+  const uint8_t* class_map;  /* PINNED, [n][out_h][out_w]      valid after ring_wait until the slot is re-acquired */
+  const uint8_t* decoded_rgba; /* PINNED, [n][out_h][out_w][4] */
+  const uint8_t* blended_rgba; /* PINNED or NULL */
+} infur_b200_slot;
+
+/* Next free slot sized for n frames of w x h; INFUR_E_TICKET when all ring_depth slots are in flight. */
+int32_t infur_b200_ring_acquire(infur_b200_handle* h, uint32_t n, uint32_t w, uint32_t hgt, infur_b200_slot* slot);
+/* Enqueue H2D copy, the whole path, and the D2H copies of the slot; returns immediately. */
+int32_t infur_b200_ring_submit(infur_b200_handle* h, uint64_t ticket);
+/* Block until the slot's results are in pinned memory; tickets complete in submission order. */
+int32_t infur_b200_ring_wait(infur_b200_handle* h, uint64_t ticket, infur_b200_slot* slot);
+
+/* ---- device-resident path (bench `value`: inputs already in HBM) --------------------------- */
+
+/* d_bgr: device pointer to n tight BGR frames.  d_class_map / d_decoded_rgba (/ d_blended, may be
+ * NULL): device outputs [n][out_h][out_w]( [4] ).  Enqueued on the handle's compute stream;
+ * `sync` != 0 waits for completion. */
+int32_t infur_b200_advance_device(infur_b200_handle* h, const uint8_t* d_bgr, uint32_t n, uint32_t w, uint32_t hgt,
+                                  uint8_t* d_class_map, uint8_t* d_decoded_rgba, uint8_t* d_blended_rgba,
+                                  uint32_t* out_w, uint32_t* out_h, int32_t sync);
+
+/* CUDA stream (cudaStream_t) the device-resident path launches on, for event timing by the caller. */
+void* infur_b200_compute_stream(const infur_b200_handle* h);
+
+/* Kernels this library has launched on the handle since create() (bench `gpu_launches`). */
+uint64_t infur_b200_launch_count(const infur_b200_handle* h);
+
+/* ---- single-stage entry points (each Processor on its own; used by the parity tests) ------- */
+
+/* Scale::advance alone (processing.rs:232-281) with the handle's current factor: host in, host out. */
+int32_t infur_b200_scale_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt,
+                                 uint8_t* out_bgr, size_t out_cap, uint32_t* out_w, uint32_t* out_h);
+
+/* Pre-processing of ImageSession::forward alone (predict_onnx.rs:103-137): [h][w][3] u8 BGR ->
+ * [3][h][w] f32 RGB-normalised. */
+int32_t infur_b200_preprocess(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* out_nchw,
+                              size_t out_cap_bytes);
+
+/* ColorCode::advance alone (decode_predict.rs:53-79) on a [k][hgt][w] f32 confidence map; any k >= 1.
+ * rgba: [hgt][w][4] premultiplied; class_map (may be NULL): [hgt][w] u8 (k_max & 0xff). */
+int32_t infur_b200_color_code(infur_b200_handle* h, const float* hm, uint32_t k, uint32_t w, uint32_t hgt,
+                              uint8_t* rgba, uint8_t* class_map);
+
+/* Fused post-kernel alone: low-res logits [k][lh][lw] f32 -> bilinear half-pixel upsample to
+ * out_w x out_h -> argmax/confidence colour (the network's final Resize, executed inside
+ * session.run predict_onnx.rs:138, fused with decode_predict.rs:53-79).  frame_bgr (may be NULL) is the
+ * [out_h][out_w][3] frame to blend onto when blended_rgba != NULL. */
+int32_t infur_b200_upsample_color(infur_b200_handle* h, const float* lowres, uint32_t k, uint32_t lw, uint32_t lh,
+                                  uint32_t out_w, uint32_t out_h, const uint8_t* frame_bgr, uint8_t* class_map,
+                                  uint8_t* decoded_rgba, uint8_t* blended_rgba, float* logits_f32);
+
+/* The 20 x 256 x 4 premultiplied colour table (decode_predict.rs:9-36 through epaint's
+ * Color32::from_rgba_unmultiplied) the post-kernel indexes; 20480 bytes. */
+int32_t infur_b200_color_lut(const infur_b200_handle* h, uint8_t* lut, size_t cap);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+
+/* One convolution through the selected implementation, host tensors in NHWC fp16 (x, residual, y),
+ * weights [cout][kh][kw][cin] fp16, bias f32.  y_f32 != NULL asks for an f32 NHWC output instead.
+ * Returns INFUR_E_UNSUPPORTED for a shape the implementation cannot run. */
+typedef struct infur_b200_conv_desc {
+  uint32_t n, h, w, cin, cout, kh, kw, stride, pad, dil;
+  int32_t relu;
+  int32_t impl; /* INFUR_CONV_TCGEN05 / INFUR_CONV_VALIDATE */
+} infur_b200_conv_desc;
+int32_t infur_b200_conv_test(infur_b200_handle* h, const infur_b200_conv_desc* d, const uint16_t* x,
+                             const uint16_t* wgt, const float* bias, const uint16_t* residual, uint16_t* y,
+                             float* y_f32, float* elapsed_ms);
+
+/* Human-readable execution plan of the loaded model for an input of w x hgt (after Scale), n frames:
+ * one line per kernel with shapes, tile choice, algorithmic FLOPs and bytes. */
+int32_t infur_b200_plan_text(infur_b200_handle* h, uint32_t n, uint32_t w, uint32_t hgt, char* buf, size_t cap,
+                             size_t* required);
+
+/* Per-kernel CUDA-event timing of one forward of the current plan (ms per op, same order as
+ * plan_text); returns the number of ops written. */
+int32_t infur_b200_profile_ops(infur_b200_handle* h, const uint8_t* d_bgr, uint32_t n, uint32_t w, uint32_t hgt,
+                               int32_t iters, float* ms, int32_t cap, int32_t* count);
+
+/* Parses an .onnx file on the CPU only (no device needed) and writes the fused op list as text;
+ * lets the loader be tested without a GPU. */
+int32_t infur_b200_onnx_describe(const char* utf8_path, char* buf, size_t cap, size_t* required);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INFUR_B200_H */

@@ -1,0 +1,435 @@
+// ONNX protobuf-wire reader + lowering to the fused conv list.  See onnx_reader.h.
+#include "onnx_reader.h"
+
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+
+#include "../../include/infur_b200.h"
+
+namespace infur {
+namespace {
+
+struct Cursor {
+  const uint8_t* p;
+  const uint8_t* end;
+  bool done() const { return p >= end; }
+  uint64_t varint() {
+    uint64_t r = 0;
+    int shift = 0;
+    while (true) {
+      if (p >= end) throw std::runtime_error("onnx: truncated varint");
+      uint8_t c = *p++;
+      r |= (uint64_t)(c & 0x7f) << shift;
+      if (!(c & 0x80)) return r;
+      shift += 7;
+      if (shift > 63) throw std::runtime_error("onnx: varint too long");
+    }
+  }
+  // Reads one field header; for length-delimited fields returns the sub-range.
+  bool next(uint32_t& field, uint32_t& wire, uint64_t& val, Cursor& sub) {
+    if (done()) return false;
+    uint64_t key = varint();
+    field = (uint32_t)(key >> 3);
+    wire = (uint32_t)(key & 7);
+    switch (wire) {
+      case 0: val = varint(); break;
+      case 1:
+        if (end - p < 8) throw std::runtime_error("onnx: truncated fixed64");
+        memcpy(&val, p, 8); p += 8; break;
+      case 2: {
+        uint64_t len = varint();
+        if ((uint64_t)(end - p) < len) throw std::runtime_error("onnx: truncated length-delimited field");
+        sub.p = p; sub.end = p + len; p += len; break;
+      }
+      case 5: {
+        if (end - p < 4) throw std::runtime_error("onnx: truncated fixed32");
+        uint32_t v; memcpy(&v, p, 4); val = v; p += 4; break;
+      }
+      default: throw std::runtime_error("onnx: unsupported wire type");
+    }
+    return true;
+  }
+};
+
+std::string str(const Cursor& c) { return std::string((const char*)c.p, (size_t)(c.end - c.p)); }
+
+void packed_varints(uint32_t wire, uint64_t val, Cursor sub, std::vector<int64_t>& out) {
+  if (wire == 0) { out.push_back((int64_t)val); return; }
+  while (!sub.done()) out.push_back((int64_t)sub.varint());
+}
+
+void parse_tensor(Cursor c, OnnxTensor& t) {
+  uint32_t f, w; uint64_t v; Cursor s{};
+  while (c.next(f, w, v, s)) {
+    switch (f) {
+      case 1: packed_varints(w, v, s, t.dims); break;
+      case 2: t.dtype = (int32_t)v; break;
+      case 4:
+        if (w == 2) { size_t n = (size_t)(s.end - s.p) / 4; size_t o = t.float_data.size(); t.float_data.resize(o + n); memcpy(t.float_data.data() + o, s.p, n * 4); }
+        else { float x; uint32_t u = (uint32_t)v; memcpy(&x, &u, 4); t.float_data.push_back(x); }
+        break;
+      case 7: packed_varints(w, v, s, t.int64_data); break;
+      case 8: t.name = str(s); break;
+      case 9: t.raw = s.p; t.raw_size = (size_t)(s.end - s.p); break;
+      case 14: if (v != 0) throw std::runtime_error("onnx: external tensor data is not supported"); break;
+      default: break;
+    }
+  }
+}
+
+void parse_attr(Cursor c, OnnxAttr& a) {
+  uint32_t f, w; uint64_t v; Cursor s{};
+  while (c.next(f, w, v, s)) {
+    switch (f) {
+      case 1: a.name = str(s); break;
+      case 2: { uint32_t u = (uint32_t)v; memcpy(&a.f, &u, 4); break; }
+      case 3: a.i = (int64_t)v; break;
+      case 4: a.s = str(s); break;
+      case 5: a.has_t = true; parse_tensor(s, a.t); break;
+      case 8: packed_varints(w, v, s, a.ints); break;
+      default: break;
+    }
+  }
+}
+
+void parse_node(Cursor c, OnnxNode& n) {
+  uint32_t f, w; uint64_t v; Cursor s{};
+  while (c.next(f, w, v, s)) {
+    switch (f) {
+      case 1: n.in.push_back(str(s)); break;
+      case 2: n.out.push_back(str(s)); break;
+      case 3: n.name = str(s); break;
+      case 4: n.op = str(s); break;
+      case 5: n.attrs.emplace_back(); parse_attr(s, n.attrs.back()); break;
+      default: break;
+    }
+  }
+}
+
+void parse_value_info(Cursor c, OnnxValueInfo& vi) {
+  uint32_t f, w; uint64_t v; Cursor s{};
+  while (c.next(f, w, v, s)) {
+    if (f == 1) vi.name = str(s);
+    else if (f == 2 && w == 2) {           // TypeProto
+      Cursor ty = s; Cursor s2{};
+      while (ty.next(f, w, v, s2)) {
+        if (f != 1 || w != 2) continue;    // tensor_type
+        Cursor tt = s2; Cursor s3{};
+        while (tt.next(f, w, v, s3)) {
+          if (f == 1) vi.elem_type = (int32_t)v;
+          else if (f == 2 && w == 2) {     // TensorShapeProto
+            vi.has_shape = true;
+            Cursor sh = s3; Cursor s4{};
+            while (sh.next(f, w, v, s4)) {
+              if (f != 1 || w != 2) continue;   // Dimension
+              int64_t dim = -1;
+              Cursor d = s4; Cursor s5{};
+              while (d.next(f, w, v, s5)) if (f == 1 && w == 0) dim = (int64_t)v;
+              vi.dims.push_back(dim);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+void parse_graph(Cursor c, OnnxGraph& g) {
+  uint32_t f, w; uint64_t v; Cursor s{};
+  while (c.next(f, w, v, s)) {
+    switch (f) {
+      case 1: g.nodes.emplace_back(); parse_node(s, g.nodes.back()); break;
+      case 5: { OnnxTensor t; parse_tensor(s, t); g.inits[t.name] = std::move(t); break; }
+      case 11: g.inputs.emplace_back(); parse_value_info(s, g.inputs.back()); break;
+      case 12: g.outputs.emplace_back(); parse_value_info(s, g.outputs.back()); break;
+      default: break;
+    }
+  }
+}
+
+const char* dtype_name(int32_t t) {
+  // Debug print of onnxruntime::TensorElementDataType, as shown by ModelInfo.input0_dtype
+  switch (t) {
+    case 1: return "Float"; case 2: return "Uint8"; case 3: return "Int8"; case 4: return "Uint16";
+    case 5: return "Int16"; case 6: return "Int32"; case 7: return "Int64"; case 8: return "String";
+    case 10: return "Float16"; case 11: return "Double"; case 12: return "Uint32"; case 13: return "Uint64";
+    default: return "Undefined";
+  }
+}
+
+std::vector<float> tensor_f32(const OnnxTensor& t, const std::string& what) {
+  if (t.dtype != 1) throw ModelError(INFUR_E_MODEL_LOAD, what + ": initializer '" + t.name + "' is not FLOAT (quantised models are not supported)");
+  size_t n = t.numel();
+  std::vector<float> v(n);
+  if (t.raw && t.raw_size == n * 4) memcpy(v.data(), t.raw, n * 4);
+  else if (t.float_data.size() == n) v = t.float_data;
+  else throw ModelError(INFUR_E_MODEL_LOAD, what + ": initializer '" + t.name + "' has inconsistent data size");
+  return v;
+}
+
+int64_t attr_i(const OnnxNode& n, const char* name, int64_t dflt) {
+  auto* a = n.attr(name);
+  return a ? a->i : dflt;
+}
+
+std::vector<int64_t> attr_ints(const OnnxNode& n, const char* name, std::vector<int64_t> dflt) {
+  auto* a = n.attr(name);
+  return (a && !a->ints.empty()) ? a->ints : dflt;
+}
+
+bool all_eq(const std::vector<int64_t>& v, int64_t x) {
+  for (auto e : v) if (e != x) return false;
+  return true;
+}
+
+}  // namespace
+
+void read_file(const std::string& path, std::vector<uint8_t>& bytes) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw std::runtime_error("cannot open '" + path + "'");
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  if (n < 0) { fclose(f); throw std::runtime_error("cannot stat '" + path + "'"); }
+  bytes.resize((size_t)n);
+  size_t got = n ? fread(bytes.data(), 1, (size_t)n, f) : 0;
+  fclose(f);
+  if (got != (size_t)n) throw std::runtime_error("short read on '" + path + "'");
+}
+
+void parse_onnx(std::vector<uint8_t>&& bytes, OnnxGraph& g) {
+  g = OnnxGraph();
+  g.file = std::move(bytes);
+  Cursor c{g.file.data(), g.file.data() + g.file.size()};
+  uint32_t f, w; uint64_t v; Cursor s{};
+  bool has_graph = false;
+  while (c.next(f, w, v, s)) {
+    switch (f) {
+      case 1: g.ir_version = (int64_t)v; break;
+      case 2: if (w == 2) g.producer = str(s); break;
+      case 7: if (w == 2) { parse_graph(s, g); has_graph = true; } break;
+      case 8: {
+        if (w != 2) break;
+        Cursor o = s; Cursor s2{}; std::string domain; int64_t ver = 0;
+        while (o.next(f, w, v, s2)) { if (f == 1) domain = str(s2); else if (f == 2) ver = (int64_t)v; }
+        if (domain.empty() || domain == "ai.onnx") g.opset = ver;
+        break;
+      }
+      default: break;
+    }
+  }
+  if (!has_graph || g.nodes.empty()) throw std::runtime_error("onnx: no graph in file (not an ONNX model?)");
+}
+
+// ---------------------------------------------------------------------------------------------
+
+void lower_model(const OnnxGraph& g, LoweredModel& m) {
+  m = LoweredModel();
+  // ---- inputs / outputs as ORT reports them: graph inputs minus initializers
+  std::vector<const OnnxValueInfo*> real_inputs;
+  for (auto& vi : g.inputs) if (!g.inits.count(vi.name)) real_inputs.push_back(&vi);
+  if (real_inputs.empty()) throw ModelError(INFUR_E_MODEL_LOAD, "model has no inputs");
+  for (auto* vi : real_inputs) m.io.input_names.push_back(vi->name);
+  for (auto& vi : g.outputs) m.io.output_names.push_back(vi.name);
+  const OnnxValueInfo& in0 = *real_inputs[0];
+  m.io.input0_dtype = dtype_name(in0.elem_type);
+
+  // infer_img_pre_proc (predict_onnx.rs:223-265), same checks in the same order
+  int col_dim = -1;
+  for (size_t i = 0; i < in0.dims.size(); ++i) if (in0.dims[i] == 3) { col_dim = (int)i; break; }
+  if (col_dim < 0) throw ModelError(INFUR_E_MODEL_INPUT_FORMAT, "couldn't locate model's color input by dimension length 3");
+  if (in0.dims.size() != 4)
+    throw ModelError(INFUR_E_MODEL_INPUT_FORMAT, "only 4 dimensions supported got " + std::to_string(in0.dims.size()));
+  if (col_dim == 1) m.io.nchw = true;
+  else if (col_dim == 3) m.io.nchw = false;
+  else throw ModelError(INFUR_E_MODEL_INPUT_FORMAT, "color dimension only at NCHW or NHWC but not in position " + std::to_string(col_dim) + " supported");
+  if (in0.elem_type == 1) m.io.float_input = true;
+  else if (in0.elem_type == 2) m.io.float_input = false;
+  else throw ModelError(INFUR_E_MODEL_INPUT_FORMAT, std::string("only Float (f32) and Uint8 (u8) input supported, got ") + dtype_name(in0.elem_type));
+  m.io.rgb = m.io.float_input;  // Model::control (:296-301): Float -> RGB + torchvision norm, else BGR
+  if (!m.io.nchw || !m.io.float_input)
+    throw ModelError(INFUR_E_MODEL_LOAD, "only NCHW Float32 image models run on the GPU path so far (NHWC / Uint8 inputs: see DESIGN.md 'next')");
+
+  // ---- pass 1: aliases, compute-node list, consumer counts
+  static const std::set<std::string> shape_ops = {"Shape", "Gather", "Unsqueeze", "Concat", "Slice", "Cast", "Constant", "Squeeze", "Floor", "Mul", "Div"};
+  std::map<std::string, std::string> alias;
+  auto resolve = [&](const std::string& n) {
+    std::string r = n;
+    for (int guard = 0; guard < 64; ++guard) { auto it = alias.find(r); if (it == alias.end()) break; r = it->second; }
+    return r;
+  };
+  std::vector<const OnnxNode*> compute;
+  std::set<std::string> shape_values;  // outputs of the size-computing subgraph
+  for (auto& n : g.nodes) {
+    if (n.op == "Identity") { if (n.in.size() == 1 && n.out.size() == 1) alias[n.out[0]] = n.in[0]; continue; }
+    if (n.op == "Conv" || n.op == "Relu" || n.op == "Add" || n.op == "MaxPool" || n.op == "Resize") { compute.push_back(&n); continue; }
+    if (shape_ops.count(n.op)) {
+      // only allowed when it does not touch an activation except through Shape
+      for (auto& o : n.out) shape_values.insert(o);
+      continue;
+    }
+    throw ModelError(INFUR_E_MODEL_LOAD, "unsupported operator '" + n.op + "' (node '" + n.name + "'); supported: Conv, Relu, Add, MaxPool, Resize"
+                     + (n.op.find("Linear") != std::string::npos || n.op[0] == 'Q' ? " -- quantised (QLinear/QDQ) models are not supported" : ""));
+  }
+  std::map<std::string, int> consumers;
+  std::map<std::string, const OnnxNode*> single_consumer;
+  for (auto* n : compute) {
+    size_t n_data = (n->op == "Conv" || n->op == "Resize") ? 1 : n->in.size();
+    for (size_t i = 0; i < n_data && i < n->in.size(); ++i) {
+      std::string r = resolve(n->in[i]);
+      consumers[r]++;
+      single_consumer[r] = n;
+    }
+  }
+  for (auto& vi : g.outputs) consumers[resolve(vi.name)] += 1000;  // graph outputs are never fused away
+  // a Shape node reading an activation is a consumer too, but a harmless one (sizes only)
+
+  // ---- pass 2: emit fused ops
+  std::map<std::string, int> tid;  // tensor name -> id
+  auto new_tensor = [&](const std::string& name, int channels) {
+    int id = m.num_tensors++;
+    tid[name] = id;
+    m.tensor_channels.push_back(channels);
+    return id;
+  };
+  m.input_tensor = new_tensor(in0.name, 3);
+  auto need = [&](const std::string& name, const OnnxNode& n) {
+    auto it = tid.find(resolve(name));
+    if (it == tid.end()) throw ModelError(INFUR_E_MODEL_LOAD, "node '" + n.name + "' (" + n.op + ") reads '" + name + "' which no supported node produces");
+    return it->second;
+  };
+  std::set<const OnnxNode*> fused;
+  struct Pending { LoweredOp op; std::string in_name; };
+  std::map<std::string, LoweredOp> pending;  // conv outputs waiting for their Add
+  auto emit = [&](LoweredOp&& op, const std::string& out_name) {
+    op.out = new_tensor(out_name, op.kind == OpKind::Conv ? op.conv.cout : m.tensor_channels[op.in]);
+    m.ops.push_back(std::move(op));
+  };
+  auto take_relu = [&](const std::string& out_name, std::string& final_name) -> bool {
+    if (consumers[out_name] == 1 && single_consumer[out_name]->op == "Relu") {
+      const OnnxNode* r = single_consumer[out_name];
+      fused.insert(r);
+      final_name = r->out[0];
+      return true;
+    }
+    final_name = out_name;
+    return false;
+  };
+
+  for (auto* np : compute) {
+    const OnnxNode& n = *np;
+    if (fused.count(np)) continue;
+    if (n.op == "Conv") {
+      if (n.in.size() < 2) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "' has no weight input");
+      auto wit = g.inits.find(resolve(n.in[1]));
+      if (wit == g.inits.end()) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': weight is not an initializer (quantised / dynamic weights are not supported)");
+      const OnnxTensor& wt = wit->second;
+      if (wt.dims.size() != 4) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': weight must be 4-D");
+      LoweredOp op; op.kind = OpKind::Conv; op.name = n.name.empty() ? n.out[0] : n.name;
+      ConvOp& c = op.conv;
+      c.cout = (int)wt.dims[0]; c.cin = (int)wt.dims[1]; c.kh = (int)wt.dims[2]; c.kw = (int)wt.dims[3];
+      if (attr_i(n, "group", 1) != 1) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': group != 1 is not supported");
+      auto strides = attr_ints(n, "strides", {1, 1}), dil = attr_ints(n, "dilations", {1, 1}), pads = attr_ints(n, "pads", {0, 0, 0, 0});
+      auto ks = attr_ints(n, "kernel_shape", {c.kh, c.kw});
+      if (ks.size() != 2 || ks[0] != c.kh || ks[1] != c.kw) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': kernel_shape does not match the weight");
+      if (auto* ap = n.attr("auto_pad")) if (!ap->s.empty() && ap->s != "NOTSET") throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': auto_pad is not supported");
+      if (strides.size() != 2 || strides[0] != strides[1] || dil.size() != 2 || dil[0] != dil[1] || pads.size() != 4 || !all_eq(pads, pads[0]) || c.kh != c.kw)
+        throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': only square kernels with symmetric stride/dilation/padding are supported");
+      c.stride = (int)strides[0]; c.dil = (int)dil[0]; c.pad = (int)pads[0];
+      std::vector<float> w = tensor_f32(wt, "Conv '" + n.name + "'");
+      c.weight.resize(w.size());
+      for (int o = 0; o < c.cout; ++o)
+        for (int i = 0; i < c.cin; ++i)
+          for (int y = 0; y < c.kh; ++y)
+            for (int x = 0; x < c.kw; ++x)
+              c.weight[(((size_t)o * c.kh + y) * c.kw + x) * c.cin + i] = w[(((size_t)o * c.cin + i) * c.kh + y) * c.kw + x];
+      if (n.in.size() >= 3 && !n.in[2].empty()) {
+        auto bit = g.inits.find(resolve(n.in[2]));
+        if (bit == g.inits.end()) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': bias is not an initializer");
+        c.bias = tensor_f32(bit->second, "Conv '" + n.name + "'");
+        if ((int)c.bias.size() != c.cout) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': bias length mismatch");
+      } else c.bias.assign(c.cout, 0.f);
+      op.in = need(n.in[0], n);
+      if (m.tensor_channels[op.in] != c.cin) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': input has " + std::to_string(m.tensor_channels[op.in]) + " channels, weight expects " + std::to_string(c.cin));
+      const std::string out_name = n.out[0];
+      if (consumers[out_name] == 1 && single_consumer[out_name]->op == "Add") { pending[out_name] = std::move(op); continue; }
+      std::string final_name;
+      op.conv.relu = take_relu(out_name, final_name);
+      emit(std::move(op), final_name);
+    } else if (n.op == "Add") {
+      if (n.in.size() != 2) throw ModelError(INFUR_E_MODEL_LOAD, "Add '" + n.name + "' must have two inputs");
+      std::string a = resolve(n.in[0]), b = resolve(n.in[1]);
+      std::string main_name, other;
+      if (pending.count(a)) { main_name = a; other = b; }
+      else if (pending.count(b)) { main_name = b; other = a; }
+      else throw ModelError(INFUR_E_MODEL_LOAD, "Add '" + n.name + "': neither input is a convolution output (stand-alone Add is not supported)");
+      if (pending.count(other)) {  // e.g. the downsample conv of a bottleneck: runs on its own first
+        LoweredOp o = std::move(pending[other]); pending.erase(other);
+        emit(std::move(o), other);
+      }
+      LoweredOp op = std::move(pending[main_name]); pending.erase(main_name);
+      op.conv.residual = need(other, n);
+      if (m.tensor_channels[op.conv.residual] != op.conv.cout) throw ModelError(INFUR_E_MODEL_LOAD, "Add '" + n.name + "': channel mismatch");
+      std::string final_name;
+      op.conv.relu = take_relu(n.out[0], final_name);
+      emit(std::move(op), final_name);
+    } else if (n.op == "Relu") {
+      throw ModelError(INFUR_E_MODEL_LOAD, "Relu '" + n.name + "' does not follow a Conv or Conv+Add (stand-alone Relu is not supported)");
+    } else if (n.op == "MaxPool") {
+      auto ks = attr_ints(n, "kernel_shape", {}), st = attr_ints(n, "strides", {1, 1}), pads = attr_ints(n, "pads", {0, 0, 0, 0}), dl = attr_ints(n, "dilations", {1, 1});
+      if (ks.size() != 2 || ks[0] != ks[1] || st.size() != 2 || st[0] != st[1] || pads.size() != 4 || !all_eq(pads, pads[0]) || attr_i(n, "ceil_mode", 0) != 0 || !all_eq(dl, 1))
+        throw ModelError(INFUR_E_MODEL_LOAD, "MaxPool '" + n.name + "': only square, symmetric, floor-mode pooling is supported");
+      LoweredOp op; op.kind = OpKind::MaxPool; op.name = n.name.empty() ? n.out[0] : n.name;
+      op.pool_k = (int)ks[0]; op.pool_s = (int)st[0]; op.pool_p = (int)pads[0];
+      op.in = need(n.in[0], n);
+      emit(std::move(op), n.out[0]);
+    } else if (n.op == "Resize") {
+      std::string mode = n.attr("mode") ? n.attr("mode")->s : "nearest";
+      std::string ctm = n.attr("coordinate_transformation_mode") ? n.attr("coordinate_transformation_mode")->s : "half_pixel";
+      if (mode != "linear" || (ctm != "half_pixel" && ctm != "pytorch_half_pixel"))
+        throw ModelError(INFUR_E_MODEL_LOAD, "Resize '" + n.name + "': only mode=linear with half_pixel / pytorch_half_pixel is supported (got " + mode + ", " + ctm + ")");
+      // the target size must come from the size-computing subgraph (Shape of the network input), i.e.
+      // "resize to the input's H x W" -- the only form FCN uses.
+      bool sized = n.in.size() >= 4 && shape_values.count(n.in[3]);
+      if (!sized) throw ModelError(INFUR_E_MODEL_LOAD, "Resize '" + n.name + "': expected a computed `sizes` input (resize to the network input size)");
+      bool is_output = false;
+      for (auto& vi : g.outputs) if (vi.name == n.out[0]) is_output = true;
+      if (!is_output) throw ModelError(INFUR_E_MODEL_LOAD, "Resize '" + n.name + "': only supported as the last node of an output head");
+      LoweredHead hd; hd.name = n.out[0]; hd.tensor = need(n.in[0], n); hd.num_classes = m.tensor_channels[hd.tensor];
+      m.heads.push_back(hd);
+    }
+  }
+  if (!pending.empty()) throw ModelError(INFUR_E_MODEL_LOAD, "internal: convolution output left without its Add");
+  if (m.heads.empty()) throw ModelError(INFUR_E_MODEL_LOAD, "model has no `Resize` output head (not an FCN-style segmentation model)");
+  // heads in graph-output order
+  std::vector<LoweredHead> ordered;
+  for (auto& vi : g.outputs) for (auto& h : m.heads) if (h.name == vi.name) ordered.push_back(h);
+  m.heads = ordered;
+}
+
+std::string describe(const LoweredModel& m) {
+  std::ostringstream os;
+  os << "inputs:";
+  for (auto& s : m.io.input_names) os << " " << s;
+  os << " dtype=" << m.io.input0_dtype << " layout=" << (m.io.nchw ? "NCHW" : "NHWC") << " color=" << (m.io.rgb ? "RGB" : "BGR") << "\n";
+  os << "outputs:";
+  for (auto& s : m.io.output_names) os << " " << s;
+  os << "\n";
+  for (size_t i = 0; i < m.ops.size(); ++i) {
+    const LoweredOp& o = m.ops[i];
+    if (o.kind == OpKind::Conv) {
+      const ConvOp& c = o.conv;
+      os << i << " conv t" << o.in << "->t" << o.out << " " << c.cin << "->" << c.cout << " k" << c.kh << " s" << c.stride << " p" << c.pad << " d" << c.dil
+         << (c.residual >= 0 ? " +t" + std::to_string(c.residual) : std::string()) << (c.relu ? " relu" : "") << "\n";
+    } else {
+      os << i << " maxpool t" << o.in << "->t" << o.out << " k" << o.pool_k << " s" << o.pool_s << " p" << o.pool_p << "\n";
+    }
+  }
+  for (auto& h : m.heads) os << "head " << h.name << " t" << h.tensor << " classes=" << h.num_classes << "\n";
+  return os.str();
+}
+
+}  // namespace infur
