@@ -94,9 +94,16 @@ int32_t infur_b200_model_load_bytes(infur_b200_handle* h, const void* onnx, size
  * (get_info() == None), INFUR_E_BUFFER_TOO_SMALL (with *required set) when cap is too small. */
 int32_t infur_b200_model_info(const infur_b200_handle* h, char* buf, size_t cap, size_t* required);
 
-/* Weight arena in device memory (packed fp16 weights + f32 biases), for an NCCL broadcast from the
- * rank that parsed the file; *dptr is a CUDA device pointer. */
-int32_t infur_b200_model_weights(const infur_b200_handle* h, void** dptr, size_t* bytes);
+/* Multi-GPU initialisation ("NCCL broadcast of weights at init only"): every rank parses the file for
+ * the graph structure, but only the root packs and uploads weights; the others pass
+ * INFUR_LOAD_SKIP_WEIGHTS (arena allocated, zero-filled), then receive the root's packed arena through
+ * model_weights_export -> ncclBroadcast (torch.distributed) -> model_weights_import.  Both copy
+ * device-to-device between the library's arena and a caller-owned DEVICE buffer of *bytes. */
+enum { INFUR_LOAD_DEFAULT = 0, INFUR_LOAD_SKIP_WEIGHTS = 1 };
+int32_t infur_b200_model_load_opts(infur_b200_handle* h, const char* utf8_path, int32_t flags);
+int32_t infur_b200_model_weights_size(const infur_b200_handle* h, size_t* bytes);
+int32_t infur_b200_model_weights_export(infur_b200_handle* h, void* d_dst, size_t bytes);
+int32_t infur_b200_model_weights_import(infur_b200_handle* h, const void* d_src, size_t bytes);
 
 /* Scale::is_dirty (processing.rs:228-230); Model and ColorCode are never dirty
  * (predict_onnx.rs:336-338, decode_predict.rs:81-83). */
@@ -126,7 +133,8 @@ typedef struct infur_b200_out {
  * Synchronous.  `bgr` is a caller-owned tight HWC B,G,R u8 image of w*h*3 bytes
  * (image-ext/src/image_bgr.rs:7-11), only read during the call.  Clears the dirty flag
  * (processing.rs:233).  Errors: INFUR_E_ZERO_SIZE_IN / _OUT, INFUR_E_BUFFER_TOO_SMALL (required[]
- * filled, nothing written), INFUR_E_RUNTIME. */
+ * filled, nothing written), INFUR_E_RUNTIME.  A call with every buffer pointer NULL is a size query:
+ * it fills out_w / out_h / num_classes / has_decoded / required[] and runs nothing. */
 int32_t infur_b200_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, uint64_t id,
                            infur_b200_out* out);
 
@@ -172,9 +180,18 @@ uint64_t infur_b200_launch_count(const infur_b200_handle* h);
 
 /* ---- single-stage entry points (each Processor on its own; used by the parity tests) ------- */
 
-/* Scale::advance alone (processing.rs:232-281) with the handle's current factor: host in, host out. */
+/* Scale::advance alone (processing.rs:232-281) with the handle's current factor: host in, host out.
+ * All pointers NULL == advance(&None, ..): clears the dirty flag and returns OK (:233-237). */
 int32_t infur_b200_scale_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt,
                                  uint8_t* out_bgr, size_t out_cap, uint32_t* out_w, uint32_t* out_h);
+
+/* Model::advance alone (predict_onnx.rs:317-334): the image is fed as is (no Scale), the outputs are the
+ * network's `out` (and, with cfg.compute_aux, `aux`) tensors with the batch dimension stripped,
+ * [K][hgt][w] f32 each -- the reference's Vec<ArrayD<f32>>.  Without a loaded model it returns OK with
+ * *has_model = 0 and leaves the buffers untouched (:321-323).  Does not touch the Scale state.
+ * Debug / parity path: it materialises full-resolution logits, which the fused path never does. */
+int32_t infur_b200_model_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* logits_f32, size_t logits_cap,
+                                 float* aux_logits_f32, size_t aux_cap, uint32_t* num_classes, int32_t* has_model);
 
 /* Pre-processing of ImageSession::forward alone (predict_onnx.rs:103-137): [h][w][3] u8 BGR ->
  * [3][h][w] f32 RGB-normalised. */

@@ -1,0 +1,662 @@
+// extern "C" surface of libinfur_b200.so -- see include/infur_b200.h for the contract of each entry point
+// and the reference item it mirrors.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "engine.h"
+#include "tables.h"
+
+namespace infur {
+Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool skip_weights, std::unique_ptr<DeviceModel>& out);
+Status get_plan(infur_b200_handle* H, int n, int w, int h, Plan** out);
+Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const OutPtrs& o, cudaStream_t s, float* op_ms, cudaEvent_t* evs);
+Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* d, const uint16_t* x, const uint16_t* wgt, const float* bias,
+                      const uint16_t* residual, uint16_t* y, float* y_f32, float* elapsed_ms);
+}  // namespace infur
+
+using namespace infur;
+
+static thread_local std::string g_create_error;
+
+static int32_t fail(infur_b200_handle* h, int code, const std::string& msg) {
+  if (h) h->last_error = msg; else g_create_error = msg;
+  return code;
+}
+static int32_t fail(infur_b200_handle* h, const Status& st) { return fail(h, st.code, st.msg); }
+
+#define API_CU(h, expr)                                                                                      \
+  do {                                                                                                       \
+    cudaError_t e__ = (expr);                                                                                \
+    if (e__ != cudaSuccess) return fail(h, INFUR_E_RUNTIME, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" {
+
+void infur_b200_default_config(infur_b200_config* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = sizeof(*cfg);
+  cfg->device = 0; cfg->max_batch = 8; cfg->ring_depth = 3; cfg->resize_mode = INFUR_RESIZE_NEAREST;
+  cfg->compute_aux = 0; cfg->blend = 0; cfg->conv_impl = INFUR_CONV_TCGEN05; cfg->use_cuda_graph = 0;
+}
+
+int32_t infur_b200_abi_version(void) { return INFUR_B200_ABI_VERSION; }
+
+int32_t infur_b200_create(const infur_b200_config* cfg, infur_b200_handle** out) {
+  if (!out) return fail(nullptr, INFUR_E_INVALID_ARG, "create: out is NULL");
+  *out = nullptr;
+  infur_b200_config c;
+  infur_b200_default_config(&c);
+  if (cfg) {
+    if (cfg->struct_size != sizeof(infur_b200_config)) return fail(nullptr, INFUR_E_INVALID_ARG, "create: config struct_size mismatch");
+    c = *cfg;
+  }
+  if (c.resize_mode != INFUR_RESIZE_NEAREST) return fail(nullptr, INFUR_E_UNSUPPORTED, "create: only INFUR_RESIZE_NEAREST (the reference's mode) is implemented");
+  if (c.conv_impl != INFUR_CONV_TCGEN05 && c.conv_impl != INFUR_CONV_VALIDATE) return fail(nullptr, INFUR_E_INVALID_ARG, "create: unknown conv_impl");
+  if (c.max_batch < 1 || c.max_batch > 64 || c.ring_depth < 1 || c.ring_depth > 16) return fail(nullptr, INFUR_E_INVALID_ARG, "create: max_batch must be 1..64, ring_depth 1..16");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(nullptr, INFUR_E_NO_DEVICE, "no CUDA device: this library has no CPU fallback"); }
+  if (c.device < 0 || c.device >= ndev) return fail(nullptr, INFUR_E_NO_DEVICE, "create: device ordinal out of range");
+  API_CU(nullptr, cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  API_CU(nullptr, cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10) return fail(nullptr, INFUR_E_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200); this library is built for sm_100a only");
+  auto* h = new infur_b200_handle();
+  h->cfg = c;
+  h->num_sms = prop.multiProcessorCount;
+  auto bail = [&](const std::string& m) { std::string mm = m; infur_b200_destroy(h); return fail(nullptr, INFUR_E_RUNTIME, mm); };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking) != cudaSuccess)
+    return bail("cudaStreamCreate failed");
+  float lut_f[768];
+  build_norm_lut(lut_f);
+  __half lut_h[768];
+  for (int i = 0; i < 768; ++i) lut_h[i] = __float2half_rn(lut_f[i]);
+  h->color_lut.resize(20 * 256 * 4);
+  build_color_lut(h->color_lut.data());
+  if (cudaMalloc(&h->d_lut_f, sizeof(lut_f)) != cudaSuccess || cudaMalloc(&h->d_lut_h, sizeof(lut_h)) != cudaSuccess ||
+      cudaMalloc(&h->d_color_lut, h->color_lut.size()) != cudaSuccess)
+    return bail("cudaMalloc of lookup tables failed");
+  cudaMemcpy(h->d_lut_f, lut_f, sizeof(lut_f), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_lut_h, lut_h, sizeof(lut_h), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_color_lut, h->color_lut.data(), h->color_lut.size(), cudaMemcpyHostToDevice);
+  cudaError_t e = conv_tc_init();
+  if (e != cudaSuccess) return bail(std::string("conv_tc_init: ") + cudaGetErrorString(e));
+  h->ring.resize((size_t)c.ring_depth);
+  *out = h;
+  return INFUR_OK;
+}
+
+static void free_slot(RingSlot& s) {
+  if (s.h_in) cudaFreeHost(s.h_in);
+  if (s.h_class) cudaFreeHost(s.h_class);
+  if (s.h_decoded) cudaFreeHost(s.h_decoded);
+  if (s.h_blended) cudaFreeHost(s.h_blended);
+  if (s.d_in) cudaFree(s.d_in);
+  if (s.d_class) cudaFree(s.d_class);
+  if (s.d_decoded) cudaFree(s.d_decoded);
+  if (s.d_blended) cudaFree(s.d_blended);
+  if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+  if (s.ev_done) cudaEventDestroy(s.ev_done);
+  if (s.ev_out) cudaEventDestroy(s.ev_out);
+  s = RingSlot();
+}
+
+void infur_b200_destroy(infur_b200_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& s : h->ring) free_slot(s);
+  h->plans.clear();
+  h->model.reset();
+  if (h->d_lut_f) cudaFree(h->d_lut_f);
+  if (h->d_lut_h) cudaFree(h->d_lut_h);
+  if (h->d_color_lut) cudaFree(h->d_color_lut);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->h2d) cudaStreamDestroy(h->h2d);
+  if (h->d2h) cudaStreamDestroy(h->d2h);
+  delete h;
+}
+
+const char* infur_b200_last_error(const infur_b200_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+int32_t infur_b200_scale_control(infur_b200_handle* h, float factor) {
+  if (!h) return INFUR_E_INVALID_ARG;
+  if (factor <= 0.0f) return fail(h, INFUR_E_SCALE_NONPOSITIVE, "Cannot scale by negative number");
+  h->dirty = factor != h->factor;   // NaN != anything: dirty, as in the reference
+  h->factor = factor;
+  return INFUR_OK;
+}
+
+int32_t infur_b200_is_dirty(const infur_b200_handle* h) { return h && h->dirty ? 1 : 0; }
+
+static int32_t load_from_bytes(infur_b200_handle* h, std::vector<uint8_t>&& bytes, int32_t flags) {
+  cudaSetDevice(h->cfg.device);
+  std::unique_ptr<DeviceModel> dm;
+  try {
+    OnnxGraph g;
+    parse_onnx(std::move(bytes), g);
+    LoweredModel lm;
+    lower_model(g, lm);
+    Status st = build_device_model(std::move(lm), h->cfg, (flags & INFUR_LOAD_SKIP_WEIGHTS) != 0, dm);
+    if (!st.ok()) return fail(h, st);
+  } catch (const ModelError& e) {
+    return fail(h, e.code, e.msg);
+  } catch (const std::exception& e) {
+    return fail(h, INFUR_E_MODEL_LOAD, std::string("Failed to load model: ") + e.what());
+  }
+  cudaStreamSynchronize(h->stream);
+  h->plans.clear();
+  h->model = std::move(dm);   // only now: a failed load keeps the previous model (predict_onnx.rs:289-308)
+  h->model_gen++;
+  return INFUR_OK;
+}
+
+int32_t infur_b200_model_load_opts(infur_b200_handle* h, const char* utf8_path, int32_t flags) {
+  if (!h || !utf8_path) return fail(h, INFUR_E_INVALID_ARG, "model_load: NULL argument");
+  if (utf8_path[0] == '\0') {   // ModelCmd::Load("") unloads (predict_onnx.rs:310-312)
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    h->plans.clear();
+    h->model.reset();
+    h->model_gen++;
+    return INFUR_OK;
+  }
+  std::vector<uint8_t> bytes;
+  try { read_file(utf8_path, bytes); }
+  catch (const std::exception& e) { return fail(h, INFUR_E_MODEL_LOAD, std::string("Failed to load model: ") + e.what()); }
+  return load_from_bytes(h, std::move(bytes), flags);
+}
+
+int32_t infur_b200_model_load(infur_b200_handle* h, const char* utf8_path) { return infur_b200_model_load_opts(h, utf8_path, INFUR_LOAD_DEFAULT); }
+
+int32_t infur_b200_model_load_bytes(infur_b200_handle* h, const void* onnx, size_t size) {
+  if (!h || (!onnx && size)) return fail(h, INFUR_E_INVALID_ARG, "model_load_bytes: NULL argument");
+  std::vector<uint8_t> bytes((const uint8_t*)onnx, (const uint8_t*)onnx + size);
+  return load_from_bytes(h, std::move(bytes), INFUR_LOAD_DEFAULT);
+}
+
+int32_t infur_b200_model_info(const infur_b200_handle* h, char* buf, size_t cap, size_t* required) {
+  if (!h) return INFUR_E_INVALID_ARG;
+  if (!h->model) return INFUR_E_INVALID_ARG;
+  const ModelIO& io = h->model->lm.io;
+  std::string s = (io.input_names.empty() ? std::string() : io.input_names[0]) + "\t" + io.input0_dtype + "\t";
+  for (size_t i = 0; i < io.output_names.size(); ++i) s += (i ? "," : "") + io.output_names[i];
+  if (required) *required = s.size() + 1;
+  if (!buf || cap < s.size() + 1) return INFUR_E_BUFFER_TOO_SMALL;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return INFUR_OK;
+}
+
+int32_t infur_b200_model_weights_size(const infur_b200_handle* h, size_t* bytes) {
+  if (!h || !bytes || !h->model) return INFUR_E_INVALID_ARG;
+  *bytes = h->model->arena_bytes;
+  return INFUR_OK;
+}
+int32_t infur_b200_model_weights_export(infur_b200_handle* h, void* d_dst, size_t bytes) {
+  if (!h || !d_dst || !h->model || bytes != h->model->arena_bytes) return fail(h, INFUR_E_INVALID_ARG, "weights_export: no model or size mismatch");
+  cudaSetDevice(h->cfg.device);
+  API_CU(h, cudaMemcpy(d_dst, h->model->arena, bytes, cudaMemcpyDeviceToDevice));
+  return INFUR_OK;
+}
+int32_t infur_b200_model_weights_import(infur_b200_handle* h, const void* d_src, size_t bytes) {
+  if (!h || !d_src || !h->model || bytes != h->model->arena_bytes) return fail(h, INFUR_E_INVALID_ARG, "weights_import: no model or size mismatch");
+  cudaSetDevice(h->cfg.device);
+  API_CU(h, cudaStreamSynchronize(h->stream));
+  API_CU(h, cudaMemcpy(h->model->arena, d_src, bytes, cudaMemcpyDeviceToDevice));
+  return INFUR_OK;
+}
+
+// ---- advance -----------------------------------------------------------------------------------
+
+static void fill_required(const Plan& p, int k, size_t req[7]) {
+  const size_t px = (size_t)p.ow * p.oh;
+  req[0] = px * 3; req[1] = px * 4; req[2] = px; req[3] = px * 4; req[4] = px * 4; req[5] = px * 4 * (size_t)k; req[6] = req[5];
+}
+
+int32_t infur_b200_advance_batch(infur_b200_handle* h, const uint8_t* bgr, uint32_t n, uint32_t w, uint32_t hgt, const uint64_t* ids,
+                                 infur_b200_out* outs) {
+  if (!h || !outs || n == 0) return fail(h, INFUR_E_INVALID_ARG, "advance: NULL argument or empty batch");
+  for (uint32_t i = 0; i < n; ++i)
+    if (outs[i].struct_size != sizeof(infur_b200_out)) return fail(h, INFUR_E_INVALID_ARG, "advance: out struct_size mismatch");
+  if (!bgr && (size_t)w * hgt != 0) return fail(h, INFUR_E_INVALID_ARG, "advance: bgr is NULL");
+  if ((int)n > h->cfg.max_batch) return fail(h, INFUR_E_INVALID_ARG, "advance: batch larger than max_batch");
+  cudaSetDevice(h->cfg.device);
+  h->dirty = false;   // Scale::advance clears dirty first (processing.rs:233)
+  Plan* pp = nullptr;
+  Status st = get_plan(h, (int)n, (int)w, (int)hgt, &pp);
+  if (!st.ok()) return fail(h, st);
+  Plan& p = *pp;
+  const int k = p.has_model ? p.k : 0;
+  size_t req[7];
+  fill_required(p, k, req);
+  bool too_small = false, want_logits = false, want_aux = false, any_buffer = false;
+  for (uint32_t i = 0; i < n; ++i) {
+    infur_b200_out& o = outs[i];
+    any_buffer |= o.scaled_bgr || o.frame_rgba || o.class_map || o.decoded_rgba || o.blended_rgba || o.logits_f32 || o.aux_logits_f32;
+    o.out_w = (uint32_t)p.ow; o.out_h = (uint32_t)p.oh; o.num_classes = (uint32_t)k; o.has_decoded = p.has_model ? 1 : 0;
+    o.id = ids ? ids[i] : 0;
+    memcpy(o.required, req, sizeof(req));
+    if (!p.has_model) { o.required[2] = o.required[3] = o.required[4] = o.required[5] = o.required[6] = 0; }
+    if (o.scaled_bgr && o.scaled_bgr_cap < req[0]) too_small = true;
+    if (o.frame_rgba && o.frame_rgba_cap < req[1]) too_small = true;
+    if (p.has_model) {
+      if (o.class_map && o.class_map_cap < req[2]) too_small = true;
+      if (o.decoded_rgba && o.decoded_rgba_cap < req[3]) too_small = true;
+      if (o.blended_rgba && o.blended_rgba_cap < req[4]) too_small = true;
+      if (o.logits_f32 && o.logits_cap < req[5]) too_small = true;
+      if (o.aux_logits_f32 && o.aux_logits_cap < req[6]) too_small = true;
+      if (o.blended_rgba && !h->cfg.blend) return fail(h, INFUR_E_INVALID_ARG, "advance: blended_rgba requested but cfg.blend == 0");
+      if (o.aux_logits_f32 && !(h->cfg.compute_aux && p.aux_lowres)) return fail(h, INFUR_E_INVALID_ARG, "advance: aux logits requested but cfg.compute_aux == 0 or the model has no aux head");
+      want_logits |= o.logits_f32 != nullptr;
+      want_aux |= o.aux_logits_f32 != nullptr;
+    }
+  }
+  if (too_small) return fail(h, INFUR_E_BUFFER_TOO_SMALL, "advance: an output buffer is too small (see required[])");
+  const size_t frame_bytes = (size_t)w * hgt * 3, px = (size_t)p.ow * p.oh;
+  if (px == 0 || !any_buffer) return INFUR_OK;   // no buffer at all = size query: out_w/out_h/num_classes/required[] only
+  API_CU(h, cudaMemcpyAsync(p.d_in, bgr, frame_bytes * n, cudaMemcpyHostToDevice, h->stream));
+  float *d_logits = nullptr, *d_aux = nullptr;
+  if (want_logits) API_CU(h, cudaMalloc(&d_logits, px * n * k * 4));
+  if (want_aux) API_CU(h, cudaMalloc(&d_aux, px * n * k * 4));
+  OutPtrs o;
+  o.class_map = p.d_class; o.decoded = p.d_decoded; o.blended = p.d_blended; o.frame_rgba = p.d_frame_rgba; o.logits = d_logits; o.aux_logits = d_aux;
+  st = run_forward(h, p, p.d_in, o, h->stream, nullptr, nullptr);
+  if (st.ok()) {
+    const uint8_t* scaled = p.factor == 1.0f ? p.d_in : p.scaled;
+    for (uint32_t i = 0; i < n && st.ok(); ++i) {
+      infur_b200_out& u = outs[i];
+      auto d2h = [&](void* dst, const void* src, size_t bytes) {
+        if (dst && st.ok()) { cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream); if (e != cudaSuccess) st = Status::error(INFUR_E_RUNTIME, cudaGetErrorString(e)); }
+      };
+      d2h(u.scaled_bgr, scaled + i * px * 3, px * 3);
+      d2h(u.frame_rgba, p.d_frame_rgba + i * px, px * 4);
+      if (p.has_model) {
+        d2h(u.class_map, p.d_class + i * px, px);
+        d2h(u.decoded_rgba, p.d_decoded + i * px, px * 4);
+        if (p.d_blended) d2h(u.blended_rgba, p.d_blended + i * px, px * 4);
+        if (d_logits) d2h(u.logits_f32, d_logits + i * px * k, px * 4 * k);
+        if (d_aux) d2h(u.aux_logits_f32, d_aux + i * px * k, px * 4 * k);
+      }
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (d_logits) cudaFree(d_logits);
+  if (d_aux) cudaFree(d_aux);
+  if (!st.ok()) return fail(h, st);
+  if (e != cudaSuccess) return fail(h, INFUR_E_RUNTIME, std::string("advance: ") + cudaGetErrorString(e));
+  return INFUR_OK;
+}
+
+int32_t infur_b200_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, uint64_t id, infur_b200_out* out) {
+  return infur_b200_advance_batch(h, bgr, 1, w, hgt, &id, out);
+}
+
+int32_t infur_b200_advance_device(infur_b200_handle* h, const uint8_t* d_bgr, uint32_t n, uint32_t w, uint32_t hgt, uint8_t* d_class_map,
+                                  uint8_t* d_decoded_rgba, uint8_t* d_blended_rgba, uint32_t* out_w, uint32_t* out_h, int32_t sync) {
+  if (!h || !d_bgr || n == 0) return fail(h, INFUR_E_INVALID_ARG, "advance_device: NULL argument");
+  cudaSetDevice(h->cfg.device);
+  h->dirty = false;
+  Plan* pp = nullptr;
+  Status st = get_plan(h, (int)n, (int)w, (int)hgt, &pp);
+  if (!st.ok()) return fail(h, st);
+  if (out_w) *out_w = (uint32_t)pp->ow;
+  if (out_h) *out_h = (uint32_t)pp->oh;
+  if (d_blended_rgba && !h->cfg.blend) return fail(h, INFUR_E_INVALID_ARG, "advance_device: blended output requested but cfg.blend == 0");
+  OutPtrs o;
+  o.class_map = d_class_map; o.decoded = reinterpret_cast<uint32_t*>(d_decoded_rgba); o.blended = reinterpret_cast<uint32_t*>(d_blended_rgba);
+  st = run_forward(h, *pp, d_bgr, o, h->stream, nullptr, nullptr);
+  if (!st.ok()) return fail(h, st);
+  if (sync) API_CU(h, cudaStreamSynchronize(h->stream));
+  return INFUR_OK;
+}
+
+void* infur_b200_compute_stream(const infur_b200_handle* h) { return h ? (void*)h->stream : nullptr; }
+uint64_t infur_b200_launch_count(const infur_b200_handle* h) { return h ? h->launches : 0; }
+
+// ---- pinned ring -------------------------------------------------------------------------------
+
+int32_t infur_b200_ring_acquire(infur_b200_handle* h, uint32_t n, uint32_t w, uint32_t hgt, infur_b200_slot* slot) {
+  if (!h || !slot || n == 0 || (int)n > h->cfg.max_batch) return fail(h, INFUR_E_INVALID_ARG, "ring_acquire: bad argument");
+  cudaSetDevice(h->cfg.device);
+  RingSlot* s = nullptr;
+  for (auto& r : h->ring) if (r.state == 0) { s = &r; break; }
+  if (!s) return fail(h, INFUR_E_TICKET, "ring_acquire: all ring slots are in flight");
+  Plan* pp = nullptr;
+  Status st = get_plan(h, (int)n, (int)w, (int)hgt, &pp);
+  if (!st.ok()) return fail(h, st);
+  const size_t in_bytes = (size_t)n * w * hgt * 3, out_px = (size_t)n * pp->ow * pp->oh;
+  if (!s->ev_h2d) {
+    API_CU(h, cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
+    API_CU(h, cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
+    API_CU(h, cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
+  }
+  if (s->in_cap < in_bytes) {
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->d_in) cudaFree(s->d_in);
+    s->h_in = nullptr; s->d_in = nullptr; s->in_cap = 0;
+    API_CU(h, cudaHostAlloc(&s->h_in, std::max<size_t>(in_bytes, 16), cudaHostAllocDefault));
+    API_CU(h, cudaMalloc(&s->d_in, std::max<size_t>(in_bytes, 16)));
+    s->in_cap = in_bytes;
+  }
+  if (s->out_cap_px < out_px || (h->cfg.blend && !s->h_blended)) {
+    if (s->h_class) cudaFreeHost(s->h_class);
+    if (s->h_decoded) cudaFreeHost(s->h_decoded);
+    if (s->h_blended) cudaFreeHost(s->h_blended);
+    if (s->d_class) cudaFree(s->d_class);
+    if (s->d_decoded) cudaFree(s->d_decoded);
+    if (s->d_blended) cudaFree(s->d_blended);
+    s->h_class = s->h_decoded = s->h_blended = nullptr; s->d_class = nullptr; s->d_decoded = s->d_blended = nullptr; s->out_cap_px = 0;
+    const size_t px = std::max<size_t>(out_px, 16);
+    API_CU(h, cudaHostAlloc(&s->h_class, px, cudaHostAllocDefault));
+    API_CU(h, cudaHostAlloc(&s->h_decoded, px * 4, cudaHostAllocDefault));
+    API_CU(h, cudaMalloc(&s->d_class, px));
+    API_CU(h, cudaMalloc(&s->d_decoded, px * 4));
+    if (h->cfg.blend) { API_CU(h, cudaHostAlloc(&s->h_blended, px * 4, cudaHostAllocDefault)); API_CU(h, cudaMalloc(&s->d_blended, px * 4)); }
+    s->out_cap_px = out_px;
+  }
+  s->state = 1; s->ticket = h->next_ticket++; s->n = n; s->w = w; s->h = hgt; s->ow = (uint32_t)pp->ow; s->oh = (uint32_t)pp->oh;
+  memset(slot, 0, sizeof(*slot));
+  slot->ticket = s->ticket; slot->n = n; slot->w = w; slot->h = hgt; slot->bgr_in = s->h_in;
+  return INFUR_OK;
+}
+
+static RingSlot* find_slot(infur_b200_handle* h, uint64_t ticket) {
+  for (auto& r : h->ring) if (r.state != 0 && r.ticket == ticket) return &r;
+  return nullptr;
+}
+
+int32_t infur_b200_ring_submit(infur_b200_handle* h, uint64_t ticket) {
+  if (!h) return INFUR_E_INVALID_ARG;
+  cudaSetDevice(h->cfg.device);
+  RingSlot* s = find_slot(h, ticket);
+  if (!s || s->state != 1) return fail(h, INFUR_E_TICKET, "ring_submit: unknown ticket or slot already submitted");
+  h->dirty = false;
+  Plan* pp = nullptr;
+  Status st = get_plan(h, (int)s->n, (int)s->w, (int)s->h, &pp);
+  if (!st.ok()) return fail(h, st);
+  Plan& p = *pp;
+  const size_t in_bytes = (size_t)s->n * s->w * s->h * 3, out_px = (size_t)s->n * p.ow * p.oh;
+  s->ow = (uint32_t)p.ow; s->oh = (uint32_t)p.oh; s->has_decoded = p.has_model ? 1 : 0; s->k = p.has_model ? (uint32_t)p.k : 0;
+  API_CU(h, cudaMemcpyAsync(s->d_in, s->h_in, in_bytes, cudaMemcpyHostToDevice, h->h2d));
+  API_CU(h, cudaEventRecord(s->ev_h2d, h->h2d));
+  API_CU(h, cudaStreamWaitEvent(h->stream, s->ev_h2d, 0));
+  OutPtrs o;
+  o.class_map = s->d_class; o.decoded = s->d_decoded; o.blended = h->cfg.blend ? s->d_blended : nullptr;
+  st = run_forward(h, p, s->d_in, o, h->stream, nullptr, nullptr);
+  if (!st.ok()) return fail(h, st);
+  API_CU(h, cudaEventRecord(s->ev_done, h->stream));
+  API_CU(h, cudaStreamWaitEvent(h->d2h, s->ev_done, 0));
+  if (p.has_model && out_px) {
+    API_CU(h, cudaMemcpyAsync(s->h_class, s->d_class, out_px, cudaMemcpyDeviceToHost, h->d2h));
+    API_CU(h, cudaMemcpyAsync(s->h_decoded, s->d_decoded, out_px * 4, cudaMemcpyDeviceToHost, h->d2h));
+    if (h->cfg.blend) API_CU(h, cudaMemcpyAsync(s->h_blended, s->d_blended, out_px * 4, cudaMemcpyDeviceToHost, h->d2h));
+  }
+  API_CU(h, cudaEventRecord(s->ev_out, h->d2h));
+  s->state = 2;
+  return INFUR_OK;
+}
+
+int32_t infur_b200_ring_wait(infur_b200_handle* h, uint64_t ticket, infur_b200_slot* slot) {
+  if (!h || !slot) return INFUR_E_INVALID_ARG;
+  cudaSetDevice(h->cfg.device);
+  RingSlot* s = find_slot(h, ticket);
+  if (!s || s->state != 2) return fail(h, INFUR_E_TICKET, "ring_wait: unknown ticket or slot not submitted");
+  API_CU(h, cudaEventSynchronize(s->ev_out));
+  memset(slot, 0, sizeof(*slot));
+  slot->ticket = ticket; slot->n = s->n; slot->w = s->w; slot->h = s->h; slot->out_w = s->ow; slot->out_h = s->oh;
+  slot->num_classes = s->k; slot->has_decoded = s->has_decoded; slot->bgr_in = s->h_in;
+  slot->class_map = s->h_class; slot->decoded_rgba = s->h_decoded; slot->blended_rgba = h->cfg.blend ? s->h_blended : nullptr;
+  s->state = 0;   // results stay valid until the slot is acquired again
+  return INFUR_OK;
+}
+
+// ---- single-stage entry points -----------------------------------------------------------------
+
+int32_t infur_b200_scale_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, uint8_t* out_bgr, size_t out_cap,
+                                 uint32_t* out_w, uint32_t* out_h) {
+  if (!h) return INFUR_E_INVALID_ARG;
+  cudaSetDevice(h->cfg.device);
+  h->dirty = false;
+  if (!bgr && !out_bgr && !out_w && !out_h) return INFUR_OK;   // advance(&None, ..): clears dirty, nothing else (processing.rs:233-237)
+  uint32_t ow, oh;
+  if (h->factor == 1.0f) { ow = w; oh = hgt; }
+  else {
+    if (w == 0 || hgt == 0) return fail(h, INFUR_E_ZERO_SIZE_IN, "scaling from 0-sized input");
+    ow = scaled_dim(w, h->factor); oh = scaled_dim(hgt, h->factor);
+    if (ow == 0 || oh == 0) return fail(h, INFUR_E_ZERO_SIZE_OUT, "scaling to 0-sized output");
+  }
+  if (out_w) *out_w = ow;
+  if (out_h) *out_h = oh;
+  const size_t need = (size_t)ow * oh * 3;
+  if (need == 0) return INFUR_OK;
+  if (!out_bgr || out_cap < need) return fail(h, INFUR_E_BUFFER_TOO_SMALL, "scale_advance: output buffer too small");
+  if (!bgr) return fail(h, INFUR_E_INVALID_ARG, "scale_advance: bgr is NULL");
+  if (h->factor == 1.0f) { memcpy(out_bgr, bgr, need); return INFUR_OK; }   // deep copy (processing.rs:238-241)
+  if (ow > (1u << 20) || oh > (1u << 20)) return fail(h, INFUR_E_UNSUPPORTED, "scale_advance: output larger than 2^20 per side");
+  std::vector<int32_t> xm, ym;
+  build_nearest_map((int)w, (int)ow, xm); build_nearest_map((int)hgt, (int)oh, ym);
+  uint8_t *d_in = nullptr, *d_out = nullptr; int32_t *d_x = nullptr, *d_y = nullptr;
+  int32_t rc = INFUR_OK;
+  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(d_x); cudaFree(d_y); };
+  if (cudaMalloc(&d_in, (size_t)w * hgt * 3) != cudaSuccess || cudaMalloc(&d_out, need) != cudaSuccess || cudaMalloc(&d_x, ow * 4) != cudaSuccess ||
+      cudaMalloc(&d_y, oh * 4) != cudaSuccess) { cleanup(); return fail(h, INFUR_E_RUNTIME, "scale_advance: cudaMalloc failed"); }
+  cudaMemcpyAsync(d_in, bgr, (size_t)w * hgt * 3, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(d_x, xm.data(), ow * 4, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(d_y, ym.data(), oh * 4, cudaMemcpyHostToDevice, h->stream);
+  PreArgs pa; memset(&pa, 0, sizeof(pa));
+  pa.src = d_in; pa.n = 1; pa.h = (int)hgt; pa.w = (int)w; pa.oh = (int)oh; pa.ow = (int)ow; pa.xmap = d_x; pa.ymap = d_y; pa.lut_h = h->d_lut_h;
+  pa.scaled_bgr = d_out;
+  cudaError_t e = launch_pre(pa, h->stream);
+  h->launches++;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_bgr, d_out, need, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) rc = fail(h, INFUR_E_RUNTIME, std::string("scale_advance: ") + cudaGetErrorString(e));
+  cleanup();
+  return rc;
+}
+
+int32_t infur_b200_model_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* logits_f32, size_t logits_cap,
+                                 float* aux_logits_f32, size_t aux_cap, uint32_t* num_classes, int32_t* has_model) {
+  if (!h) return INFUR_E_INVALID_ARG;
+  if (has_model) *has_model = h->model ? 1 : 0;
+  if (num_classes) *num_classes = 0;
+  if (!h->model) return INFUR_OK;   // no session: Ok(()) and `out` untouched (predict_onnx.rs:321-323)
+  const float factor = h->factor;
+  const bool dirty = h->dirty;
+  h->factor = 1.0f;                 // the Model stage receives the already scaled image
+  infur_b200_out o;
+  memset(&o, 0, sizeof(o));
+  o.struct_size = sizeof(o);
+  o.logits_f32 = logits_f32; o.logits_cap = logits_cap; o.aux_logits_f32 = aux_logits_f32; o.aux_logits_cap = aux_cap;
+  const int32_t rc = infur_b200_advance_batch(h, bgr, 1, w, hgt, nullptr, &o);
+  h->factor = factor; h->dirty = dirty;
+  if (num_classes) *num_classes = o.num_classes;
+  return rc;
+}
+
+int32_t infur_b200_preprocess(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* out_nchw, size_t out_cap_bytes) {
+  if (!h) return INFUR_E_INVALID_ARG;
+  cudaSetDevice(h->cfg.device);
+  const size_t px = (size_t)w * hgt;
+  if (px == 0) return INFUR_OK;
+  if (!bgr || !out_nchw || out_cap_bytes < px * 12) return fail(h, INFUR_E_BUFFER_TOO_SMALL, "preprocess: bad buffers");
+  uint8_t* d_in = nullptr; float* d_out = nullptr;
+  if (cudaMalloc(&d_in, px * 3) != cudaSuccess || cudaMalloc(&d_out, px * 12) != cudaSuccess) { cudaFree(d_in); cudaFree(d_out); return fail(h, INFUR_E_RUNTIME, "preprocess: cudaMalloc failed"); }
+  cudaMemcpyAsync(d_in, bgr, px * 3, cudaMemcpyHostToDevice, h->stream);
+  cudaError_t e = launch_preprocess_f32(d_in, (int)hgt, (int)w, h->d_lut_f, d_out, h->stream);
+  h->launches++;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_nchw, d_out, px * 12, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_in); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(h, INFUR_E_RUNTIME, std::string("preprocess: ") + cudaGetErrorString(e));
+  return INFUR_OK;
+}
+
+int32_t infur_b200_color_code(infur_b200_handle* h, const float* hm, uint32_t k, uint32_t w, uint32_t hgt, uint8_t* rgba, uint8_t* class_map) {
+  if (!h || k == 0) return fail(h, INFUR_E_INVALID_ARG, "color_code: bad argument");
+  cudaSetDevice(h->cfg.device);
+  const size_t px = (size_t)w * hgt;
+  if (px == 0) return INFUR_OK;
+  if (!hm || !rgba) return fail(h, INFUR_E_INVALID_ARG, "color_code: NULL buffer");
+  float* d_hm = nullptr; uint32_t* d_rgba = nullptr; uint8_t* d_cls = nullptr;
+  if (cudaMalloc(&d_hm, px * k * 4) != cudaSuccess || cudaMalloc(&d_rgba, px * 4) != cudaSuccess || cudaMalloc(&d_cls, px) != cudaSuccess) {
+    cudaFree(d_hm); cudaFree(d_rgba); cudaFree(d_cls); return fail(h, INFUR_E_RUNTIME, "color_code: cudaMalloc failed");
+  }
+  cudaMemcpyAsync(d_hm, hm, px * k * 4, cudaMemcpyHostToDevice, h->stream);
+  cudaError_t e = launch_color_code(d_hm, (int)k, (int)hgt, (int)w, h->d_color_lut, d_rgba, d_cls, h->stream);
+  h->launches++;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(rgba, d_rgba, px * 4, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && class_map) e = cudaMemcpyAsync(class_map, d_cls, px, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_hm); cudaFree(d_rgba); cudaFree(d_cls);
+  if (e != cudaSuccess) return fail(h, INFUR_E_RUNTIME, std::string("color_code: ") + cudaGetErrorString(e));
+  return INFUR_OK;
+}
+
+int32_t infur_b200_upsample_color(infur_b200_handle* h, const float* lowres, uint32_t k, uint32_t lw, uint32_t lh, uint32_t out_w,
+                                  uint32_t out_h, const uint8_t* frame_bgr, uint8_t* class_map, uint8_t* decoded_rgba, uint8_t* blended_rgba,
+                                  float* logits_f32) {
+  if (!h || !lowres || !decoded_rgba || k == 0 || lw == 0 || lh == 0) return fail(h, INFUR_E_INVALID_ARG, "upsample_color: bad argument");
+  if (blended_rgba && !frame_bgr) return fail(h, INFUR_E_INVALID_ARG, "upsample_color: blending needs frame_bgr");
+  cudaSetDevice(h->cfg.device);
+  const size_t px = (size_t)out_w * out_h;
+  if (px == 0) return INFUR_OK;
+  Plan tmp;   // owns the scratch allocations
+  tmp.n = 1; tmp.ow = (int)out_w; tmp.oh = (int)out_h;
+  const int ldk = (int)((k + 3) / 4 * 4);
+  // repack [k][lh][lw] -> [lh][lw][ldk]
+  std::vector<float> packed((size_t)lh * lw * ldk, 0.f);
+  for (uint32_t c = 0; c < k; ++c)
+    for (size_t i = 0; i < (size_t)lh * lw; ++i) packed[i * ldk + c] = lowres[(size_t)c * lh * lw + i];
+  auto up = [&](auto*& ptr, const void* src, size_t bytes) -> bool {
+    void* q = nullptr;
+    if (cudaMalloc(&q, std::max<size_t>(bytes, 16)) != cudaSuccess) return false;
+    tmp.owned.push_back(q);
+    if (src && cudaMemcpy(q, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    ptr = reinterpret_cast<typename std::remove_reference<decltype(ptr)>::type>(q);
+    return true;
+  };
+  std::vector<int32_t> i0, i1; std::vector<float> l0, l1;
+  PostArgs q; memset(&q, 0, sizeof(q));
+  float* d_low = nullptr; uint8_t* d_frame = nullptr; uint8_t* d_cls = nullptr; uint32_t *d_dec = nullptr, *d_bl = nullptr; float* d_log = nullptr;
+  int32_t *dy0 = nullptr, *dy1 = nullptr, *dx0 = nullptr, *dx1 = nullptr; float *dly0 = nullptr, *dly1 = nullptr, *dlx0 = nullptr, *dlx1 = nullptr;
+  bool ok = up(d_low, packed.data(), packed.size() * 4);
+  build_bilinear_table((int)lh, (int)out_h, i0, i1, l0, l1);
+  int max_lr = 1, max_lc = 1;
+  for (int Y0 = 0; Y0 < (int)out_h; Y0 += 32) max_lr = std::max(max_lr, i1[std::min<int>(Y0 + 32, out_h) - 1] - i0[Y0] + 1);
+  ok = ok && up(dy0, i0.data(), out_h * 4) && up(dy1, i1.data(), out_h * 4) && up(dly0, l0.data(), out_h * 4) && up(dly1, l1.data(), out_h * 4);
+  build_bilinear_table((int)lw, (int)out_w, i0, i1, l0, l1);
+  for (int X0 = 0; X0 < (int)out_w; X0 += 32) max_lc = std::max(max_lc, i1[std::min<int>(X0 + 32, out_w) - 1] - i0[X0] + 1);
+  ok = ok && up(dx0, i0.data(), out_w * 4) && up(dx1, i1.data(), out_w * 4) && up(dlx0, l0.data(), out_w * 4) && up(dlx1, l1.data(), out_w * 4);
+  if (frame_bgr) ok = ok && up(d_frame, frame_bgr, px * 3);
+  ok = ok && up(d_cls, nullptr, px) && up(d_dec, nullptr, px * 4);
+  if (blended_rgba) ok = ok && up(d_bl, nullptr, px * 4);
+  if (logits_f32) ok = ok && up(d_log, nullptr, px * 4 * k);
+  if (!ok) return fail(h, INFUR_E_RUNTIME, "upsample_color: device allocation or upload failed");
+  q.lowres = d_low; q.n = 1; q.lh = (int)lh; q.lw = (int)lw; q.ldk = ldk; q.k = (int)k; q.oh = (int)out_h; q.ow = (int)out_w;
+  q.y0 = dy0; q.y1 = dy1; q.ly0 = dly0; q.ly1 = dly1; q.x0 = dx0; q.x1 = dx1; q.lx0 = dlx0; q.lx1 = dlx1;
+  q.color_lut = h->d_color_lut; q.frame_bgr = d_frame; q.class_map = d_cls; q.decoded = d_dec; q.blended = d_bl; q.logits = d_log;
+  q.max_lr = max_lr; q.max_lc = max_lc;
+  if (post_smem_bytes(q) > 200 * 1024) return fail(h, INFUR_E_UNSUPPORTED, "upsample_color: low-res patch per tile does not fit shared memory (upsampling ratio too small / too many classes)");
+  cudaError_t e = launch_post(q, h->stream);
+  h->launches++;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(decoded_rgba, d_dec, px * 4, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && class_map) e = cudaMemcpyAsync(class_map, d_cls, px, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && blended_rgba) e = cudaMemcpyAsync(blended_rgba, d_bl, px * 4, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && logits_f32) e = cudaMemcpyAsync(logits_f32, d_log, px * 4 * k, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(h, INFUR_E_RUNTIME, std::string("upsample_color: ") + cudaGetErrorString(e));
+  return INFUR_OK;
+}
+
+int32_t infur_b200_color_lut(const infur_b200_handle* h, uint8_t* lut, size_t cap) {
+  if (!h || !lut || cap < h->color_lut.size()) return INFUR_E_BUFFER_TOO_SMALL;
+  memcpy(lut, h->color_lut.data(), h->color_lut.size());
+  return INFUR_OK;
+}
+
+// ---- diagnostics -------------------------------------------------------------------------------
+
+int32_t infur_b200_conv_test(infur_b200_handle* h, const infur_b200_conv_desc* d, const uint16_t* x, const uint16_t* wgt, const float* bias,
+                             const uint16_t* residual, uint16_t* y, float* y_f32, float* elapsed_ms) {
+  if (!h || !d || !x || !wgt || !bias || (!y && !y_f32)) return fail(h, INFUR_E_INVALID_ARG, "conv_test: NULL argument");
+  cudaSetDevice(h->cfg.device);
+  Status st = conv_test_impl(h, d, x, wgt, bias, residual, y, y_f32, elapsed_ms);
+  if (!st.ok()) return fail(h, st);
+  return INFUR_OK;
+}
+
+static int32_t copy_text(const std::string& s, char* buf, size_t cap, size_t* required) {
+  if (required) *required = s.size() + 1;
+  if (!buf || cap < s.size() + 1) return INFUR_E_BUFFER_TOO_SMALL;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return INFUR_OK;
+}
+
+int32_t infur_b200_plan_text(infur_b200_handle* h, uint32_t n, uint32_t w, uint32_t hgt, char* buf, size_t cap, size_t* required) {
+  if (!h) return INFUR_E_INVALID_ARG;
+  cudaSetDevice(h->cfg.device);
+  Plan* pp = nullptr;
+  Status st = get_plan(h, (int)n, (int)w, (int)hgt, &pp);
+  if (!st.ok()) return fail(h, st);
+  std::ostringstream os;
+  os << "plan n=" << pp->n << " in=" << pp->w << "x" << pp->h << " scaled=" << pp->ow << "x" << pp->oh << " lowres=" << pp->lw << "x" << pp->lh
+     << " classes=" << pp->k << " activation_bytes=" << pp->act_bytes << "\n";
+  double fl = 0, by = 0;
+  for (auto& po : pp->ops) { os << po.text << "\n"; fl += po.flops; by += po.bytes; }
+  os << "total GFLOP " << fl * 1e-9 << " layer-wise MB " << by * 1e-6 << "\n";
+  return copy_text(os.str(), buf, cap, required);
+}
+
+int32_t infur_b200_profile_ops(infur_b200_handle* h, const uint8_t* d_bgr, uint32_t n, uint32_t w, uint32_t hgt, int32_t iters, float* ms,
+                               int32_t cap, int32_t* count) {
+  if (!h || !d_bgr || !ms || !count || iters < 1) return fail(h, INFUR_E_INVALID_ARG, "profile_ops: bad argument");
+  cudaSetDevice(h->cfg.device);
+  Plan* pp = nullptr;
+  Status st = get_plan(h, (int)n, (int)w, (int)hgt, &pp);
+  if (!st.ok()) return fail(h, st);
+  if (!pp->has_model) return fail(h, INFUR_E_INVALID_ARG, "profile_ops: no model loaded");
+  const int nops = (int)pp->ops.size();
+  *count = nops;
+  if (cap < nops) return fail(h, INFUR_E_BUFFER_TOO_SMALL, "profile_ops: ms[] too small");
+  std::vector<cudaEvent_t> evs((size_t)nops + 1);
+  for (auto& e : evs) cudaEventCreate(&e);
+  std::vector<double> acc((size_t)nops, 0.0);
+  OutPtrs o; o.class_map = pp->d_class; o.decoded = pp->d_decoded;
+  for (int it = 0; it < iters && st.ok(); ++it) {
+    st = run_forward(h, *pp, d_bgr, o, h->stream, nullptr, evs.data());
+    if (!st.ok()) break;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { st = Status::error(INFUR_E_RUNTIME, "profile_ops: stream sync failed"); break; }
+    for (int i = 0; i < nops; ++i) { float t = 0; cudaEventElapsedTime(&t, evs[i], evs[i + 1]); acc[i] += t; }
+  }
+  for (auto& e : evs) cudaEventDestroy(e);
+  if (!st.ok()) return fail(h, st);
+  for (int i = 0; i < nops; ++i) ms[i] = (float)(acc[i] / iters);
+  return INFUR_OK;
+}
+
+int32_t infur_b200_onnx_describe(const char* utf8_path, char* buf, size_t cap, size_t* required) {
+  if (!utf8_path) return INFUR_E_INVALID_ARG;
+  std::string text;
+  int32_t rc = INFUR_OK;
+  try {
+    std::vector<uint8_t> bytes;
+    read_file(utf8_path, bytes);
+    OnnxGraph g;
+    parse_onnx(std::move(bytes), g);
+    LoweredModel lm;
+    lower_model(g, lm);
+    text = describe(lm);
+  } catch (const ModelError& e) {
+    text = e.msg; rc = e.code;
+  } catch (const std::exception& e) {
+    text = std::string("Failed to load model: ") + e.what(); rc = INFUR_E_MODEL_LOAD;
+  }
+  int32_t c = copy_text(text, buf, cap, required);
+  return rc != INFUR_OK ? rc : c;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+// tcgen05 implicit-GEMM convolution kernel (see conv_tc.h for the math and the data layout).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0    TMA producer   - one elected lane issues the A (4-D activation box) and B (2-D weight box)
+//                              loads of each 64-channel K block into a ring of smem stages
+//   warp 1    MMA issuer     - one elected lane issues 4 x tcgen05.mma (M128 x N x K16) per K block into one
+//                              of two TMEM accumulator stages; tcgen05.commit releases the smem stage
+//   warp 2    TMEM allocator
+//   warps 4-7 epilogue       - tcgen05.ld the finished accumulator (thread = output pixel), + bias
+//                              (+ residual) (ReLU) -> fp16 NHWC (or f32 logits), overlapping the next
+//                              tile's MMAs through the second accumulator stage
+#include "conv_tc.h"
+#include "ptx.cuh"
+
+namespace infur {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                         // fp16 elements = one 128-byte swizzle span
+constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulator stages; power of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  // barrier block: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = g.num_taps * g.cchunks;
+
+  if (warp == 0 && ptx::elect_one()) {
+    for (int v = 0; v < kMaxViews; ++v) ptx::prefetch_tmap(&maps.a[v]);
+    ptx::prefetch_tmap(&maps.b);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_addr, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  const int bw_log2 = g.bw_log2;
+  const int bw = 1 << bw_log2;
+  const int bh = kBlockM >> bw_log2;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const int nt = tile % g.tiles_n;
+        int m = tile / g.tiles_n;
+        const int tx = m % g.tiles_x; m /= g.tiles_x;
+        const int ty = m % g.tiles_y;
+        const int img = m / g.tiles_y;
+        const int ox0 = tx << bw_log2, oy0 = ty * bh;
+        int kb = 0;
+        for (int tap = 0; tap < g.num_taps; ++tap) {
+          const CUtensorMap* am = &maps.a[g.tap_view[tap]];
+          const int x = ox0 + g.tap_dx[tap], y = oy0 + g.tap_dy[tap];
+          for (int cc = 0; cc < g.cchunks; ++cc, ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + stage * C::kStageBytes;
+            ptx::mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
+            ptx::tma_load_4d(a_dst, am, full_bar(stage), cc * kBlockK, x, y, img);
+            ptx::tma_load_2d(a_dst + kABytes, &maps.b, full_bar(stage), kb * kBlockK, nt * BLOCK_N);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue drained this accumulator stage
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::kStageBytes;
+          const uint64_t a_desc = ptx::make_smem_desc(a_addr, 128);
+          const uint64_t b_desc = ptx::make_smem_desc(a_addr + kABytes, 128);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advancing 16 fp16 along K inside the swizzle span = +32 bytes = +2 in the (addr >> 4) field
+            ptx::umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(empty_bar(stage));
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull_bar(as));
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int quad = warp - kEpiWarp0;       // == warp % 4: the TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;        // accumulator row = pixel inside the tile
+    const int px = row & (bw - 1), py = row >> bw_log2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % g.tiles_n;
+      int m = tile / g.tiles_n;
+      const int tx = m % g.tiles_x; m /= g.tiles_x;
+      const int ty = m % g.tiles_y;
+      const int img = m / g.tiles_y;
+      const int ox = (tx << bw_log2) + px, oy = ty * bh + py;
+      const bool valid = ox < g.ow && oy < g.oh;
+      const size_t pix = ((size_t)img * g.oh + oy) * g.ow + ox;
+      const int n0 = nt * BLOCK_N;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      ptx::mbar_wait(tfull_bar(as), aphase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, acc);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+            v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+            v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+          }
+          const size_t off = pix * (size_t)g.out_ld + (size_t)(n0 + c0);
+          if (g.residual != nullptr) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(g.residual + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 r = __ldg(r4 + j);
+              const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(h[q]);
+                v[8 * j + 2 * q] += f.x;
+                v[8 * j + 2 * q + 1] += f.y;
+              }
+            }
+          }
+          if (g.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (g.out_f32 != nullptr) {
+            float4* o4 = reinterpret_cast<float4*>(g.out_f32 + off);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(g.out + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+              o4[j] = o;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int BLOCK_N>
+cudaError_t launch_one(const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream) {
+  const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  conv_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg<BLOCK_N>::kSmemBytes, stream>>>(maps, g);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int conv_tc_stages(int block_n) {
+  switch (block_n) {
+    case 32: return Cfg<32>::kStages;
+    case 64: return Cfg<64>::kStages;
+    case 128: return Cfg<128>::kStages;
+    default: return Cfg<256>::kStages;
+  }
+}
+
+cudaError_t conv_tc_init() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmemBytes)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream) {
+  switch (block_n) {
+    case 32: return launch_one<32>(maps, g, num_sms, stream);
+    case 64: return launch_one<64>(maps, g, num_sms, stream);
+    case 128: return launch_one<128>(maps, g, num_sms, stream);
+    case 256: return launch_one<256>(maps, g, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace infur

@@ -1,0 +1,51 @@
+// tcgen05 implicit-GEMM convolution for NHWC fp16 activations (the arithmetic the reference hands to
+// ONNX Runtime's Conv/Relu/Add nodes inside session.run, infur/src/predict_onnx.rs:138).
+//
+//   out[n][oy][ox][co] = act( bias[co] + sum_{tap,ci} in[n][oy*s+dy(tap)][ox*s+dx(tap)][ci] * w[co][tap][ci] (+ residual) )
+//
+// GEMM view: M = output pixels (tiles of 128 = bw x bh rectangle of one image), N = cout, K = taps*cin.
+// A tiles are fetched by TMA straight from the activation tensor (4-D tiled maps, zero fill outside
+// the image = the conv padding; strided convs read through per-parity strided views), B tiles from
+// the [cout][taps*cin] weight matrix; both land in 128B-swizzled smem and feed tcgen05.mma with the
+// accumulator in TMEM.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace infur {
+
+constexpr int kMaxTaps = 49;
+constexpr int kMaxViews = 4;
+
+struct ConvTcGeom {
+  int32_t n_img, oh, ow;
+  int32_t bw_log2;            // tile is (1 << bw_log2) wide, 128 >> bw_log2 high
+  int32_t tiles_x, tiles_y, tiles_n, num_tiles;
+  int32_t num_taps, cchunks;  // K blocks = num_taps * cchunks, 64 input channels each
+  int32_t out_ld;             // elements between consecutive output pixels
+  int32_t relu;
+  int32_t store_mode;         // 0: per-thread vector stores; 1: smem-staged TMA store (fp16 only)
+  const float* bias;          // [tiles_n * BLOCK_N]
+  const __half* residual;     // NHWC like out, or nullptr
+  __half* out;                // fp16 NHWC, or nullptr when out_f32 is used
+  float* out_f32;             // f32 NHWC (logit head)
+  int8_t tap_view[kMaxTaps + 3];
+  int16_t tap_dx[kMaxTaps + 1];
+  int16_t tap_dy[kMaxTaps + 1];
+};
+
+struct alignas(64) ConvTcMaps {
+  CUtensorMap a[kMaxViews];  // activation views
+  CUtensorMap b;             // weights [cout][K]
+  CUtensorMap c;             // output (store_mode 1)
+};
+
+// block_n in {32, 64, 128, 256}.  Returns cudaSuccess or the launch error.
+cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream);
+// One-time: opt in to the dynamic shared memory each instantiation needs.
+cudaError_t conv_tc_init();
+int conv_tc_stages(int block_n);
+
+}  // namespace infur

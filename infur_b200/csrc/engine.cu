@@ -1,0 +1,614 @@
+// Device model, execution plans and the forward pass behind the C ABI.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "tables.h"
+
+namespace infur {
+
+#define CU_TRY(expr)                                                                                        \
+  do {                                                                                                      \
+    cudaError_t e__ = (expr);                                                                               \
+    if (e__ != cudaSuccess)                                                                                 \
+      return Status::error(INFUR_E_RUNTIME, std::string(#expr) + ": " + cudaGetErrorString(e__));           \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libcuda is not linked, so the
+// library still loads (and exports its symbols) on a machine without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static Status make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return Status::error(INFUR_E_RUNTIME, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::ostringstream os;
+    os << "cuTensorMapEncodeTiled failed (CUresult " << (int)r << ") rank " << rank << " dims";
+    for (int i = 0; i < rank; ++i) os << " " << dims[i];
+    os << " strides";
+    for (int i = 0; i + 1 < rank; ++i) os << " " << strides_bytes[i];
+    os << " box";
+    for (int i = 0; i < rank; ++i) os << " " << box[i];
+    return Status::error(INFUR_E_RUNTIME, os.str());
+  }
+  return Status();
+}
+
+DeviceModel::~DeviceModel() { if (arena) cudaFree(arena); }
+Plan::~Plan() { for (void* p : owned) cudaFree(p); }
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
+
+// ------------------------------------------------------------------------------------------------
+// Model: classify each conv, pack weights into one device arena.
+
+static void classify_conv(const ConvOp& c, bool reads_input, bool is_head, DevConv& d) {
+  d.cin = c.cin; d.cout = c.cout; d.kh = c.kh; d.kw = c.kw; d.stride = c.stride; d.pad = c.pad; d.dil = c.dil; d.relu = c.relu;
+  d.stem = false; d.tc_ok = false;
+  static const int cands[4] = {256, 128, 64, 32};
+  d.block_n = 32;
+  for (int bn : cands) {
+    const int padded = (int)align_up((size_t)c.cout, (size_t)bn);
+    if (padded - c.cout < bn / 2 || bn == 32) { d.block_n = bn; d.cout_pad = padded; break; }
+  }
+  if (!is_head && d.cout_pad != c.cout) { d.why_not = "cout is not a multiple of 64 for an fp16 NHWC output"; }
+  if (reads_input && c.cin == 3 && c.kh == 7 && c.kw == 7 && c.stride == 2 && c.pad == 3 && c.dil == 1) {
+    d.stem = true; d.taps = 7; d.cchunks = 1; d.kdim = 7 * 64;
+    d.tc_ok = d.why_not.empty();
+    return;
+  }
+  d.taps = c.kh * c.kw; d.cchunks = c.cin / 64; d.kdim = d.taps * c.cin;
+  if (c.cin % 64 != 0) d.why_not = "cin is not a multiple of 64";
+  else if (c.stride != 1 && c.stride != 2) d.why_not = "stride must be 1 or 2";
+  else if (d.taps > kMaxTaps) d.why_not = "more than 49 filter taps";
+  d.tc_ok = d.why_not.empty();
+}
+
+Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool skip_weights, std::unique_ptr<DeviceModel>& out) {
+  auto dm = std::unique_ptr<DeviceModel>(new DeviceModel());
+  dm->lm = std::move(lm);
+  LoweredModel& m = dm->lm;
+  if (m.heads.empty()) return Status::error(INFUR_E_MODEL_LOAD, "model has no output head");
+  dm->out_head = 0;                                   // the reference consumes out[0] only (app.rs:116)
+  dm->aux_head = m.heads.size() > 1 ? 1 : -1;
+  // ops needed for the computed heads
+  std::vector<int> producer(m.num_tensors, -1);
+  for (size_t i = 0; i < m.ops.size(); ++i) producer[m.ops[i].out] = (int)i;
+  dm->needed.assign(m.ops.size(), 0);
+  std::vector<int> stack;
+  stack.push_back(m.heads[dm->out_head].tensor);
+  if (cfg.compute_aux && dm->aux_head >= 0) stack.push_back(m.heads[dm->aux_head].tensor);
+  while (!stack.empty()) {
+    int t = stack.back(); stack.pop_back();
+    int p = t >= 0 ? producer[t] : -1;
+    if (p < 0 || dm->needed[p]) continue;
+    dm->needed[p] = 1;
+    stack.push_back(m.ops[p].in);
+    if (m.ops[p].kind == OpKind::Conv && m.ops[p].conv.residual >= 0) stack.push_back(m.ops[p].conv.residual);
+  }
+  std::vector<char> is_head_tensor(m.num_tensors, 0);
+  for (auto& h : m.heads) is_head_tensor[h.tensor] = 1;
+
+  dm->convs.resize(m.ops.size());
+  size_t off = 0;
+  for (size_t i = 0; i < m.ops.size(); ++i) {
+    if (m.ops[i].kind != OpKind::Conv || !dm->needed[i]) continue;
+    const ConvOp& c = m.ops[i].conv;
+    DevConv& d = dm->convs[i];
+    classify_conv(c, m.ops[i].in == m.input_tensor, is_head_tensor[m.ops[i].out] != 0, d);
+    if (!d.tc_ok && cfg.conv_impl == INFUR_CONV_TCGEN05)
+      return Status::error(INFUR_E_MODEL_LOAD, "convolution '" + m.ops[i].name + "' cannot run on the tcgen05 path: " + d.why_not);
+    d.w_off = off; off = align_up(off + (size_t)d.cout_pad * d.kdim * 2, 256);
+    if (d.stem) { d.wv_off = off; off = align_up(off + (size_t)c.cout * c.kh * c.kw * c.cin * 2, 256); }
+    else d.wv_off = d.w_off;
+    d.b_off = off; off = align_up(off + (size_t)d.cout_pad * 4, 256);
+  }
+  dm->arena_bytes = off;
+  CU_TRY(cudaMalloc(&dm->arena, off ? off : 256));
+  if (skip_weights) {
+    CU_TRY(cudaMemset(dm->arena, 0, off));
+  } else {
+    std::vector<uint8_t> host(off, 0);
+    for (size_t i = 0; i < m.ops.size(); ++i) {
+      if (m.ops[i].kind != OpKind::Conv || !dm->needed[i]) continue;
+      const ConvOp& c = m.ops[i].conv;
+      const DevConv& d = dm->convs[i];
+      __half* w16 = reinterpret_cast<__half*>(host.data() + d.w_off);
+      if (d.stem) {
+        for (int co = 0; co < c.cout; ++co)
+          for (int ky = 0; ky < 7; ++ky)
+            for (int kx = 0; kx < 7; ++kx)
+              for (int ci = 0; ci < 3; ++ci)
+                w16[((size_t)co * 7 + ky) * 64 + (kx + 1) * 4 + ci] = __float2half_rn(c.weight[(((size_t)co * 7 + ky) * 7 + kx) * 3 + ci]);
+        __half* wv = reinterpret_cast<__half*>(host.data() + d.wv_off);
+        for (size_t j = 0; j < c.weight.size(); ++j) wv[j] = __float2half_rn(c.weight[j]);
+      } else {
+        for (size_t j = 0; j < c.weight.size(); ++j) w16[j] = __float2half_rn(c.weight[j]);  // [cout][kh][kw][cin] == [cout][kdim]
+      }
+      float* b = reinterpret_cast<float*>(host.data() + d.b_off);
+      for (int co = 0; co < c.cout; ++co) b[co] = c.bias[co];
+    }
+    CU_TRY(cudaMemcpy(dm->arena, host.data(), off, cudaMemcpyHostToDevice));
+  }
+  for (auto& op : m.ops) { std::vector<float>().swap(op.conv.weight); }
+  out = std::move(dm);
+  return Status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// One tcgen05 conv launch description: tensor maps + geometry.
+
+struct ConvIO {
+  const __half* x = nullptr;   // NHWC fp16 [n][h][w][cin], or the padded stem buffer
+  int n = 0, h = 0, w = 0;     // logical input size
+  int oh = 0, ow = 0;
+  const __half* wgt = nullptr; // [cout_pad][kdim]
+  const float* bias = nullptr;
+  const __half* residual = nullptr;
+  __half* y = nullptr;
+  float* y_f32 = nullptr;
+  int out_ld = 0;
+};
+
+static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po) {
+  ConvTcGeom& g = po.geom;
+  memset(&g, 0, sizeof(g));
+  memset(&po.maps, 0, sizeof(po.maps));
+  g.n_img = io.n; g.oh = io.oh; g.ow = io.ow;
+  // tile shape: bw x bh = 128 output pixels; least overhang, ties to 16 x 8
+  int best = -1; long best_cost = 0;
+  static const int order[6] = {4, 3, 5, 6, 7, 2};
+  for (int l2 : order) {
+    const int bw = 1 << l2, bh = 128 >> l2;
+    const long cost = (long)((io.ow + bw - 1) / bw) * ((io.oh + bh - 1) / bh);
+    if (best < 0 || cost < best_cost) { best = l2; best_cost = cost; }
+  }
+  g.bw_log2 = best;
+  const int bw = 1 << best, bh = 128 >> best;
+  g.tiles_x = (io.ow + bw - 1) / bw; g.tiles_y = (io.oh + bh - 1) / bh;
+  g.tiles_n = d.cout_pad / d.block_n;
+  g.num_tiles = io.n * g.tiles_x * g.tiles_y * g.tiles_n;
+  g.num_taps = d.taps; g.cchunks = d.cchunks;
+  g.out_ld = io.out_ld; g.relu = d.relu ? 1 : 0; g.store_mode = 0;
+  g.bias = io.bias; g.residual = io.residual; g.out = io.y; g.out_f32 = io.y_f32;
+  Status st;
+  const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  if (d.stem) {
+    const int pitch = stem_pitch_px(io.w), rows = stem_rows(io.h);
+    for (int p = 0; p < 2; ++p) {
+      const uint64_t dims[4] = {64, (uint64_t)io.ow, (uint64_t)((rows - p + 1) / 2), (uint64_t)io.n};
+      const uint64_t strides[3] = {16, (uint64_t)pitch * 8 * 2, (uint64_t)rows * pitch * 8};
+      st = make_tmap_f16(&po.maps.a[p], io.x + (size_t)p * pitch * 4, 4, dims, strides, box);
+      if (!st.ok()) return st;
+    }
+    po.maps.a[2] = po.maps.a[0]; po.maps.a[3] = po.maps.a[0];
+    for (int ky = 0; ky < 7; ++ky) { g.tap_view[ky] = (int8_t)(ky & 1); g.tap_dx[ky] = 0; g.tap_dy[ky] = (int16_t)(ky >> 1); }
+  } else {
+    const int s = d.stride;
+    bool have[4] = {false, false, false, false};
+    for (int py = 0; py < s; ++py)
+      for (int px = 0; px < s; ++px) {
+        const int vw = (io.w - px + s - 1) / s, vh = (io.h - py + s - 1) / s;
+        if (vw <= 0 || vh <= 0) continue;
+        const uint64_t dims[4] = {(uint64_t)d.cin, (uint64_t)vw, (uint64_t)vh, (uint64_t)io.n};
+        const uint64_t strides[3] = {(uint64_t)s * d.cin * 2, (uint64_t)s * io.w * d.cin * 2, (uint64_t)io.h * io.w * d.cin * 2};
+        st = make_tmap_f16(&po.maps.a[py * s + px], io.x + ((size_t)py * io.w + px) * d.cin, 4, dims, strides, box);
+        if (!st.ok()) return st;
+        have[py * s + px] = true;
+      }
+    int first = -1;
+    for (int v = 0; v < 4; ++v) if (have[v]) { first = v; break; }
+    if (first < 0) return Status::error(INFUR_E_SHAPE, "convolution input is empty");
+    for (int v = 0; v < 4; ++v) if (!have[v]) po.maps.a[v] = po.maps.a[first];
+    for (int ky = 0; ky < d.kh; ++ky)
+      for (int kx = 0; kx < d.kw; ++kx) {
+        const int t = ky * d.kw + kx;
+        const int offy = ky * d.dil - d.pad, offx = kx * d.dil - d.pad;
+        const int qy = floordiv(offy, s), qx = floordiv(offx, s);
+        const int py = offy - qy * s, px = offx - qx * s;
+        // a tap whose parity view does not exist reads only padding: point it far outside any view
+        g.tap_view[t] = (int8_t)(have[py * s + px] ? py * s + px : first);
+        g.tap_dy[t] = (int16_t)(have[py * s + px] ? qy : 30000);
+        g.tap_dx[t] = (int16_t)qx;
+      }
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)d.kdim, (uint64_t)d.cout_pad};
+    const uint64_t strides[1] = {(uint64_t)d.kdim * 2};
+    const uint32_t bbox[2] = {64, (uint32_t)d.block_n};
+    st = make_tmap_f16(&po.maps.b, io.wgt, 2, dims, strides, bbox);
+    if (!st.ok()) return st;
+  }
+  po.maps.c = po.maps.b;
+  return Status();
+}
+
+static void setup_direct(const DevConv& d, const ConvIO& io, const __half* wv, DirectConvArgs& a) {
+  memset(&a, 0, sizeof(a));
+  a.x = io.x; a.w = wv; a.bias = io.bias; a.residual = io.residual; a.y = io.y; a.y_f32 = io.y_f32;
+  a.n = io.n; a.h = io.h; a.wd = io.w; a.cin = d.cin; a.cout = d.cout; a.kh = d.kh; a.kw = d.kw; a.stride = d.stride; a.pad = d.pad;
+  a.dil = d.dil; a.oh = io.oh; a.ow = io.ow; a.relu = d.relu ? 1 : 0; a.out_ld = io.out_ld;
+  if (d.stem) { a.x_pitch_px = stem_pitch_px(io.w); a.x_rows = stem_rows(io.h); a.x_c = 4; a.x_off_y = kStemPadTop; a.x_off_x = kStemPadLeft; }
+  else { a.x_pitch_px = io.w; a.x_rows = io.h; a.x_c = d.cin; a.x_off_y = 0; a.x_off_x = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plan
+
+template <typename T>
+static Status dev_alloc(Plan& p, T** ptr, size_t count) {
+  void* q = nullptr;
+  CU_TRY(cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 256)));
+  p.owned.push_back(q);
+  *ptr = reinterpret_cast<T*>(q);
+  return Status();
+}
+template <typename T>
+static Status dev_upload(Plan& p, T** ptr, const std::vector<T>& v) {
+  Status st = dev_alloc(p, ptr, v.size());
+  if (!st.ok()) return st;
+  if (!v.empty()) CU_TRY(cudaMemcpy(*ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return Status();
+}
+
+static Status build_bilinear(Plan& p, int lh, int lw) {
+  std::vector<int32_t> i0, i1; std::vector<float> l0, l1;
+  Status st;
+  build_bilinear_table(lh, p.oh, i0, i1, l0, l1);
+  p.max_lr = 1;
+  for (int Y0 = 0; Y0 < p.oh; Y0 += 32) p.max_lr = std::max(p.max_lr, i1[std::min(Y0 + 32, p.oh) - 1] - i0[Y0] + 1);
+  if (!(st = dev_upload(p, &p.y0, i0)).ok() || !(st = dev_upload(p, &p.y1, i1)).ok() || !(st = dev_upload(p, &p.ly0, l0)).ok() ||
+      !(st = dev_upload(p, &p.ly1, l1)).ok())
+    return st;
+  build_bilinear_table(lw, p.ow, i0, i1, l0, l1);
+  p.max_lc = 1;
+  for (int X0 = 0; X0 < p.ow; X0 += 32) p.max_lc = std::max(p.max_lc, i1[std::min(X0 + 32, p.ow) - 1] - i0[X0] + 1);
+  if (!(st = dev_upload(p, &p.x0, i0)).ok() || !(st = dev_upload(p, &p.x1, i1)).ok() || !(st = dev_upload(p, &p.lx0, l0)).ok() ||
+      !(st = dev_upload(p, &p.lx1, l1)).ok())
+    return st;
+  return Status();
+}
+
+Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Plan>& out) {
+  auto pl = std::unique_ptr<Plan>(new Plan());
+  Plan& p = *pl;
+  p.n = n; p.w = w; p.h = h; p.factor = H->factor;
+  const bool unit = H->factor == 1.0f;
+  if (unit) { p.ow = w; p.oh = h; }
+  else {
+    if (w == 0 || h == 0) return Status::error(INFUR_E_ZERO_SIZE_IN, "scaling from 0-sized input");
+    p.ow = (int)std::min<uint32_t>(scaled_dim((uint32_t)w, H->factor), 1u << 20);
+    p.oh = (int)std::min<uint32_t>(scaled_dim((uint32_t)h, H->factor), 1u << 20);
+    if (p.ow == 0 || p.oh == 0) return Status::error(INFUR_E_ZERO_SIZE_OUT, "scaling to 0-sized output");
+  }
+  Status st;
+  const size_t in_bytes = (size_t)n * w * h * 3, out_px = (size_t)n * p.ow * p.oh;
+  if (!(st = dev_alloc(p, &p.d_in, in_bytes)).ok()) return st;
+  if (!unit) {
+    std::vector<int32_t> xm, ym;
+    build_nearest_map(w, p.ow, xm); build_nearest_map(h, p.oh, ym);
+    if (!(st = dev_upload(p, &p.xmap, xm)).ok() || !(st = dev_upload(p, &p.ymap, ym)).ok()) return st;
+    if (!(st = dev_alloc(p, &p.scaled, out_px * 3)).ok()) return st;
+  }
+  if (!(st = dev_alloc(p, &p.d_frame_rgba, out_px)).ok()) return st;
+  DeviceModel* M = H->model.get();
+  p.has_model = M != nullptr;
+  if (!M || out_px == 0) { p.has_model = M != nullptr && out_px != 0; out = std::move(pl); return Status(); }
+
+  if (!(st = dev_alloc(p, &p.d_class, out_px)).ok() || !(st = dev_alloc(p, &p.d_decoded, out_px)).ok()) return st;
+  if (H->cfg.blend && !(st = dev_alloc(p, &p.d_blended, out_px)).ok()) return st;
+
+  const LoweredModel& m = M->lm;
+  // ---- shapes
+  p.tensors.assign(m.num_tensors, TensorInfo());
+  p.tensors[m.input_tensor].h = p.oh; p.tensors[m.input_tensor].w = p.ow; p.tensors[m.input_tensor].c = 3;
+  std::vector<char> is_head_tensor(m.num_tensors, 0);
+  for (auto& hd : m.heads) is_head_tensor[hd.tensor] = 1;
+  std::vector<int> last_use(m.num_tensors, -1);
+  for (size_t i = 0; i < m.ops.size(); ++i) {
+    if (!M->needed[i]) continue;
+    const LoweredOp& op = m.ops[i];
+    const TensorInfo& ti = p.tensors[op.in];
+    TensorInfo& to = p.tensors[op.out];
+    int k, s, pad, dil;
+    if (op.kind == OpKind::Conv) { k = op.conv.kh; s = op.conv.stride; pad = op.conv.pad; dil = op.conv.dil; to.c = op.conv.cout; }
+    else { k = op.pool_k; s = op.pool_s; pad = op.pool_p; dil = 1; to.c = ti.c; }
+    const int eh = ti.h + 2 * pad - dil * (k - 1) - 1, ew = ti.w + 2 * pad - dil * (k - 1) - 1;
+    if (eh < 0 || ew < 0) return Status::error(INFUR_E_SHAPE, "Invalid input shape: image too small for '" + op.name + "'");
+    to.h = eh / s + 1; to.w = ew / s + 1;
+    if (op.kind == OpKind::Conv && is_head_tensor[op.out]) { to.f32 = true; to.ld = M->convs[i].cout_pad; to.bytes = (size_t)n * to.h * to.w * to.ld * 4; }
+    else { to.ld = to.c; to.bytes = (size_t)n * to.h * to.w * to.c * 2; }
+    last_use[op.in] = (int)i;
+    if (op.kind == OpKind::Conv && op.conv.residual >= 0) {
+      const TensorInfo& tr = p.tensors[op.conv.residual];
+      if (tr.h != to.h || tr.w != to.w || tr.c != to.c) return Status::error(INFUR_E_SHAPE, "Invalid input shape: residual size mismatch at '" + op.name + "'");
+      last_use[op.conv.residual] = (int)i;
+    }
+    if (op.kind == OpKind::MaxPool && ti.c % 8 != 0) return Status::error(INFUR_E_UNSUPPORTED, "MaxPool needs channels % 8 == 0");
+  }
+  for (auto& hd : m.heads) last_use[hd.tensor] = 1 << 30;
+
+  // ---- stem input (zero border written once; the pre-kernel only touches the interior)
+  {
+    const size_t bytes = (size_t)n * stem_rows(p.oh) * stem_pitch_px(p.ow) * 8;
+    if (!(st = dev_alloc(p, reinterpret_cast<uint8_t**>(&p.stem_in), bytes)).ok()) return st;
+    CU_TRY(cudaMemset(p.stem_in, 0, bytes));
+    p.tensors[m.input_tensor].ptr = p.stem_in;
+  }
+  // ---- activation buffers by liveness
+  struct Buf { void* ptr; size_t bytes; bool free_; };
+  std::vector<Buf> pool;
+  std::vector<int> tensor_buf(m.num_tensors, -1);
+  for (size_t i = 0; i < m.ops.size(); ++i) {
+    if (!M->needed[i]) continue;
+    const LoweredOp& op = m.ops[i];
+    TensorInfo& to = p.tensors[op.out];
+    int pick = -1;
+    for (size_t b = 0; b < pool.size(); ++b)
+      if (pool[b].free_ && pool[b].bytes >= to.bytes && (pick < 0 || pool[b].bytes < pool[pick].bytes)) pick = (int)b;
+    if (pick < 0) {
+      uint8_t* q = nullptr;
+      if (!(st = dev_alloc(p, &q, to.bytes)).ok()) return st;
+      pool.push_back({q, to.bytes, false});
+      pick = (int)pool.size() - 1;
+      p.act_bytes += to.bytes;
+    }
+    pool[pick].free_ = false;
+    tensor_buf[op.out] = pick;
+    to.ptr = pool[pick].ptr;
+    auto release = [&](int t) { if (t >= 0 && tensor_buf[t] >= 0 && last_use[t] == (int)i) pool[tensor_buf[t]].free_ = true; };
+    release(op.in);
+    if (op.kind == OpKind::Conv) release(op.conv.residual);
+  }
+  // ---- ops
+  for (size_t i = 0; i < m.ops.size(); ++i) {
+    if (!M->needed[i]) continue;
+    const LoweredOp& op = m.ops[i];
+    const TensorInfo& ti = p.tensors[op.in];
+    const TensorInfo& to = p.tensors[op.out];
+    PlanOp po;
+    po.op = (int)i;
+    std::ostringstream os;
+    if (op.kind == OpKind::Conv) {
+      const DevConv& d = M->convs[i];
+      po.is_conv = true;
+      ConvIO io;
+      io.x = reinterpret_cast<const __half*>(ti.ptr); io.n = n; io.h = ti.h; io.w = ti.w; io.oh = to.h; io.ow = to.w;
+      io.wgt = reinterpret_cast<const __half*>(M->arena + d.w_off);
+      io.bias = reinterpret_cast<const float*>(M->arena + d.b_off);
+      io.residual = op.conv.residual >= 0 ? reinterpret_cast<const __half*>(p.tensors[op.conv.residual].ptr) : nullptr;
+      if (to.f32) io.y_f32 = reinterpret_cast<float*>(to.ptr); else io.y = reinterpret_cast<__half*>(to.ptr);
+      io.out_ld = to.ld;
+      if (d.tc_ok) { if (!(st = setup_conv_tc(d, io, po)).ok()) return st; }
+      setup_direct(d, io, reinterpret_cast<const __half*>(M->arena + d.wv_off), po.direct);
+      po.flops = 2.0 * n * to.h * to.w * (double)d.cout * d.kh * d.kw * d.cin;
+      po.bytes = (double)n * ti.h * ti.w * d.cin * 2 + (double)to.bytes + (io.residual ? (double)n * to.h * to.w * to.c * 2 : 0.0) +
+                 (double)d.cout * d.kh * d.kw * d.cin * 2;
+      os << "conv " << op.name << " [" << n << "x" << ti.h << "x" << ti.w << "x" << d.cin << "] -> [" << to.h << "x" << to.w << "x" << d.cout
+         << "] k" << d.kh << " s" << d.stride << " p" << d.pad << " d" << d.dil << (io.residual ? " +res" : "") << (d.relu ? " relu" : "");
+      if (d.tc_ok)
+        os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << d.block_n << " tiles "
+           << po.geom.num_tiles << " kblocks " << d.taps * d.cchunks;
+      os << " | GFLOP " << po.flops * 1e-9 << " MB " << po.bytes * 1e-6;
+    } else {
+      po.flops = 0;
+      po.bytes = (double)n * ti.h * ti.w * ti.c * 2 + (double)to.bytes;
+      os << "maxpool " << op.name << " [" << n << "x" << ti.h << "x" << ti.w << "x" << ti.c << "] -> [" << to.h << "x" << to.w << "] k" << op.pool_k
+         << " s" << op.pool_s << " | MB " << po.bytes * 1e-6;
+    }
+    po.text = os.str();
+    p.ops.push_back(po);
+  }
+  // ---- head / post
+  const LoweredHead& hd = m.heads[M->out_head];
+  const TensorInfo& th = p.tensors[hd.tensor];
+  if (!th.f32) return Status::error(INFUR_E_UNSUPPORTED, "output head is not produced by a convolution");
+  p.lowres = reinterpret_cast<float*>(th.ptr); p.lh = th.h; p.lw = th.w; p.k = hd.num_classes; p.ldk = th.ld;
+  if (H->cfg.compute_aux && M->aux_head >= 0) p.aux_lowres = reinterpret_cast<float*>(p.tensors[m.heads[M->aux_head].tensor].ptr);
+  if (!(st = build_bilinear(p, p.lh, p.lw)).ok()) return st;
+  out = std::move(pl);
+  return Status();
+}
+
+Status get_plan(infur_b200_handle* H, int n, int w, int h, Plan** out) {
+  uint32_t fbits; memcpy(&fbits, &H->factor, 4);
+  auto key = std::make_tuple(n, w, h, fbits, H->model_gen);
+  auto it = H->plans.find(key);
+  if (it == H->plans.end()) {
+    // keep the cache small: a size / scale / model change retires the old plans
+    if (H->plans.size() >= 4) { cudaStreamSynchronize(H->stream); H->plans.clear(); }
+    std::unique_ptr<Plan> p;
+    Status st = build_plan(H, n, w, h, p);
+    if (!st.ok()) return st;
+    it = H->plans.emplace(key, std::move(p)).first;
+  }
+  *out = it->second.get();
+  return Status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward: Scale -> Model -> ColorCode on device buffers.
+
+Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const OutPtrs& o, cudaStream_t s, float* op_ms = nullptr,
+                   cudaEvent_t* evs = nullptr) {
+  const size_t out_px = (size_t)p.n * p.ow * p.oh;
+  if (out_px == 0) return Status();
+  const bool unit = p.factor == 1.0f;
+  PreArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.src = d_bgr; pa.n = p.n; pa.h = p.h; pa.w = p.w; pa.oh = p.oh; pa.ow = p.ow;
+  pa.xmap = p.xmap; pa.ymap = p.ymap; pa.lut_h = H->d_lut_h;
+  pa.stem_in = p.has_model ? p.stem_in : nullptr;
+  pa.scaled_bgr = unit ? nullptr : p.scaled;
+  const uint8_t* frame = unit ? d_bgr : p.scaled;
+  if (pa.stem_in || pa.scaled_bgr) { CU_TRY(launch_pre(pa, s)); H->launches++; }
+  if (!p.has_model) {
+    if (o.frame_rgba) { CU_TRY(launch_frame_rgba(frame, out_px, o.frame_rgba, s)); H->launches++; }
+    return Status();
+  }
+  const DeviceModel& M = *H->model;
+  int ei = 0;
+  if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
+  for (PlanOp& po : p.ops) {
+    const LoweredOp& op = M.lm.ops[po.op];
+    if (po.is_conv) {
+      const DevConv& d = M.convs[po.op];
+      if (H->cfg.conv_impl == INFUR_CONV_TCGEN05) CU_TRY(conv_tc_launch(d.block_n, po.maps, po.geom, H->num_sms, s));
+      else CU_TRY(launch_direct_conv(po.direct, s));
+    } else {
+      const TensorInfo& ti = p.tensors[op.in];
+      const TensorInfo& to = p.tensors[op.out];
+      CU_TRY(launch_maxpool(reinterpret_cast<const __half*>(ti.ptr), reinterpret_cast<__half*>(to.ptr), p.n, ti.h, ti.w, ti.c, to.h, to.w,
+                            op.pool_k, op.pool_s, op.pool_p, s));
+    }
+    H->launches++;
+    if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
+  }
+  PostArgs q;
+  memset(&q, 0, sizeof(q));
+  q.lowres = p.lowres; q.n = p.n; q.lh = p.lh; q.lw = p.lw; q.ldk = p.ldk; q.k = p.k; q.oh = p.oh; q.ow = p.ow;
+  q.y0 = p.y0; q.y1 = p.y1; q.ly0 = p.ly0; q.ly1 = p.ly1; q.x0 = p.x0; q.x1 = p.x1; q.lx0 = p.lx0; q.lx1 = p.lx1;
+  q.color_lut = H->d_color_lut; q.frame_bgr = frame;
+  q.class_map = o.class_map; q.decoded = o.decoded; q.blended = o.blended; q.frame_rgba = o.frame_rgba; q.logits = o.logits;
+  q.max_lr = p.max_lr; q.max_lc = p.max_lc;
+  if (!q.decoded) q.decoded = p.d_decoded;
+  if (o.aux_logits && p.aux_lowres) {
+    // debug path: the aux head through the same post kernel first; only its logits are kept
+    PostArgs qa = q;
+    qa.lowres = p.aux_lowres; qa.logits = o.aux_logits; qa.class_map = nullptr; qa.blended = nullptr; qa.frame_rgba = nullptr;
+    qa.decoded = p.d_decoded;
+    CU_TRY(launch_post(qa, s));
+    H->launches++;
+  }
+  CU_TRY(launch_post(q, s));
+  H->launches++;
+  (void)op_ms;
+  return Status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagnostics: one convolution through either implementation, host tensors in / out.
+
+Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, const uint16_t* x, const uint16_t* wgt, const float* bias,
+                      const uint16_t* residual, uint16_t* y, float* y_f32, float* elapsed_ms) {
+  ConvOp c;
+  c.cin = (int)cd->cin; c.cout = (int)cd->cout; c.kh = (int)cd->kh; c.kw = (int)cd->kw; c.stride = (int)cd->stride; c.pad = (int)cd->pad;
+  c.dil = (int)cd->dil; c.relu = cd->relu != 0;
+  if (cd->n == 0 || cd->h == 0 || cd->w == 0 || c.cin <= 0 || c.cout <= 0 || c.kh <= 0 || c.kw <= 0 || c.stride <= 0 || c.dil <= 0 || c.pad < 0)
+    return Status::error(INFUR_E_INVALID_ARG, "conv_test: bad descriptor");
+  const int n = (int)cd->n, h = (int)cd->h, w = (int)cd->w;
+  const int eh = h + 2 * c.pad - c.dil * (c.kh - 1) - 1, ew = w + 2 * c.pad - c.dil * (c.kw - 1) - 1;
+  if (eh < 0 || ew < 0) return Status::error(INFUR_E_SHAPE, "conv_test: input smaller than the filter");
+  const int oh = eh / c.stride + 1, ow = ew / c.stride + 1;
+  const bool f32out = y_f32 != nullptr;
+  DevConv d;
+  classify_conv(c, c.cin == 3, f32out, d);
+  const bool tc = cd->impl == INFUR_CONV_TCGEN05;
+  if (tc && !d.tc_ok) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: shape not supported by the tcgen05 kernel: " + d.why_not);
+  Plan tmp;
+  Status st;
+  const size_t wcount = (size_t)c.cout * c.kh * c.kw * c.cin;
+  // weights
+  std::vector<__half> wp((size_t)d.cout_pad * d.kdim, __float2half_rn(0.f));
+  const __half* wh = reinterpret_cast<const __half*>(wgt);
+  if (d.stem) {
+    for (int co = 0; co < c.cout; ++co)
+      for (int ky = 0; ky < 7; ++ky)
+        for (int kx = 0; kx < 7; ++kx)
+          for (int ci = 0; ci < 3; ++ci) wp[((size_t)co * 7 + ky) * 64 + (kx + 1) * 4 + ci] = wh[(((size_t)co * 7 + ky) * 7 + kx) * 3 + ci];
+  } else if (d.tc_ok) {
+    for (size_t j = 0; j < wcount; ++j) wp[j] = wh[j];
+  }
+  __half *d_w = nullptr, *d_wv = nullptr, *d_x = nullptr, *d_res = nullptr, *d_y = nullptr;
+  float *d_b = nullptr, *d_yf = nullptr;
+  std::vector<float> bp((size_t)d.cout_pad, 0.f);
+  for (int co = 0; co < c.cout; ++co) bp[co] = bias[co];
+  if (!(st = dev_upload(tmp, &d_w, wp)).ok() || !(st = dev_upload(tmp, &d_b, bp)).ok()) return st;
+  {
+    std::vector<__half> wv(wh, wh + wcount);
+    if (!(st = dev_upload(tmp, &d_wv, wv)).ok()) return st;
+  }
+  // input
+  if (d.stem) {
+    const int pitch = stem_pitch_px(w), rows = stem_rows(h);
+    std::vector<__half> xp((size_t)n * rows * pitch * 4, __float2half_rn(0.f));
+    const __half* xh = reinterpret_cast<const __half*>(x);
+    for (int i = 0; i < n; ++i)
+      for (int yy = 0; yy < h; ++yy)
+        for (int xx = 0; xx < w; ++xx)
+          for (int ci = 0; ci < 3; ++ci)
+            xp[(((size_t)i * rows + yy + kStemPadTop) * pitch + xx + kStemPadLeft) * 4 + ci] = xh[(((size_t)i * h + yy) * w + xx) * 3 + ci];
+    if (!(st = dev_upload(tmp, &d_x, xp)).ok()) return st;
+  } else {
+    std::vector<__half> xv(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(x) + (size_t)n * h * w * c.cin);
+    if (!(st = dev_upload(tmp, &d_x, xv)).ok()) return st;
+  }
+  const int out_ld = f32out ? d.cout_pad : c.cout;
+  const size_t ocount = (size_t)n * oh * ow * out_ld;
+  if (residual) {
+    std::vector<__half> rv(reinterpret_cast<const __half*>(residual), reinterpret_cast<const __half*>(residual) + (size_t)n * oh * ow * c.cout);
+    if (f32out) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: residual with f32 output is not supported");
+    if (!(st = dev_upload(tmp, &d_res, rv)).ok()) return st;
+  }
+  if (f32out) { if (!(st = dev_alloc(tmp, &d_yf, ocount)).ok()) return st; CU_TRY(cudaMemset(d_yf, 0, ocount * 4)); }
+  else { if (!(st = dev_alloc(tmp, &d_y, ocount)).ok()) return st; CU_TRY(cudaMemset(d_y, 0, ocount * 2)); }
+  ConvIO io;
+  io.x = d_x; io.n = n; io.h = h; io.w = w; io.oh = oh; io.ow = ow; io.wgt = d_w; io.bias = d_b; io.residual = d_res; io.y = d_y; io.y_f32 = d_yf;
+  io.out_ld = out_ld;
+  PlanOp po;
+  if (tc) { if (!(st = setup_conv_tc(d, io, po)).ok()) return st; }
+  else setup_direct(d, io, d_wv, po.direct);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int reps = elapsed_ms ? 3 : 1;
+  cudaError_t err = cudaSuccess;
+  for (int r = 0; r < reps && err == cudaSuccess; ++r) {
+    if (r == reps - 1) cudaEventRecord(e0, H->stream);
+    err = tc ? conv_tc_launch(d.block_n, po.maps, po.geom, H->num_sms, H->stream) : launch_direct_conv(po.direct, H->stream);
+    H->launches++;
+  }
+  cudaEventRecord(e1, H->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(H->stream);
+  float ms = 0.f;
+  if (err == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (err != cudaSuccess) return Status::error(INFUR_E_RUNTIME, std::string("conv_test: ") + cudaGetErrorString(err));
+  if (elapsed_ms) *elapsed_ms = ms;
+  if (f32out) {
+    std::vector<float> tmpo(ocount);
+    CU_TRY(cudaMemcpy(tmpo.data(), d_yf, ocount * 4, cudaMemcpyDeviceToHost));
+    for (size_t px = 0; px < (size_t)n * oh * ow; ++px)
+      for (int co = 0; co < c.cout; ++co) y_f32[px * c.cout + co] = tmpo[px * out_ld + co];
+  } else {
+    CU_TRY(cudaMemcpy(y, d_y, ocount * 2, cudaMemcpyDeviceToHost));
+  }
+  return Status();
+}
+
+}  // namespace infur

@@ -1,0 +1,141 @@
+// Engine internals behind the C ABI (include/infur_b200.h): device model, execution plans, forward.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/infur_b200.h"
+#include "conv_tc.h"
+#include "kernels.h"
+#include "onnx_reader.h"
+
+namespace infur {
+
+struct Status {
+  int code = INFUR_OK;
+  std::string msg;
+  bool ok() const { return code == INFUR_OK; }
+  static Status error(int c, std::string m) { Status s; s.code = c; s.msg = std::move(m); return s; }
+};
+
+// One convolution of the lowered model with its packed device weights.
+struct DevConv {
+  int cin = 0, cout = 0, kh = 1, kw = 1, stride = 1, pad = 0, dil = 1;
+  bool relu = false;
+  bool stem = false;       // 7x7/s2 RGB stem: reads the padded NHWC4 buffer through 16-pixel windows
+  bool tc_ok = false;      // expressible by the tcgen05 kernel
+  std::string why_not;     // reason when !tc_ok
+  int block_n = 0, cout_pad = 0, taps = 0, cchunks = 0, kdim = 0;
+  size_t w_off = 0;        // fp16 [cout_pad][kdim] for the tcgen05 kernel (byte offset into the arena)
+  size_t wv_off = 0;       // fp16 [cout][kh][kw][cin] for the validation kernel (== w_off unless stem)
+  size_t b_off = 0;        // f32 [cout_pad]
+};
+
+struct DeviceModel {
+  LoweredModel lm;               // weights released after upload
+  std::vector<DevConv> convs;    // parallel to lm.ops (unused entries for MaxPool)
+  std::vector<char> needed;      // op is on the path of a computed head
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  int out_head = -1, aux_head = -1;
+  ~DeviceModel();
+};
+
+struct TensorInfo {
+  int h = 0, w = 0, c = 0, ld = 0;   // ld = channel stride (>= c)
+  bool f32 = false;
+  size_t bytes = 0;
+  void* ptr = nullptr;
+};
+
+struct PlanOp {
+  int op = -1;                 // index into model ops
+  bool is_conv = false;
+  ConvTcMaps maps;
+  ConvTcGeom geom;
+  DirectConvArgs direct;       // validation path
+  double flops = 0, bytes = 0; // algorithmic, for plan_text / roofline
+  std::string text;
+};
+
+struct Plan {
+  int n = 0, w = 0, h = 0;       // input frames
+  int ow = 0, oh = 0;            // after Scale
+  float factor = 1.f;
+  bool has_model = false;
+  int lh = 0, lw = 0, k = 0, ldk = 0;
+  std::vector<TensorInfo> tensors;
+  std::vector<PlanOp> ops;
+  std::vector<void*> owned;      // device allocations
+  // device buffers
+  int32_t *xmap = nullptr, *ymap = nullptr;
+  int32_t *y0 = nullptr, *y1 = nullptr, *x0 = nullptr, *x1 = nullptr;
+  float *ly0 = nullptr, *ly1 = nullptr, *lx0 = nullptr, *lx1 = nullptr;
+  __half* stem_in = nullptr;
+  uint8_t* scaled = nullptr;     // Scale output when factor != 1
+  float* lowres = nullptr;       // [n][lh][lw][ldk]
+  float* aux_lowres = nullptr;
+  int max_lr = 0, max_lc = 0;
+  // staging for the host-buffer entry points
+  uint8_t* d_in = nullptr;
+  uint8_t* d_class = nullptr;
+  uint32_t *d_decoded = nullptr, *d_blended = nullptr, *d_frame_rgba = nullptr;
+  float* d_logits = nullptr;
+  size_t act_bytes = 0;
+  ~Plan();
+};
+
+struct OutPtrs {
+  uint8_t* class_map = nullptr;
+  uint32_t* decoded = nullptr;
+  uint32_t* blended = nullptr;
+  uint32_t* frame_rgba = nullptr;
+  float* logits = nullptr;      // out head, full resolution (debug)
+  float* aux_logits = nullptr;
+};
+
+struct RingSlot {
+  int state = 0;  // 0 free, 1 acquired, 2 submitted
+  uint64_t ticket = 0;
+  uint32_t n = 0, w = 0, h = 0, ow = 0, oh = 0;
+  size_t in_cap = 0, out_cap_px = 0;
+  uint8_t* h_in = nullptr;      // pinned
+  uint8_t* h_class = nullptr;
+  uint8_t* h_decoded = nullptr;
+  uint8_t* h_blended = nullptr;
+  uint8_t* d_in = nullptr;
+  uint8_t* d_class = nullptr;
+  uint32_t* d_decoded = nullptr;
+  uint32_t* d_blended = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_out = nullptr;
+  int has_decoded = 0;
+  uint32_t k = 0;
+};
+
+}  // namespace infur
+
+struct infur_b200_handle {
+  infur_b200_config cfg;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+  std::string last_error;
+  float factor = 1.0f;
+  bool dirty = true;
+  float* d_lut_f = nullptr;
+  __half* d_lut_h = nullptr;
+  uint32_t* d_color_lut = nullptr;
+  std::vector<uint8_t> color_lut;
+  std::unique_ptr<infur::DeviceModel> model;
+  uint64_t model_gen = 0;
+  std::map<std::tuple<int, int, int, uint32_t, uint64_t>, std::unique_ptr<infur::Plan>> plans;
+  uint64_t launches = 0;
+  std::vector<infur::RingSlot> ring;
+  uint64_t next_ticket = 1;
+  uint64_t next_wait = 1;
+};

@@ -1,0 +1,328 @@
+// Pre-kernel (Scale + ImageSession::forward pre-processing), max-pool, post-kernel (final bilinear
+// Resize fused with ColorCode) and the slow validation convolution.  All integer/LUT paths are
+// bit-exact with the reference semantics; float paths use explicitly un-fused f32 operations in the
+// reference's order.
+#include "kernels.h"
+
+namespace infur {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// K0: Scale::advance (nearest gather, infur/src/processing.rs:232-281) fused with the u8 -> normalised
+// conversion of ImageSession::forward (infur/src/predict_onnx.rs:103-137).  The normalisation has only
+// 256 inputs per channel, so a [3][256] table built on the host with the reference's three separately
+// rounded f32 operations reproduces it exactly; the table is pre-rounded to fp16 (the network's
+// activation type).
+__global__ void __launch_bounds__(256) pre_generic_kernel(PreArgs a, int stem_pitch, int stem_rows_) {
+  __shared__ __half lut[3 * 256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = a.lut_h[i];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int img = blockIdx.z;
+  if (x >= a.ow) return;
+  const int sx = a.xmap ? a.xmap[x] : x;
+  const int sy = a.ymap ? a.ymap[y] : y;
+  const uint8_t* p = a.src + (((size_t)img * a.h + sy) * a.w + sx) * 3;
+  const uint8_t b = p[0], g = p[1], r = p[2];
+  if (a.scaled_bgr) {
+    uint8_t* q = a.scaled_bgr + (((size_t)img * a.oh + y) * a.ow + x) * 3;
+    q[0] = b; q[1] = g; q[2] = r;
+  }
+  if (a.stem_in) {
+    __half2 rg = __halves2half2(lut[r], lut[256 + g]);
+    __half2 b0 = __halves2half2(lut[512 + b], __ushort_as_half((unsigned short)0));
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&rg);
+    v.y = *reinterpret_cast<uint32_t*>(&b0);
+    uint2* dst = reinterpret_cast<uint2*>(a.stem_in) + ((size_t)img * stem_rows_ + (y + kStemPadTop)) * stem_pitch + (x + kStemPadLeft);
+    *dst = v;
+  }
+}
+
+// Unit-scale fast path: 4 pixels per thread, 3 x 32-bit loads -> 2 x 128-bit stores.  Needs w % 4 == 0.
+__global__ void __launch_bounds__(256) pre_unit_vec4_kernel(PreArgs a, int stem_pitch, int stem_rows_) {
+  __shared__ __half lut[3 * 256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = a.lut_h[i];
+  __syncthreads();
+  const int x4 = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pixels
+  const int y = blockIdx.y;
+  const int img = blockIdx.z;
+  if (x4 * 4 >= a.w) return;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(a.src + (((size_t)img * a.h + y) * a.w + (size_t)x4 * 4) * 3);
+  const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+  // bytes: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+  const uint8_t bb[4] = {(uint8_t)(w0), (uint8_t)(w0 >> 24), (uint8_t)(w1 >> 16), (uint8_t)(w2 >> 8)};
+  const uint8_t gg[4] = {(uint8_t)(w0 >> 8), (uint8_t)(w1), (uint8_t)(w1 >> 24), (uint8_t)(w2 >> 16)};
+  const uint8_t rr[4] = {(uint8_t)(w0 >> 16), (uint8_t)(w1 >> 8), (uint8_t)(w2), (uint8_t)(w2 >> 24)};
+  uint32_t o[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 rg = __halves2half2(lut[rr[i]], lut[256 + gg[i]]);
+    __half2 b0 = __halves2half2(lut[512 + bb[i]], __ushort_as_half((unsigned short)0));
+    o[2 * i] = *reinterpret_cast<uint32_t*>(&rg);
+    o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&b0);
+  }
+  // kStemPadLeft = 4 pixels = 32 bytes, x4*4 pixels = 32*x4 bytes: 16-byte aligned stores
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(a.stem_in) +
+                                        ((size_t)img * stem_rows_ + (y + kStemPadTop)) * stem_pitch + ((size_t)x4 * 4 + kStemPadLeft));
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+__global__ void __launch_bounds__(256) preprocess_f32_kernel(const uint8_t* __restrict__ bgr, int h, int w, const float* __restrict__ lut_f,
+                                                              float* __restrict__ out) {
+  __shared__ float lut[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = lut_f[i];
+  __syncthreads();
+  const size_t npix = (size_t)h * w;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const uint8_t* p = bgr + i * 3;
+  out[i] = lut[p[2]];
+  out[npix + i] = lut[256 + p[1]];
+  out[2 * npix + i] = lut[512 + p[0]];
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n, int h, int w, int c8,
+                                                       int oh, int ow, int k, int stride, int pad) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)n * oh * ow * c8;
+  if (idx >= total) return;
+  const int cg = (int)(idx % c8);
+  size_t t = idx / c8;
+  const int ox = (int)(t % ow); t /= ow;
+  const int oy = (int)(t % oh);
+  const int img = (int)(t / oh);
+  const __half2 ninf = __float2half2_rn(-65504.f);
+  __half2 m[4] = {ninf, ninf, ninf, ninf};
+  bool any = false;
+  for (int ky = 0; ky < k; ++ky) {
+    const int iy = oy * stride + ky - pad;
+    if (iy < 0 || iy >= h) continue;
+    for (int kx = 0; kx < k; ++kx) {
+      const int ix = ox * stride + kx - pad;
+      if (ix < 0 || ix >= w) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)img * h + iy) * w + ix) * (size_t)(c8 * 8)) + cg);
+      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+      if (!any) { m[0] = hv[0]; m[1] = hv[1]; m[2] = hv[2]; m[3] = hv[3]; any = true; }
+      else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m[q] = __hmax2(m[q], hv[q]);
+      }
+    }
+  }
+  uint4 o;
+  __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) ho[q] = m[q];
+  reinterpret_cast<uint4*>(out)[idx] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: the network's final Resize(linear, half_pixel) fused with ColorCode::advance
+// (infur/src/decode_predict.rs:53-79) and color_code (:32-36).  One CTA = one 32 x 32 output tile:
+//   phase 0  copy the low-res patch the tile touches into smem (coalesced 128-bit loads)
+//   phase 1  horizontal interpolation  t[k][lr][x] = lx0*L[lr][x0][k] + lx1*L[lr][x1][k]   (once per low-res row)
+//   phase 2  per pixel: v = ly0*t[k][y0][x] + ly1*t[k][y1][x]; strict '>' scan from (0, 0.0); alpha = trunc(sat(c*255));
+//            colour from the 20x256 premultiplied table; optional "over" blend and BGR->RGBA of the frame.
+// The full-resolution logits (174 MB per 1080p frame in the reference) are never materialised.
+constexpr int kPostTile = 32;
+// smem pixel stride of the low-res patch: odd, so that neighbouring low-res pixels fall into different banks
+__host__ __device__ inline int post_pad(int k) { return (((k + 3) >> 2) << 2) | 1; }
+
+__global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
+  extern __shared__ float sm[];
+  const int X0 = blockIdx.x * kPostTile, Y0 = blockIdx.y * kPostTile, img = blockIdx.z;
+  const int X1 = min(X0 + kPostTile, a.ow) - 1, Y1 = min(Y0 + kPostTile, a.oh) - 1;
+  const int lc0 = a.x0[X0], lc1 = a.x1[X1], lr0 = a.y0[Y0], lr1 = a.y1[Y1];
+  const int ncol = lc1 - lc0 + 1, nrow = lr1 - lr0 + 1;
+  const int kPostPad = post_pad(a.k);
+  float* patch = sm;                                   // [nrow][ncol][kPostPad]
+  float* hor = sm + (size_t)a.max_lr * a.max_lc * kPostPad;  // [k][nrow][32]
+  const int tid = threadIdx.x;
+  const int kq = (a.k + 3) >> 2;  // float4 per low-res pixel that carry classes
+  for (int i = tid; i < nrow * ncol * kq; i += blockDim.x) {
+    const int q = i % kq;
+    const int pc = (i / kq) % ncol;
+    const int pr = i / (kq * ncol);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.lowres + (((size_t)img * a.lh + (lr0 + pr)) * a.lw + (lc0 + pc)) * a.ldk) + q);
+    float* d = patch + (pr * ncol + pc) * kPostPad + q * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int x = X0 + lane;
+  const bool xin = x < a.ow;
+  const int xi = xin ? x : a.ow - 1;
+  {
+    const int c0 = a.x0[xi] - lc0, c1 = a.x1[xi] - lc0;
+    const float w0 = a.lx0[xi], w1 = a.lx1[xi];
+    for (int i = warp; i < a.k * nrow; i += 4) {
+      const int k = i % a.k, pr = i / a.k;
+      const float* rowp = patch + (size_t)pr * ncol * kPostPad + k;
+      const float t = __fadd_rn(__fmul_rn(w0, rowp[c0 * kPostPad]), __fmul_rn(w1, rowp[c1 * kPostPad]));
+      hor[((size_t)k * nrow + pr) * kPostTile + lane] = t;
+    }
+  }
+  __syncthreads();
+  if (!xin) return;
+  const size_t plane = (size_t)a.oh * a.ow;
+  for (int ry = warp * 8; ry < warp * 8 + 8; ++ry) {
+    const int y = Y0 + ry;
+    if (y >= a.oh) break;
+    const int r0 = a.y0[y] - lr0, r1 = a.y1[y] - lr0;
+    const float w0 = a.ly0[y], w1 = a.ly1[y];
+    int k_max = 0;
+    float c_max = 0.f;
+    const size_t pix = (size_t)y * a.ow + x;
+    for (int k = 0; k < a.k; ++k) {
+      const float* hk = hor + (size_t)k * nrow * kPostTile + lane;
+      const float v = __fadd_rn(__fmul_rn(w0, hk[r0 * kPostTile]), __fmul_rn(w1, hk[r1 * kPostTile]));
+      if (a.logits) a.logits[((size_t)img * a.k + k) * plane + pix] = v;
+      if (v > c_max) { k_max = k; c_max = v; }
+    }
+    const float av = __fmul_rn(c_max, 255.0f);
+    const int alpha = av >= 255.0f ? 255 : (int)av;  // c_max >= 0 always; trunc toward zero, saturate
+    const uint32_t col = __ldg(a.color_lut + (k_max % 20) * 256 + alpha);
+    const size_t gp = (size_t)img * plane + pix;
+    if (a.class_map) a.class_map[gp] = (uint8_t)k_max;
+    a.decoded[gp] = col;
+    if (a.frame_bgr && (a.blended || a.frame_rgba)) {
+      const uint8_t* f = a.frame_bgr + gp * 3;
+      const uint32_t fb = f[0], fg = f[1], fr = f[2];
+      if (a.frame_rgba) a.frame_rgba[gp] = fr | (fg << 8) | (fb << 16) | 0xff000000u;
+      if (a.blended) {
+        const uint32_t ia = 255u - (col >> 24);
+        const uint32_t r = min(255u, (col & 0xff) + (fr * ia + 127u) / 255u);
+        const uint32_t g = min(255u, ((col >> 8) & 0xff) + (fg * ia + 127u) / 255u);
+        const uint32_t b = min(255u, ((col >> 16) & 0xff) + (fb * ia + 127u) / 255u);
+        a.blended[gp] = r | (g << 8) | (b << 16) | 0xff000000u;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) color_code_kernel(const float* __restrict__ hm, int k, size_t npix, const uint32_t* __restrict__ lut,
+                                                          uint32_t* __restrict__ rgba, uint8_t* __restrict__ class_map) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  int k_max = 0;
+  float c_max = 0.f;
+  for (int c = 0; c < k; ++c) {
+    const float v = __ldg(hm + (size_t)c * npix + i);
+    if (v > c_max) { k_max = c; c_max = v; }
+  }
+  const float av = __fmul_rn(c_max, 255.0f);
+  const int alpha = av >= 255.0f ? 255 : (int)av;
+  rgba[i] = __ldg(lut + (k_max % 20) * 256 + alpha);
+  if (class_map) class_map[i] = (uint8_t)k_max;
+}
+
+__global__ void __launch_bounds__(256) frame_rgba_kernel(const uint8_t* __restrict__ bgr, size_t npix, uint32_t* __restrict__ rgba) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const uint8_t* f = bgr + i * 3;
+  rgba[i] = (uint32_t)f[2] | ((uint32_t)f[1] << 8) | ((uint32_t)f[0] << 16) | 0xff000000u;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) direct_conv_kernel(DirectConvArgs a) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)a.n * a.oh * a.ow * a.cout;
+  if (idx >= total) return;
+  const int co = (int)(idx % a.cout);
+  size_t t = idx / a.cout;
+  const int ox = (int)(t % a.ow); t /= a.ow;
+  const int oy = (int)(t % a.oh);
+  const int img = (int)(t / a.oh);
+  float acc = 0.f;
+  for (int ky = 0; ky < a.kh; ++ky) {
+    const int iy = oy * a.stride + ky * a.dil - a.pad;
+    if (iy < 0 || iy >= a.h) continue;
+    for (int kx = 0; kx < a.kw; ++kx) {
+      const int ix = ox * a.stride + kx * a.dil - a.pad;
+      if (ix < 0 || ix >= a.wd) continue;
+      const __half* xp = a.x + (((size_t)img * a.x_rows + (iy + a.x_off_y)) * a.x_pitch_px + (ix + a.x_off_x)) * a.x_c;
+      const __half* wp = a.w + (((size_t)co * a.kh + ky) * a.kw + kx) * a.cin;
+      for (int ci = 0; ci < a.cin; ++ci) acc = fmaf(__half2float(xp[ci]), __half2float(wp[ci]), acc);
+    }
+  }
+  acc += a.bias[co];
+  const size_t o = (((size_t)img * a.oh + oy) * a.ow + ox) * a.out_ld + co;
+  if (a.residual) acc += __half2float(a.residual[o]);
+  if (a.relu) acc = fmaxf(acc, 0.f);
+  if (a.y_f32) a.y_f32[o] = acc;
+  else a.y[o] = __float2half_rn(acc);
+}
+
+}  // namespace
+
+cudaError_t launch_pre(const PreArgs& a, cudaStream_t s) {
+  const int pitch = stem_pitch_px(a.ow), rows = stem_rows(a.oh);
+  const bool unit = a.xmap == nullptr && a.ymap == nullptr && a.scaled_bgr == nullptr && a.stem_in != nullptr && (a.w % 4) == 0 &&
+                    a.oh == a.h && a.ow == a.w;
+  if (unit) {
+    dim3 grid((a.w / 4 + 255) / 256, a.h, a.n);
+    pre_unit_vec4_kernel<<<grid, 256, 0, s>>>(a, pitch, rows);
+  } else {
+    dim3 grid((a.ow + 255) / 256, a.oh, a.n);
+    pre_generic_kernel<<<grid, 256, 0, s>>>(a, pitch, rows);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_preprocess_f32(const uint8_t* bgr, int h, int w, const float* lut_f, float* out, cudaStream_t s) {
+  const size_t npix = (size_t)h * w;
+  preprocess_f32_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(bgr, h, w, lut_f, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool(const __half* in, __half* out, int n, int h, int w, int c, int oh, int ow, int k, int stride, int pad,
+                           cudaStream_t s) {
+  const size_t total = (size_t)n * oh * ow * (c / 8);
+  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, n, h, w, c / 8, oh, ow, k, stride, pad);
+  return cudaGetLastError();
+}
+
+size_t post_smem_bytes(const PostArgs& a) {
+  return ((size_t)a.max_lr * a.max_lc * post_pad(a.k) + (size_t)a.k * a.max_lr * kPostTile) * sizeof(float);
+}
+
+cudaError_t launch_post(const PostArgs& a, cudaStream_t s) {
+  const size_t smem = post_smem_bytes(a);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid((a.ow + kPostTile - 1) / kPostTile, (a.oh + kPostTile - 1) / kPostTile, a.n);
+  post_kernel<<<grid, 128, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_color_code(const float* hm, int k, int h, int w, const uint32_t* color_lut, uint32_t* rgba, uint8_t* class_map,
+                              cudaStream_t s) {
+  const size_t npix = (size_t)h * w;
+  if (npix == 0) return cudaSuccess;
+  color_code_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(hm, k, npix, color_lut, rgba, class_map);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_frame_rgba(const uint8_t* bgr, size_t npix, uint32_t* rgba, cudaStream_t s) {
+  if (npix == 0) return cudaSuccess;
+  frame_rgba_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(bgr, npix, rgba);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_direct_conv(const DirectConvArgs& a, cudaStream_t s) {
+  const size_t total = (size_t)a.n * a.oh * a.ow * a.cout;
+  direct_conv_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace infur

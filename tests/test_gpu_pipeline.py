@@ -1,0 +1,147 @@
+"""GPU: the whole Scale -> Model -> ColorCode path through the C ABI against the oracle.
+
+Parity bar (DESIGN.md "Parity"): Scale / pre-processing / ColorCode / colour table are bit-exact.  The network
+computes in fp16 with f32 accumulation, so against the oracle with the same rounding points
+(oracle.fcn.forward_lowres_fp16emu) the class map must agree on >= 99.5 % of pixels and every disagreeing pixel must
+be a near-tie of the oracle (top-2 margin < 0.05 logits); decoded RGBA is within +-1 u8 wherever the class agrees."""
+import numpy as np
+import pytest
+
+import oracle
+from infur_b200 import _lib as L
+from infur_b200 import processors as P
+from infur_b200 import synth
+from oracle import fcn
+
+pytestmark = pytest.mark.gpu
+
+MARGIN = 0.05
+
+
+def check_against_oracle(out_class, out_rgba, ref, min_match):
+    same = out_class == ref["class_map"]
+    match = same.mean()
+    lg = np.sort(ref["logits"], axis=0)
+    margin = lg[-1] - np.maximum(lg[-2], 0.0)   # the scan starts from 0.0, so 0 competes too
+    assert match >= min_match, f"class map agreement {match:.5f}"
+    if (~same).any():
+        assert margin[~same].max() < MARGIN, f"a disagreeing pixel has oracle margin {margin[~same].max():.4f}"
+    d = np.abs(out_rgba.astype(np.int32) - ref["decoded_rgba"].astype(np.int32))[same]
+    assert d.max() <= 1
+    return match
+
+
+@pytest.mark.parametrize("factor,w,h", [(1.0, 320, 240), (0.5, 640, 480), (1.0, 200, 136)])
+def test_pipeline_tiny(handle, tiny, factor, w, h):
+    path, model = tiny
+    pipe = P.GpuPipeline(handle)
+    pipe.control(("Model", path))
+    pipe.control(("Scale", factor))
+    frame = synth.synth_frame(w, h, 2)
+    g = pipe.advance(P.Frame(11, frame))
+    ref = fcn.pipeline(model, frame, factor, emulate_fp16=True)
+    assert g.id == 11 and g.size == [ref["scaled_bgr"].shape[1], ref["scaled_bgr"].shape[0]]
+    assert (g.buffer == ref["frame_rgba"]).all()
+    check_against_oracle(g.class_map, g.decoded_buffer, ref, 0.995)
+    assert (g.blended == oracle.blend_over(g.decoded_buffer, g.buffer)).all()
+    pipe.control(("Scale", 1.0))
+
+
+def test_pipeline_fcn50_config1(handle, fcn50):
+    """configs[0] analogue: 320x240 synthetic clip, scale 1.0, FCN-ResNet50."""
+    path, model = fcn50
+    handle.model_load(path)
+    handle.scale_control(1.0)
+    frames = np.stack([synth.synth_frame(320, 240, i) for i in range(4)])
+    res = handle.advance_batch(frames, ids=[1, 2, 3, 4])
+    for i, r in enumerate(res):
+        ref = fcn.pipeline(model, frames[i], 1.0, emulate_fp16=True)
+        check_against_oracle(r["class_map"], r["decoded_rgba"], ref, 0.995)
+        ref32 = fcn.pipeline(model, frames[i], 1.0, emulate_fp16=False)
+        assert (r["class_map"] == ref32["class_map"]).mean() > 0.98   # vs the pure fp32 oracle
+
+
+def test_infer_seg_model(handle, fcn50):
+    """predict_onnx.rs:356-381: load, info, zero 320x240 image -> two outputs of [21,240,320]."""
+    path, model = fcn50
+    m = P.Model(handle)
+    m.control(path)
+    info = m.get_info()
+    assert info.input_names == ["input"] and info.input0_dtype == "Float" and info.output_names == ["out", "aux"]
+    out = m.advance(np.zeros((240, 320, 3), np.uint8), [])
+    assert len(out) == 2
+    for t in out:
+        assert t.shape == (21, 240, 320) and t.dtype == np.float32
+    ref = fcn.pipeline(model, np.zeros((240, 320, 3), np.uint8), 1.0, emulate_fp16=True)
+    assert np.abs(out[0] - ref["logits"]).max() < 0.05 * max(1.0, np.abs(ref["logits"]).max())
+
+
+def test_model_load_errors_keep_previous(handle, tiny, tmp_path):
+    path, _ = tiny
+    handle.model_load(path)
+    bad = tmp_path / "bad.onnx"
+    bad.write_bytes(b"not an onnx file at all")
+    with pytest.raises(P.ModelCmdError):
+        handle.model_load(str(bad))
+    with pytest.raises(P.ModelCmdError):
+        handle.model_load(str(tmp_path / "missing.onnx"))
+    assert handle.model_info() is not None          # previous model stays (predict_onnx.rs:289-308)
+    handle.model_load("")                           # "" unloads (:310-312)
+    assert handle.model_info() is None
+    m = P.Model(handle)
+    assert m.advance(np.zeros((8, 8, 3), np.uint8), "untouched") == "untouched"
+    r = handle.advance(synth.synth_frame(64, 48, 0), 5)
+    assert r["has_decoded"] is False and r["decoded_rgba"] is None   # decoded_img = None (app.rs:127-129)
+    assert (r["frame_rgba"] == oracle.frame_rgba(synth.synth_frame(64, 48, 0))).all()
+
+
+def test_batch_equals_single_and_ring(handle, tiny):
+    path, _ = tiny
+    handle.model_load(path)
+    handle.scale_control(1.0)
+    frames = np.stack([synth.synth_frame(160, 120, i) for i in range(5)])
+    batch = handle.advance_batch(frames, ids=list(range(1, 6)))
+    for i in range(5):
+        one = handle.advance(frames[i], i + 1)
+        assert (one["class_map"] == batch[i]["class_map"]).all() and (one["decoded_rgba"] == batch[i]["decoded_rgba"]).all()
+    tickets = []
+    for s in range(3):                               # ring_depth = 3 slots in flight
+        t, view = handle.ring_acquire(5, 160, 120)
+        view[...] = np.roll(frames, s, axis=0)
+        handle.ring_submit(t)
+        tickets.append(t)
+    with pytest.raises(P.InfurError) as e:
+        handle.ring_acquire(5, 160, 120)
+    assert e.value.code == L.E_TICKET
+    for s, t in enumerate(tickets):
+        r = handle.ring_wait(t)
+        for i in range(5):
+            j = (i - s) % 5
+            assert (r["class_map"][i] == batch[j]["class_map"]).all() and (r["decoded_rgba"][i] == batch[j]["decoded_rgba"]).all()
+
+
+def test_validate_impl_agrees(tiny):
+    """The tcgen05 path against the CUDA-core validation path on the same frame (independent arithmetic order)."""
+    path, _ = tiny
+    frame = synth.synth_frame(192, 128, 4)
+    outs = []
+    for impl in (L.CONV_VALIDATE, L.CONV_TCGEN05):
+        with P.Handle(max_batch=1, conv_impl=impl) as h:
+            h.model_load(path)
+            outs.append(h.advance(frame, 1, want=("class_map", "logits_f32")))
+    assert (outs[0]["class_map"] == outs[1]["class_map"]).mean() > 0.995
+    assert np.abs(outs[0]["logits_f32"] - outs[1]["logits_f32"]).max() < 0.05
+
+
+def test_switch_scale_sizes(handle, tiny):
+    """app.rs:174-235 sizes: [w*f, h*f] for f in {0.5, 1, 2} and re-scaling the same frame when dirty."""
+    path, _ = tiny
+    pipe = P.GpuPipeline(handle)
+    pipe.control(("Model", path))
+    frame = P.Frame(1, synth.synth_frame(160, 90, 0))
+    for f, size in ((0.5, [80, 45]), (1.0, [160, 90]), (2.0, [320, 180])):
+        pipe.control(("Scale", f))
+        g = pipe.advance(frame)
+        assert g.size == size and g.decoded_buffer.shape[:2] == (size[1], size[0])
+        assert not pipe.is_dirty()
+    pipe.control(("Scale", 1.0))
