@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Headline benchmark: 1080p frames/s through Scale -> FCN-ResNet50 -> ColorCode (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One *step* = one batch of ``--batch`` (default 8) synthetic 1920x1080 BGR frames through the whole hot path
+(``configs[2]``: "1080p stream, batch=8 frames, 1xB200, pinned ring buffer"; the single-frame ``configs[1]``
+latency is reported beside it as ``single_frame``).  For N > 1 the driver launches one rank per GPU with
+torchrun; frames are sharded by rank (weak scaling: every rank runs its own batch, no collective on the
+frame path; the packed weights are NCCL-broadcast from rank 0 at load).
+
+Printed by rank 0 as ONE JSON line:
+  value         frames/s, inputs already resident in HBM (``infur_b200_advance_device``), CUDA events on the
+                library's compute stream, max over ranks
+  e2e           frames/s through the pinned ring (``ring_acquire`` / ``ring_submit`` / ``ring_wait``): host memcpy
+                of every frame into the pinned slot, H2D, the path, D2H of class map + RGBA, all inside the timed
+                region
+  roofline      the tcgen05 implicit-GEMM conv kernel (all 55 conv launches of one step): algorithmic conv FLOPs
+                / summed CUDA-event time of those launches, against the measured bf16 peak
+  cpu_baseline  the oracle pipeline (PyTorch-CPU fp32 + numpy) on the box's host cores, bounded sample
+``--impl reference`` times that CPU pipeline alone (the reference's onnxruntime path cannot be built here:
+no Rust, no onnxruntime, no model file -- see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+FLOPS_NO_AUX = {(1920, 1080): 2189.025e9}   # 2 x MACs of the 55 convs of the `out` head
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_pipeline_fps(frames: np.ndarray, model, threads: int, reps: int) -> tuple[float, float]:
+    """The oracle restatement of the reference path (Scale 1.0 -> pre-process -> FCN-ResNet50 fp32, both heads and
+    both full-resolution Resize ops as ONNX Runtime executes them -> ColorCode on `out`), PyTorch-CPU + numpy."""
+    import torch
+    import torch.nn.functional as F
+
+    import oracle
+
+    torch.set_num_threads(threads)
+    model.eval()
+    times = []
+    with torch.no_grad():
+        for i in range(reps + 1):
+            bgr = frames[i % len(frames)]
+            t0 = time.perf_counter()
+            scaled = oracle.scale_nearest(bgr, 1.0)
+            x = torch.from_numpy(oracle.preprocess_f32(scaled)[None])
+            feats = model.backbone(x)
+            out = F.interpolate(model.classifier(feats["out"]), size=x.shape[-2:], mode="bilinear", align_corners=False)
+            if model.aux_classifier is not None:
+                F.interpolate(model.aux_classifier(feats["aux"]), size=x.shape[-2:], mode="bilinear", align_corners=False)
+            oracle.color_code_image(out[0].numpy())
+            oracle.frame_rgba(scaled)
+            dt = time.perf_counter() - t0
+            if i > 0:   # first frame = warm-up
+                times.append(dt)
+    med = float(np.median(times))
+    return 1.0 / med, med
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    from infur_b200 import synth
+
+    cores = os.cpu_count() or 1
+    _, model = synth.ensure_fixture("fcn50")
+    frames = np.stack([synth.synth_frame(W, H, i) for i in range(2)])
+    import torch
+    import torch.nn.functional as F
+
+    import oracle
+
+    torch.set_num_threads(cores)
+    model.eval()
+
+    def one(i):
+        with torch.no_grad():
+            bgr = frames[i % len(frames)]
+            scaled = oracle.scale_nearest(bgr, 1.0)
+            x = torch.from_numpy(oracle.preprocess_f32(scaled)[None])
+            feats = model.backbone(x)
+            out = F.interpolate(model.classifier(feats["out"]), size=x.shape[-2:], mode="bilinear", align_corners=False)
+            F.interpolate(model.aux_classifier(feats["aux"]), size=x.shape[-2:], mode="bilinear", align_corners=False)
+            oracle.color_code_image(out[0].numpy())
+            oracle.frame_rgba(scaled)
+
+    for i in range(args.warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    sample = f"{args.steps} single 1920x1080 frames (one frame per step), torch-CPU fp32 FCN-ResNet50 both heads + numpy Scale/ColorCode"
+    print(json.dumps({
+        "impl": "reference", "metric": "1080p frames/sec through FCN-ResNet50", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1080p synthetic stream, FCN-ResNet50 (seeded synthetic weights), scale 1.0; CPU restatement of the reference's "
+                               "onnxruntime path (the reference itself cannot be built here: no Rust/onnxruntime/model file)", "frames_per_step": 1},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    from infur_b200 import processors as P
+    from infur_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    B = args.batch
+    path = synth.fixture_path("fcn50")
+    if rank == 0 and not os.path.exists(path):
+        synth.ensure_fixture("fcn50")
+    barrier()
+
+    h = P.Handle(device=local_rank, max_batch=B, ring_depth=args.ring_depth)
+    # weights: rank 0 packs + uploads, every other rank receives the packed arena over NCCL (init only)
+    h.model_load(path, skip_weights=(rank != 0))
+    if world > 1:
+        nbytes = h.weights_size()
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            h.weights_export(blob.data_ptr(), nbytes)
+        torch.cuda.synchronize()
+        dist.broadcast(blob, 0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            h.weights_import(blob.data_ptr(), nbytes)
+        del blob
+    h.scale_control(1.0)
+
+    # synthetic frames: nsets batches of B distinct frames per rank (input set 4 x 8 x 6.2 MB = 199 MB > 126 MB L2;
+    # one step also streams > 30 GB of activations through HBM, so nothing survives in L2 between steps)
+    nsets = 4
+    base = np.stack([synth.synth_frame(W, H, rank * 64 + i) for i in range(B)])
+    host_sets = [np.ascontiguousarray(np.roll(base, s, axis=0)) for s in range(nsets)]
+    d_sets = [torch.from_numpy(x).to(dev) for x in host_sets]
+    d_class = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    d_rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.ExternalStream(h.compute_stream(), device=dev)
+
+    def step_device(i):
+        h.advance_device(d_sets[i % nsets].data_ptr(), B, W, H, d_class.data_ptr(), d_rgba.data_ptr())
+
+    # ---- value: device-resident
+    for i in range(args.warmup):
+        step_device(i)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = h.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    e1.record(stream)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    launches = h.launch_count() - l0
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: pinned ring, host buffers in and out
+    depth = args.ring_depth
+    sink = np.zeros(2, dtype=np.int64)
+
+    def run_ring(nsteps):
+        inflight = []
+        for i in range(nsteps):
+            if len(inflight) == depth:
+                r = h.ring_wait(inflight.pop(0))
+                sink[0] += int(r["class_map"][0, 0, 0]); sink[1] += int(r["decoded_rgba"][B - 1, H - 1, W - 1, 3])
+            t, view = h.ring_acquire(B, W, H)
+            np.copyto(view, host_sets[i % nsets])      # the frame source writes into pinned memory
+            h.ring_submit(t)
+            inflight.append(t)
+        for t in inflight:
+            r = h.ring_wait(t)
+            sink[0] += int(r["class_map"][0, 0, 0]); sink[1] += int(r["decoded_rgba"][B - 1, H - 1, W - 1, 3])
+
+    run_ring(max(args.warmup, depth))
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    run_ring(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = world * B * args.steps / e2e_s
+
+    # ---- single-frame latency (configs[1]) and per-kernel roofline, rank 0 only, outside the timed regions
+    out = None
+    if rank == 0:
+        pk = peaks()
+        one = np.ascontiguousarray(base[0])
+        h.advance(one, 1)
+        lat = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            h.advance(one, 1, want=("class_map", "decoded_rgba"))
+            lat.append(time.perf_counter() - t0)
+        plan = h.plan_text(B, W, H).splitlines()
+        op_lines = [ln for ln in plan if ln.startswith("conv ") or ln.startswith("maxpool ")]
+        op_ms = h.profile_ops(d_sets[0].data_ptr(), B, W, H, iters=max(2, min(args.steps, 5)))
+        conv_ms = sum(m for ln, m in zip(op_lines, op_ms) if ln.startswith("conv "))
+        n_conv = sum(1 for ln in op_lines if ln.startswith("conv "))
+        flops = B * FLOPS_NO_AUX[(W, H)]
+        achieved = flops / (conv_ms * 1e-3) / 1e12
+        roofline = {
+            "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv+bias+ReLU(+residual)), all %d launches of one step" % n_conv,
+            "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+            "flops_per_launch_avg": flops / n_conv, "ms_per_launch_avg": conv_ms / n_conv, "ms_all_launches": conv_ms,
+            "peak_source": pk["source"] + " (sustained cuBLAS bf16: the kernel is timed inside a long step)",
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            _, model = synth.ensure_fixture("fcn50")
+            cores = os.cpu_count() or 1
+            fps_cpu, sec = cpu_pipeline_fps(base[:2], model, cores, reps=args.cpu_frames)
+            cpu = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_frames} single 1920x1080 frames after 1 warm-up (median {sec:.2f} s/frame); oracle port: torch-CPU fp32 "
+                             "FCN-ResNet50 both heads + numpy Scale/ColorCode"}
+        out = {
+            "metric": "1080p frames/sec through FCN-ResNet50", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "configs[2]: 1080p synthetic stream, batch=8 frames per step per GPU, FCN-ResNet50 (seeded synthetic weights "
+                                   "in an opset-12 .onnx), scale 1.0, out head only, class map + premultiplied RGBA out",
+                       "frames_per_step_per_gpu": B, "width": W, "height": H, "ring_depth": depth, "sharding": "frames by rank, no collective",
+                       "l2": "inputs cycle through 4 x 8 distinct frames (199 MB) and each step streams > 30 GB of activations: larger than L2"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * W * H * 3, "d2h_bytes_per_step": B * W * H * 5,
+                    "api": "infur_b200_ring_acquire/submit/wait, host memcpy into the pinned slot inside the timed region"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "single_frame": {"workload": "configs[1]: one 1080p frame, synchronous infur_b200_advance, host buffers", "ms": 1e3 * float(np.median(lat))},
+        }
+    h.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--ring-depth", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
