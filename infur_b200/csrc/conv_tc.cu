@@ -7,8 +7,12 @@
 //                              of two TMEM accumulator stages; tcgen05.commit releases the smem stage
 //   warp 2    TMEM allocator
 //   warps 4-7 epilogue       - tcgen05.ld the finished accumulator (thread = output pixel), + bias
-//                              (+ residual) (ReLU) -> fp16 NHWC (or f32 logits), overlapping the next
-//                              tile's MMAs through the second accumulator stage
+//                              (+ residual) (ReLU) -> fp16, overlapping the next tile's MMAs through the
+//                              second accumulator stage.  fp16 outputs are staged per 64-channel chunk in
+//                              128B-swizzled smem and written with TMA stores (which also clip tiles that
+//                              overhang the image); the residual chunk is TMA-prefetched into the same
+//                              buffer up to 4 chunks ahead, so the HBM traffic of the epilogue is fully
+//                              asynchronous.  The f32 logit head (21 channels) uses direct stores.
 #include "conv_tc.h"
 #include "ptx.cuh"
 
@@ -22,28 +26,226 @@ constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
 
+constexpr int kMaxStages = 8;
+constexpr int kEpiBufBytes = kBlockM * 64 * 2;      // one 64-channel output chunk: 128 rows x 128 B
+constexpr int kMaxEpiBufs = 4;
+constexpr int kSmemLimit = 232448;                  // 227 KB per CTA
+constexpr int kBarBytes = 256;
+
 template <int BLOCK_N>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulator stages; power of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  // epilogue buffers: 0 (direct stores), 2 (TMA store), 4 (TMA store + TMA residual prefetch)
+  static constexpr int stages(int epi_bufs) {
+    int s = (kSmemLimit - 1024 - kBarBytes - epi_bufs * kEpiBufBytes) / kStageBytes;
+    return s > kMaxStages ? kMaxStages : s;
+  }
+  static constexpr int smem_bytes(int epi_bufs) { return stages(epi_bufs) * kStageBytes + epi_bufs * kEpiBufBytes + 1024 + kBarBytes; }
 };
+
+struct TileCoord { int nt, ox0, oy0, img; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcGeom& g, int tile) {
+  TileCoord t;
+  t.nt = tile % g.tiles_n;
+  int m = tile / g.tiles_n;
+  const int tx = m % g.tiles_x; m /= g.tiles_x;
+  const int ty = m % g.tiles_y;
+  t.img = m / g.tiles_y;
+  t.ox0 = tx << g.bw_log2;
+  t.oy0 = ty * (kBlockM >> g.bw_log2);
+  return t;
+}
+
+// Direct-store epilogue (f32 logit head): thread = output pixel, 32 channels at a time.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int quad, int lane,
+                                                int row) {
+  const int bw_log2 = g.bw_log2;
+  const int px = row & ((1 << bw_log2) - 1), py = row >> bw_log2;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+    const TileCoord tc = decode_tile(g, tile);
+    const int ox = tc.ox0 + px, oy = tc.oy0 + py;
+    const bool valid = ox < g.ow && oy < g.oh;
+    const size_t pix = ((size_t)tc.img * g.oh + oy) * g.ow + ox;
+    const int n0 = tc.nt * BLOCK_N;
+    const int as = it & 1;
+    const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+    ptx::mbar_wait(tfull0 + 8u * as, aphase);
+    ptx::tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t acc[32];
+      ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, acc);
+      ptx::tmem_ld_wait();
+      if (valid) {
+        const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+          v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+          v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+          v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+        }
+        const size_t off = pix * (size_t)g.out_ld + (size_t)(n0 + c0);
+        if (g.residual != nullptr) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(g.residual + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 r = __ldg(r4 + j);
+            const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(h[q]);
+              v[8 * j + 2 * q] += f.x;
+              v[8 * j + 2 * q + 1] += f.y;
+            }
+          }
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (g.out_f32 != nullptr) {
+          float4* o4 = reinterpret_cast<float4*>(g.out_f32 + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          uint4* o4 = reinterpret_cast<uint4*>(g.out + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+            o4[j] = o;
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(tempty0 + 8u * as);
+  }
+}
+
+// TMA-staged epilogue for fp16 NHWC outputs.  The tile's output is produced in 64-channel chunks; chunk q of
+// this CTA (running count over all its tiles) lives in smem buffer q % EB as 128 rows (pixels) x 128 B with
+// the 128B swizzle the tensor maps expect.  HAS_RES: the residual chunk is TMA-loaded into the buffer ahead
+// of time (up to EB chunks in flight), the sum is written back in place and TMA-stored.  One elected thread
+// (the leader) issues every bulk copy, so bulk-group accounting stays in one thread.
+template <int BLOCK_N, bool HAS_RES>
+__device__ __forceinline__ void epilogue_tma(const ConvTcMaps& maps, const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                             uint32_t res0, uint32_t epi_base, int quad, int lane, int row) {
+  constexpr int CH = BLOCK_N / 64;            // chunks per tile
+  constexpr int EB = HAS_RES ? 4 : 2;         // smem chunk buffers
+  const bool leader = quad == 0 && lane == 0;
+  const int my_tiles = (int)blockIdx.x < g.num_tiles ? (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total = my_tiles * CH;
+  auto issue_res = [&](int qq) {
+    const TileCoord tc = decode_tile(g, (int)blockIdx.x + (qq / CH) * (int)gridDim.x);
+    const int b = qq % EB;
+    ptx::mbar_expect_tx(res0 + 8u * b, (uint32_t)kEpiBufBytes);
+    ptx::tma_load_4d(epi_base + b * kEpiBufBytes, &maps.r, res0 + 8u * b, tc.nt * BLOCK_N + (qq % CH) * 64, tc.ox0, tc.oy0, tc.img);
+  };
+  if (HAS_RES && leader) {
+    for (int p = 0; p < EB && p < total; ++p) issue_res(p);
+  }
+  const uint32_t sw = (uint32_t)(row & 7);
+  int q = 0, it = 0;
+  for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+    const TileCoord tc = decode_tile(g, tile);
+    const int n0 = tc.nt * BLOCK_N;
+    const int as = it & 1;
+    const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+    ptx::mbar_wait(tfull0 + 8u * as, aphase);
+    ptx::tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
+#pragma unroll 1
+    for (int c = 0; c < CH; ++c, ++q) {
+      const int b = q % EB;
+      const uint32_t rowp = epi_base + b * kEpiBufBytes + (uint32_t)row * 128u;
+      uint32_t acc[64];
+      ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+      ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+      ptx::tmem_ld_wait();
+      if (c == CH - 1) {   // accumulator stage fully read: hand it back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty0 + 8u * as);
+      }
+      if (HAS_RES) ptx::mbar_wait(res0 + 8u * b, (uint32_t)(q / EB) & 1u);
+      const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0 + c * 64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {            // 16-byte group j = channels 8j .. 8j+7 of this pixel
+        const uint32_t addr = rowp + (((uint32_t)j ^ sw) << 4);
+        const float4 bl = __ldg(b4 + 2 * j), bh = __ldg(b4 + 2 * j + 1);
+        float v[8];
+        v[0] = __uint_as_float(acc[8 * j + 0]) + bl.x; v[1] = __uint_as_float(acc[8 * j + 1]) + bl.y;
+        v[2] = __uint_as_float(acc[8 * j + 2]) + bl.z; v[3] = __uint_as_float(acc[8 * j + 3]) + bl.w;
+        v[4] = __uint_as_float(acc[8 * j + 4]) + bh.x; v[5] = __uint_as_float(acc[8 * j + 5]) + bh.y;
+        v[6] = __uint_as_float(acc[8 * j + 6]) + bh.z; v[7] = __uint_as_float(acc[8 * j + 7]) + bh.w;
+        if (HAS_RES) {
+          uint4 r;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+          const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(h[t]);
+            v[2 * t] += f.x;
+            v[2 * t + 1] += f.y;
+          }
+        }
+        if (g.relu) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+        }
+        uint4 o;
+        __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+      }
+      ptx::fence_proxy_async_smem();
+      // without a residual nobody else signals that buffer (q+1) % EB is free again: the leader makes sure every
+      // earlier store has been read out of smem before the barrier that releases the other threads
+      if (!HAS_RES && leader) ptx::tma_store_wait_read<0>();
+      ptx::named_bar_sync(1, 128);
+      if (leader) {
+        ptx::tma_store_4d(&maps.c, epi_base + b * kEpiBufBytes, n0 + c * 64, tc.ox0, tc.oy0, tc.img);
+        ptx::tma_store_commit();
+        if (HAS_RES && q >= 1 && q - 1 + EB < total) {
+          ptx::tma_store_wait_read<1>();        // the store of chunk q-1 has left its buffer
+          issue_res(q - 1 + EB);
+        }
+      }
+    }
+  }
+  if (leader) ptx::tma_store_wait_read<0>();
+}
+
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
+  const int num_stages = g.stages;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
-  // barrier block: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+  const uint32_t epi_base = smem_base + num_stages * C::kStageBytes;          // 1024-aligned: stage sizes are multiples of 4 KB
+  const uint32_t bar_base = epi_base + g.epi_bufs * kEpiBufBytes;
+  // barrier block: full[8], empty[8], tmem_full[2], tmem_empty[2], res_full[4], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * C::kStages + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto res_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 4 + kMaxEpiBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -52,10 +254,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   if (warp == 0 && ptx::elect_one()) {
     for (int v = 0; v < kMaxViews; ++v) ptx::prefetch_tmap(&maps.a[v]);
     ptx::prefetch_tmap(&maps.b);
+    if (g.store_mode != 0) ptx::prefetch_tmap(&maps.c);
+    if (g.store_mode == 2) ptx::prefetch_tmap(&maps.r);
   }
   if (warp == 1 && ptx::elect_one()) {
-    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < num_stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < kMaxEpiBufs; ++s) ptx::mbar_init(res_bar(s), 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -94,7 +299,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
             ptx::mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
             ptx::tma_load_4d(a_dst, am, full_bar(stage), cc * kBlockK, x, y, img);
             ptx::tma_load_2d(a_dst + kABytes, &maps.b, full_bar(stage), kb * kBlockK, nt * BLOCK_N);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            if (++stage == num_stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -124,7 +329,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
             ptx::umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
           ptx::umma_commit(empty_bar(stage));
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
         }
         ptx::umma_commit(tfull_bar(as));
       }
@@ -133,78 +338,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     // ===================== epilogue =====================
     const int quad = warp - kEpiWarp0;       // == warp % 4: the TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;        // accumulator row = pixel inside the tile
-    const int px = row & (bw - 1), py = row >> bw_log2;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile % g.tiles_n;
-      int m = tile / g.tiles_n;
-      const int tx = m % g.tiles_x; m /= g.tiles_x;
-      const int ty = m % g.tiles_y;
-      const int img = m / g.tiles_y;
-      const int ox = (tx << bw_log2) + px, oy = ty * bh + py;
-      const bool valid = ox < g.ow && oy < g.oh;
-      const size_t pix = ((size_t)img * g.oh + oy) * g.ow + ox;
-      const int n0 = nt * BLOCK_N;
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      ptx::mbar_wait(tfull_bar(as), aphase);
-      ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t acc[32];
-        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, acc);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
-            v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
-            v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
-            v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
-          }
-          const size_t off = pix * (size_t)g.out_ld + (size_t)(n0 + c0);
-          if (g.residual != nullptr) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(g.residual + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 r = __ldg(r4 + j);
-              const __half2* h = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = __half22float2(h[q]);
-                v[8 * j + 2 * q] += f.x;
-                v[8 * j + 2 * q + 1] += f.y;
-              }
-            }
-          }
-          if (g.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (g.out_f32 != nullptr) {
-            float4* o4 = reinterpret_cast<float4*>(g.out_f32 + off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(g.out + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              __half2* h = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
-              o4[j] = o;
-            }
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+    if (g.store_mode == 0) {
+      epilogue_direct<BLOCK_N>(g, tmem_base, tfull_bar(0), tempty_bar(0), quad, lane, row);
+    } else if constexpr (BLOCK_N >= 64) {
+      if (g.store_mode == 1) epilogue_tma<BLOCK_N, false>(maps, g, tmem_base, tfull_bar(0), tempty_bar(0), res_bar(0), epi_base, quad, lane, row);
+      else epilogue_tma<BLOCK_N, true>(maps, g, tmem_base, tfull_bar(0), tempty_bar(0), res_bar(0), epi_base, quad, lane, row);
     }
   }
 
@@ -220,27 +358,28 @@ template <int BLOCK_N>
 cudaError_t launch_one(const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream) {
   const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
   if (grid <= 0) return cudaSuccess;
-  conv_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg<BLOCK_N>::kSmemBytes, stream>>>(maps, g);
+  if (g.stages != Cfg<BLOCK_N>::stages(g.epi_bufs) || (g.store_mode != 0 && BLOCK_N < 64)) return cudaErrorInvalidValue;
+  conv_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream>>>(maps, g);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-int conv_tc_stages(int block_n) {
+int conv_tc_stages(int block_n, int epi_bufs) {
   switch (block_n) {
-    case 32: return Cfg<32>::kStages;
-    case 64: return Cfg<64>::kStages;
-    case 128: return Cfg<128>::kStages;
-    default: return Cfg<256>::kStages;
+    case 32: return Cfg<32>::stages(epi_bufs);
+    case 64: return Cfg<64>::stages(epi_bufs);
+    case 128: return Cfg<128>::stages(epi_bufs);
+    default: return Cfg<256>::stages(epi_bufs);
   }
 }
 
 cudaError_t conv_tc_init() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::kSmemBytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmemBytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 

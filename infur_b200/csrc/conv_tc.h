@@ -26,7 +26,8 @@ struct ConvTcGeom {
   int32_t num_taps, cchunks;  // K blocks = num_taps * cchunks, 64 input channels each
   int32_t out_ld;             // elements between consecutive output pixels
   int32_t relu;
-  int32_t store_mode;         // 0: per-thread vector stores; 1: smem-staged TMA store (fp16 only)
+  int32_t store_mode;         // 0: per-thread vector stores (f32 head); 1: smem-staged TMA store; 2: + TMA residual prefetch
+  int32_t stages, epi_bufs;   // smem pipeline depth and epilogue chunk buffers (0 / 2 / 4), see conv_tc_stages
   const float* bias;          // [tiles_n * BLOCK_N]
   const __half* residual;     // NHWC like out, or nullptr
   __half* out;                // fp16 NHWC, or nullptr when out_f32 is used
@@ -39,13 +40,14 @@ struct ConvTcGeom {
 struct alignas(64) ConvTcMaps {
   CUtensorMap a[kMaxViews];  // activation views
   CUtensorMap b;             // weights [cout][K]
-  CUtensorMap c;             // output (store_mode 1)
+  CUtensorMap c;             // output (store_mode 1, 2): 4-D NHWC, box 64 channels x tile
+  CUtensorMap r;             // residual (store_mode 2), same geometry as c
 };
 
 // block_n in {32, 64, 128, 256}.  Returns cudaSuccess or the launch error.
 cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream);
 // One-time: opt in to the dynamic shared memory each instantiation needs.
 cudaError_t conv_tc_init();
-int conv_tc_stages(int block_n);
+int conv_tc_stages(int block_n, int epi_bufs);
 
 }  // namespace infur

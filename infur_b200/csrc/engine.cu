@@ -195,7 +195,10 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po) {
   g.tiles_n = d.cout_pad / d.block_n;
   g.num_tiles = io.n * g.tiles_x * g.tiles_y * g.tiles_n;
   g.num_taps = d.taps; g.cchunks = d.cchunks;
-  g.out_ld = io.out_ld; g.relu = d.relu ? 1 : 0; g.store_mode = 0;
+  g.out_ld = io.out_ld; g.relu = d.relu ? 1 : 0;
+  g.store_mode = io.y_f32 ? 0 : (io.residual ? 2 : 1);
+  g.epi_bufs = g.store_mode == 0 ? 0 : (g.store_mode == 1 ? 2 : 4);
+  g.stages = conv_tc_stages(d.block_n, g.epi_bufs);
   g.bias = io.bias; g.residual = io.residual; g.out = io.y; g.out_f32 = io.y_f32;
   Status st;
   const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
@@ -245,7 +248,18 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po) {
     st = make_tmap_f16(&po.maps.b, io.wgt, 2, dims, strides, bbox);
     if (!st.ok()) return st;
   }
-  po.maps.c = po.maps.b;
+  po.maps.c = po.maps.b; po.maps.r = po.maps.b;
+  if (g.store_mode != 0) {
+    // output / residual: NHWC fp16 [n][oh][ow][out_ld], stored (loaded) in 64-channel x tile boxes
+    const uint64_t dims[4] = {(uint64_t)d.cout, (uint64_t)io.ow, (uint64_t)io.oh, (uint64_t)io.n};
+    const uint64_t strides[3] = {(uint64_t)io.out_ld * 2, (uint64_t)io.ow * io.out_ld * 2, (uint64_t)io.oh * io.ow * io.out_ld * 2};
+    st = make_tmap_f16(&po.maps.c, io.y, 4, dims, strides, box);
+    if (!st.ok()) return st;
+    if (io.residual) {
+      st = make_tmap_f16(&po.maps.r, io.residual, 4, dims, strides, box);
+      if (!st.ok()) return st;
+    }
+  }
   return Status();
 }
 

