@@ -6,7 +6,9 @@
 //   warp 1    MMA issuer     - one elected lane issues 4 x tcgen05.mma (M128 x N x K16) per K block into one
 //                              of two TMEM accumulator stages; tcgen05.commit releases the smem stage
 //   warp 2    TMEM allocator
-//   warps 4-7 epilogue       - tcgen05.ld the finished accumulator (thread = output pixel), + bias
+//   warp 3    epilogue DMA   - one elected lane issues the TMA stores of finished output chunks and the TMA
+//                              prefetch of residual chunks (all bulk-group accounting in one thread)
+//   warps 4-11 epilogue      - tcgen05.ld the finished accumulator (thread = output pixel), + bias
 //                              (+ residual) (ReLU) -> fp16, overlapping the next tile's MMAs through the
 //                              second accumulator stage.  fp16 outputs are staged per 64-channel chunk in
 //                              128B-swizzled smem and written with TMA stores (which also clip tiles that
@@ -23,14 +25,16 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                         // fp16 elements = one 128-byte swizzle span
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kDmaWarp = 3;
 
 constexpr int kMaxStages = 8;
 constexpr int kEpiBufBytes = kBlockM * 64 * 2;      // one 64-channel output chunk: 128 rows x 128 B
 constexpr int kMaxEpiBufs = 4;
 constexpr int kSmemLimit = 232448;                  // 227 KB per CTA
-constexpr int kBarBytes = 256;
+constexpr int kBarBytes = 512;
 
 template <int BLOCK_N>
 struct Cfg {
@@ -136,64 +140,69 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 
 // TMA-staged epilogue for fp16 NHWC outputs.  The tile's output is produced in 64-channel chunks; chunk q of
 // this CTA (running count over all its tiles) lives in smem buffer q % EB as 128 rows (pixels) x 128 B with
-// the 128B swizzle the tensor maps expect.  HAS_RES: the residual chunk is TMA-loaded into the buffer ahead
-// of time (up to EB chunks in flight), the sum is written back in place and TMA-stored.  One elected thread
-// (the leader) issues every bulk copy, so bulk-group accounting stays in one thread.
+// the 128B swizzle the tensor maps expect.  Eight warps: warp ew owns TMEM lane quadrant ew % 4 (32 pixels) and
+// channel half ew / 4 (32 of the chunk's 64 channels).  HAS_RES: the residual chunk was TMA-loaded into the
+// buffer ahead of time by the DMA warp; the sum is written back in place.  No CTA-wide barrier: a warp
+// announces its part through the chunk_ready mbarrier and moves on.
+struct EpiBars { uint32_t res, ready, free_; };
+
 template <int BLOCK_N, bool HAS_RES>
-__device__ __forceinline__ void epilogue_tma(const ConvTcMaps& maps, const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                             uint32_t res0, uint32_t epi_base, int quad, int lane, int row) {
+__device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, const EpiBars eb,
+                                             uint32_t epi_base, int ew, int lane) {
   constexpr int CH = BLOCK_N / 64;            // chunks per tile
   constexpr int EB = HAS_RES ? 4 : 2;         // smem chunk buffers
-  const bool leader = quad == 0 && lane == 0;
-  const int my_tiles = (int)blockIdx.x < g.num_tiles ? (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int total = my_tiles * CH;
-  auto issue_res = [&](int qq) {
-    const TileCoord tc = decode_tile(g, (int)blockIdx.x + (qq / CH) * (int)gridDim.x);
-    const int b = qq % EB;
-    ptx::mbar_expect_tx(res0 + 8u * b, (uint32_t)kEpiBufBytes);
-    ptx::tma_load_4d(epi_base + b * kEpiBufBytes, &maps.r, res0 + 8u * b, tc.nt * BLOCK_N + (qq % CH) * 64, tc.ox0, tc.oy0, tc.img);
-  };
-  if (HAS_RES && leader) {
-    for (int p = 0; p < EB && p < total; ++p) issue_res(p);
-  }
+  const int quad = ew & 3, half = ew >> 2;
+  const int row = quad * 32 + lane;
   const uint32_t sw = (uint32_t)(row & 7);
   int q = 0, it = 0;
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-    const TileCoord tc = decode_tile(g, tile);
-    const int n0 = tc.nt * BLOCK_N;
+    const int n0 = (tile % g.tiles_n) * BLOCK_N;
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
     ptx::mbar_wait(tfull0 + 8u * as, aphase);
     ptx::tc_fence_after();
-    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + half * 32);
 #pragma unroll 1
     for (int c = 0; c < CH; ++c, ++q) {
       const int b = q % EB;
+      const uint32_t use = (uint32_t)(q / EB);
       const uint32_t rowp = epi_base + b * kEpiBufBytes + (uint32_t)row * 128u;
-      uint32_t acc[64];
-      ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
-      ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+      float4 bias[8];
+      {
+        const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0 + c * 64 + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bias[j] = __ldg(b4 + j);
+      }
+      uint32_t acc[32];
+      ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), acc);
       ptx::tmem_ld_wait();
       if (c == CH - 1) {   // accumulator stage fully read: hand it back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tempty0 + 8u * as);
       }
-      if (HAS_RES) ptx::mbar_wait(res0 + 8u * b, (uint32_t)(q / EB) & 1u);
-      const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0 + c * 64);
+      uint4 res[4];
+      if (HAS_RES) {
+        ptx::mbar_wait(eb.res + 8u * b, use & 1u);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {            // 16-byte group j = channels 8j .. 8j+7 of this pixel
-        const uint32_t addr = rowp + (((uint32_t)j ^ sw) << 4);
-        const float4 bl = __ldg(b4 + 2 * j), bh = __ldg(b4 + 2 * j + 1);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t addr = rowp + (((uint32_t)(half * 4 + j) ^ sw) << 4);
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(res[j].x), "=r"(res[j].y), "=r"(res[j].z), "=r"(res[j].w) : "r"(addr));
+        }
+      } else if (use >= 1) {
+        ptx::mbar_wait(eb.free_ + 8u * b, (use - 1u) & 1u);   // the previous store out of this buffer has been read
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {            // 16-byte group = 8 channels of this pixel
+        const uint32_t addr = rowp + (((uint32_t)(half * 4 + j) ^ sw) << 4);
+        const float4 bl = bias[2 * j], bh = bias[2 * j + 1];
         float v[8];
         v[0] = __uint_as_float(acc[8 * j + 0]) + bl.x; v[1] = __uint_as_float(acc[8 * j + 1]) + bl.y;
         v[2] = __uint_as_float(acc[8 * j + 2]) + bl.z; v[3] = __uint_as_float(acc[8 * j + 3]) + bl.w;
         v[4] = __uint_as_float(acc[8 * j + 4]) + bh.x; v[5] = __uint_as_float(acc[8 * j + 5]) + bh.y;
         v[6] = __uint_as_float(acc[8 * j + 6]) + bh.z; v[7] = __uint_as_float(acc[8 * j + 7]) + bh.w;
         if (HAS_RES) {
-          uint4 r;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-          const __half2* h = reinterpret_cast<const __half2*>(&r);
+          const __half2* h = reinterpret_cast<const __half2*>(&res[j]);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 f = __half22float2(h[t]);
@@ -211,24 +220,51 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcMaps& maps, const ConvT
         for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
       }
-      ptx::fence_proxy_async_smem();
-      // without a residual nobody else signals that buffer (q+1) % EB is free again: the leader makes sure every
-      // earlier store has been read out of smem before the barrier that releases the other threads
-      if (!HAS_RES && leader) ptx::tma_store_wait_read<0>();
-      ptx::named_bar_sync(1, 128);
-      if (leader) {
-        ptx::tma_store_4d(&maps.c, epi_base + b * kEpiBufBytes, n0 + c * 64, tc.ox0, tc.oy0, tc.img);
-        ptx::tma_store_commit();
-        if (HAS_RES && q >= 1 && q - 1 + EB < total) {
-          ptx::tma_store_wait_read<1>();        // the store of chunk q-1 has left its buffer
-          issue_res(q - 1 + EB);
+      ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA store
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(eb.ready + 8u * b);
+    }
+  }
+}
+
+// The single thread that owns every bulk copy of the epilogue: stores chunk q when all eight warps have
+// written it, then (one store later, so it never waits on the store it just issued) recycles the previous
+// buffer: HAS_RES -> prefetch the residual of chunk q-1+EB into it, else -> mark it free.
+template <int BLOCK_N, bool HAS_RES>
+__device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvTcGeom& g, const EpiBars eb, uint32_t epi_base) {
+  constexpr int CH = BLOCK_N / 64;
+  constexpr int EB = HAS_RES ? 4 : 2;
+  const int my_tiles = (int)blockIdx.x < g.num_tiles ? (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total = my_tiles * CH;
+  auto issue_res = [&](int qq) {
+    const TileCoord tc = decode_tile(g, (int)blockIdx.x + (qq / CH) * (int)gridDim.x);
+    const int b = qq % EB;
+    ptx::mbar_expect_tx(eb.res + 8u * b, (uint32_t)kEpiBufBytes);
+    ptx::tma_load_4d(epi_base + b * kEpiBufBytes, &maps.r, eb.res + 8u * b, tc.nt * BLOCK_N + (qq % CH) * 64, tc.ox0, tc.oy0, tc.img);
+  };
+  if (HAS_RES) {
+    for (int p = 0; p < EB && p < total; ++p) issue_res(p);
+  }
+  int q = 0;
+  for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+    const TileCoord tc = decode_tile(g, tile);
+    for (int c = 0; c < CH; ++c, ++q) {
+      const int b = q % EB;
+      ptx::mbar_wait(eb.ready + 8u * b, (uint32_t)(q / EB) & 1u);
+      ptx::tma_store_4d(&maps.c, epi_base + b * kEpiBufBytes, tc.nt * BLOCK_N + c * 64, tc.ox0, tc.oy0, tc.img);
+      ptx::tma_store_commit();
+      if (q >= 1) {
+        ptx::tma_store_wait_read<1>();          // the store of chunk q-1 has left its buffer
+        if (HAS_RES) {
+          if (q - 1 + EB < total) issue_res(q - 1 + EB);
+        } else {
+          ptx::mbar_arrive(eb.free_ + 8u * ((q - 1) % EB));
         }
       }
     }
   }
-  if (leader) ptx::tma_store_wait_read<0>();
+  ptx::tma_store_wait<0>();
 }
-
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -239,13 +275,16 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + num_stages * C::kStageBytes;          // 1024-aligned: stage sizes are multiples of 4 KB
   const uint32_t bar_base = epi_base + g.epi_bufs * kEpiBufBytes;
-  // barrier block: full[8], empty[8], tmem_full[2], tmem_empty[2], res_full[4], tmem_ptr
+  // barrier block: full[8], empty[8], tmem_full[2], tmem_empty[2], res_full[4], chunk_ready[4], buf_free[4], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
-  auto res_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + s); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 4 + kMaxEpiBufs);
+  EpiBars eb;
+  eb.res = bar_base + 8u * (2 * kMaxStages + 4);
+  eb.ready = eb.res + 8u * kMaxEpiBufs;
+  eb.free_ = eb.ready + 8u * kMaxEpiBufs;
+  const uint32_t tmem_ptr_addr = eb.free_ + 8u * kMaxEpiBufs;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -259,8 +298,12 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < num_stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
-    for (int s = 0; s < kMaxEpiBufs; ++s) ptx::mbar_init(res_bar(s), 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), g.store_mode == 0 ? 4 : kEpiWarps); }
+    for (int s = 0; s < kMaxEpiBufs; ++s) {
+      ptx::mbar_init(eb.res + 8u * s, 1);
+      ptx::mbar_init(eb.ready + 8u * s, kEpiWarps);
+      ptx::mbar_init(eb.free_ + 8u * s, 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -334,15 +377,22 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
         ptx::umma_commit(tfull_bar(as));
       }
     }
+  } else if (warp == kDmaWarp) {
+    // ===================== epilogue DMA =====================
+    if constexpr (BLOCK_N >= 64) {
+      if (ptx::elect_one()) {
+        if (g.store_mode == 1) epilogue_dma<BLOCK_N, false>(maps, g, eb, epi_base);
+        else if (g.store_mode == 2) epilogue_dma<BLOCK_N, true>(maps, g, eb, epi_base);
+      }
+    }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
-    const int quad = warp - kEpiWarp0;       // == warp % 4: the TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;        // accumulator row = pixel inside the tile
+    const int ew = warp - kEpiWarp0;         // ew % 4 == warp % 4: the TMEM lane quadrant this warp may read
     if (g.store_mode == 0) {
-      epilogue_direct<BLOCK_N>(g, tmem_base, tfull_bar(0), tempty_bar(0), quad, lane, row);
+      if (ew < 4) epilogue_direct<BLOCK_N>(g, tmem_base, tfull_bar(0), tempty_bar(0), ew, lane, ew * 32 + lane);
     } else if constexpr (BLOCK_N >= 64) {
-      if (g.store_mode == 1) epilogue_tma<BLOCK_N, false>(maps, g, tmem_base, tfull_bar(0), tempty_bar(0), res_bar(0), epi_base, quad, lane, row);
-      else epilogue_tma<BLOCK_N, true>(maps, g, tmem_base, tfull_bar(0), tempty_bar(0), res_bar(0), epi_base, quad, lane, row);
+      if (g.store_mode == 1) epilogue_tma<BLOCK_N, false>(g, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      else epilogue_tma<BLOCK_N, true>(g, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
     }
   }
 
