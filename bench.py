@@ -307,6 +307,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         plan = h.plan_text(B, W, H).splitlines()
         op_lines = [ln for ln in plan if ln.startswith("conv ") or ln.startswith("maxpool ")]
         op_ms = h.profile_ops(d_sets[0].data_ptr(), B, W, H, iters=max(2, min(args.steps, 5)))
+        pre_ms, post_ms = op_ms[len(op_lines)], op_ms[len(op_lines) + 1]
+        pool_ms = sum(m for ln, m in zip(op_lines, op_ms) if ln.startswith("maxpool "))
         conv_ms = sum(m for ln, m in zip(op_lines, op_ms) if ln.startswith("conv "))
         n_conv = sum(1 for ln in op_lines if ln.startswith("conv "))
         flops = B * FLOPS_NO_AUX[(W, H)]
@@ -318,6 +320,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "flops_per_launch_avg": flops / n_conv, "ms_per_launch_avg": conv_ms / n_conv, "ms_all_launches": conv_ms,
             "peak_source": pk["source"] + " (sustained cuBLAS bf16: the kernel is timed inside a long step)",
         }
+        # the HBM-bound kernels either side of the network (algorithmic bytes per 1080p frame)
+        def hbm(name, mb_per_frame, t_ms):
+            gbs = B * mb_per_frame * 1e6 / (t_ms * 1e-3) / 1e9
+            return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                    "ms_per_launch": t_ms, "algorithmic_MB_per_frame": mb_per_frame}
+        other = [hbm("pre_unit_vec4_kernel (Scale 1.0 + u8->fp16 normalise)", 6.2208 + 12.4416, pre_ms),
+                 hbm("maxpool_kernel (3x3/s2, NHWC fp16)", 66.3552 + 16.5888, pool_ms),
+                 hbm("post_kernel (bilinear x8 upsample + argmax + colour)", 2.7216 + 8.2944 + 2.0736, post_ms)]
         cpu = None
         if not args.no_cpu_baseline:
             _, model = synth.ensure_fixture("fcn50")
@@ -336,7 +346,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                        "l2": "inputs cycle through 4 x 8 distinct frames (199 MB) and each step streams > 30 GB of activations: larger than L2"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * W * H * 3, "d2h_bytes_per_step": B * W * H * 5,
                     "api": "infur_b200_ring_acquire/submit/wait, host memcpy into the pinned slot inside the timed region"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_other_kernels": other, "cpu_baseline": cpu,
             "single_frame": {"workload": "configs[1]: one 1080p frame, synchronous infur_b200_advance, host buffers", "ms": 1e3 * float(np.median(lat))},
         }
     h.close()
@@ -350,7 +360,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8)

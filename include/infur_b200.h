@@ -59,6 +59,8 @@ typedef struct infur_b200_config {
   int32_t blend;         /* also produce blended_rgba (new feature; gui.rs:324-329 "todo: blend somehow?") */
   int32_t conv_impl;     /* INFUR_CONV_TCGEN05 */
   int32_t use_cuda_graph;/* capture the per-shape forward into a CUDA graph */
+  int32_t autotune;      /* time the N-tile candidates of every convolution once per (shape, batch) plan and keep the fastest
+                          * (default 1; results are bit-identical for every choice) */
 } infur_b200_config;
 
 /* Fills *cfg with the defaults of the three stages: factor 1.0, dirty, no model
@@ -234,8 +236,9 @@ int32_t infur_b200_conv_test(infur_b200_handle* h, const infur_b200_conv_desc* d
 int32_t infur_b200_plan_text(infur_b200_handle* h, uint32_t n, uint32_t w, uint32_t hgt, char* buf, size_t cap,
                              size_t* required);
 
-/* Per-kernel CUDA-event timing of one forward of the current plan (ms per op, same order as
- * plan_text); returns the number of ops written. */
+/* Per-kernel CUDA-event timing of one forward of the current plan: ms per op in plan_text order, followed
+ * by two more entries, the pre-kernel (Scale + normalise) and the post-kernel (upsample + ColorCode).
+ * *count = number of entries written (ops + 2). */
 int32_t infur_b200_profile_ops(infur_b200_handle* h, const uint8_t* d_bgr, uint32_t n, uint32_t w, uint32_t hgt,
                                int32_t iters, float* ms, int32_t cap, int32_t* count);
 

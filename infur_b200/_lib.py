@@ -36,7 +36,7 @@ class Config(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("max_batch", C.c_int32), ("ring_depth", C.c_int32),
         ("resize_mode", C.c_int32), ("compute_aux", C.c_int32), ("blend", C.c_int32), ("conv_impl", C.c_int32),
-        ("use_cuda_graph", C.c_int32),
+        ("use_cuda_graph", C.c_int32), ("autotune", C.c_int32),
     ]
 
 

@@ -39,7 +39,7 @@ void infur_b200_default_config(infur_b200_config* cfg) {
   memset(cfg, 0, sizeof(*cfg));
   cfg->struct_size = sizeof(*cfg);
   cfg->device = 0; cfg->max_batch = 8; cfg->ring_depth = 3; cfg->resize_mode = INFUR_RESIZE_NEAREST;
-  cfg->compute_aux = 0; cfg->blend = 0; cfg->conv_impl = INFUR_CONV_TCGEN05; cfg->use_cuda_graph = 0;
+  cfg->compute_aux = 0; cfg->blend = 0; cfg->conv_impl = INFUR_CONV_TCGEN05; cfg->use_cuda_graph = 0; cfg->autotune = 1;
 }
 
 int32_t infur_b200_abi_version(void) { return INFUR_B200_ABI_VERSION; }
@@ -620,21 +620,25 @@ int32_t infur_b200_profile_ops(infur_b200_handle* h, const uint8_t* d_bgr, uint3
   if (!st.ok()) return fail(h, st);
   if (!pp->has_model) return fail(h, INFUR_E_INVALID_ARG, "profile_ops: no model loaded");
   const int nops = (int)pp->ops.size();
-  *count = nops;
-  if (cap < nops) return fail(h, INFUR_E_BUFFER_TOO_SMALL, "profile_ops: ms[] too small");
-  std::vector<cudaEvent_t> evs((size_t)nops + 1);
+  *count = nops + 2;
+  if (cap < nops + 2) return fail(h, INFUR_E_BUFFER_TOO_SMALL, "profile_ops: ms[] too small");
+  // events: [0] start, [1] after the pre-kernel, [2 .. nops+1] after each op, [nops+2] after the post-kernel
+  std::vector<cudaEvent_t> evs((size_t)nops + 3);
   for (auto& e : evs) cudaEventCreate(&e);
-  std::vector<double> acc((size_t)nops, 0.0);
+  std::vector<double> acc((size_t)nops + 2, 0.0);
   OutPtrs o; o.class_map = pp->d_class; o.decoded = pp->d_decoded;
   for (int it = 0; it < iters && st.ok(); ++it) {
     st = run_forward(h, *pp, d_bgr, o, h->stream, nullptr, evs.data());
     if (!st.ok()) break;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { st = Status::error(INFUR_E_RUNTIME, "profile_ops: stream sync failed"); break; }
-    for (int i = 0; i < nops; ++i) { float t = 0; cudaEventElapsedTime(&t, evs[i], evs[i + 1]); acc[i] += t; }
+    for (int i = 0; i < nops + 2; ++i) { float t = 0; cudaEventElapsedTime(&t, evs[i], evs[i + 1]); acc[i] += t; }
   }
   for (auto& e : evs) cudaEventDestroy(e);
   if (!st.ok()) return fail(h, st);
-  for (int i = 0; i < nops; ++i) ms[i] = (float)(acc[i] / iters);
+  // output order: the nops plan ops, then the pre-kernel, then the post-kernel
+  for (int i = 0; i < nops; ++i) ms[i] = (float)(acc[i + 1] / iters);
+  ms[nops] = (float)(acc[0] / iters);
+  ms[nops + 1] = (float)(acc[nops + 1] / iters);
   return INFUR_OK;
 }
 

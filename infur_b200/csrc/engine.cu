@@ -176,7 +176,8 @@ struct ConvIO {
   int out_ld = 0;
 };
 
-static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po) {
+static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int block_n) {
+  po.block_n = block_n;
   ConvTcGeom& g = po.geom;
   memset(&g, 0, sizeof(g));
   memset(&po.maps, 0, sizeof(po.maps));
@@ -192,13 +193,13 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po) {
   g.bw_log2 = best;
   const int bw = 1 << best, bh = 128 >> best;
   g.tiles_x = (io.ow + bw - 1) / bw; g.tiles_y = (io.oh + bh - 1) / bh;
-  g.tiles_n = d.cout_pad / d.block_n;
+  g.tiles_n = d.cout_pad / block_n;
   g.num_tiles = io.n * g.tiles_x * g.tiles_y * g.tiles_n;
   g.num_taps = d.taps; g.cchunks = d.cchunks;
   g.out_ld = io.out_ld; g.relu = d.relu ? 1 : 0;
   g.store_mode = io.y_f32 ? 0 : (io.residual ? 2 : 1);
   g.epi_bufs = g.store_mode == 0 ? 0 : (g.store_mode == 1 ? 2 : 4);
-  g.stages = conv_tc_stages(d.block_n, g.epi_bufs);
+  g.stages = conv_tc_stages(block_n, g.epi_bufs);
   g.bias = io.bias; g.residual = io.residual; g.out = io.y; g.out_f32 = io.y_f32;
   Status st;
   const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
@@ -244,7 +245,7 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po) {
   {
     const uint64_t dims[2] = {(uint64_t)d.kdim, (uint64_t)d.cout_pad};
     const uint64_t strides[1] = {(uint64_t)d.kdim * 2};
-    const uint32_t bbox[2] = {64, (uint32_t)d.block_n};
+    const uint32_t bbox[2] = {64, (uint32_t)block_n};
     st = make_tmap_f16(&po.maps.b, io.wgt, 2, dims, strides, bbox);
     if (!st.ok()) return st;
   }
@@ -270,6 +271,41 @@ static void setup_direct(const DevConv& d, const ConvIO& io, const __half* wv, D
   a.dil = d.dil; a.oh = io.oh; a.ow = io.ow; a.relu = d.relu ? 1 : 0; a.out_ld = io.out_ld;
   if (d.stem) { a.x_pitch_px = stem_pitch_px(io.w); a.x_rows = stem_rows(io.h); a.x_c = 4; a.x_off_y = kStemPadTop; a.x_off_x = kStemPadLeft; }
   else { a.x_pitch_px = io.w; a.x_rows = io.h; a.x_c = d.cin; a.x_off_y = 0; a.x_off_x = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-op choice of the N tile (256 / 128 / 64 output channels) by measurement at plan-build time.  The
+// accumulation order of every output element is the same for all choices (K blocks in sequence), so the
+// result is bit-identical whichever wins; only time differs: a narrower tile leaves room for more pipeline
+// stages (more HBM bytes in flight for the memory-bound 1x1 convs), a wider one halves the activation re-reads.
+static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO& io, PlanOp& po) {
+  static const int cands[3] = {256, 128, 64};
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  int best_bn = po.block_n;
+  float best_ms = 1e30f;
+  Status st;
+  for (int bn : cands) {
+    if (bn > d.block_n || d.cout_pad % bn != 0) continue;
+    PlanOp trial;
+    if (!(st = setup_conv_tc(d, io, trial, bn)).ok()) break;
+    cudaError_t e = conv_tc_launch(bn, trial.maps, trial.geom, H->num_sms, H->stream);   // warm-up
+    cudaEventRecord(e0, H->stream);
+    for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = conv_tc_launch(bn, trial.maps, trial.geom, H->num_sms, H->stream);
+    cudaEventRecord(e1, H->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    H->launches += 3;
+    if (e != cudaSuccess) { st = Status::error(INFUR_E_RUNTIME, std::string("autotune: ") + cudaGetErrorString(e)); break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best_ms) { best_ms = ms; best_bn = bn; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!st.ok()) return st;
+  if (best_bn != po.block_n) st = setup_conv_tc(d, io, po, best_bn);
+  return st;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,7 +455,10 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       io.residual = op.conv.residual >= 0 ? reinterpret_cast<const __half*>(p.tensors[op.conv.residual].ptr) : nullptr;
       if (to.f32) io.y_f32 = reinterpret_cast<float*>(to.ptr); else io.y = reinterpret_cast<__half*>(to.ptr);
       io.out_ld = to.ld;
-      if (d.tc_ok) { if (!(st = setup_conv_tc(d, io, po)).ok()) return st; }
+      if (d.tc_ok) { if (!(st = setup_conv_tc(d, io, po, d.block_n)).ok()) return st; }
+      if (d.tc_ok && !to.f32 && H->cfg.autotune && H->cfg.conv_impl == INFUR_CONV_TCGEN05) {
+        if (!(st = tune_block_n(H, d, io, po)).ok()) return st;
+      }
       setup_direct(d, io, reinterpret_cast<const __half*>(M->arena + d.wv_off), po.direct);
       po.flops = 2.0 * n * to.h * to.w * (double)d.cout * d.kh * d.kw * d.cin;
       po.bytes = (double)n * ti.h * ti.w * d.cin * 2 + (double)to.bytes + (io.residual ? (double)n * to.h * to.w * to.c * 2 : 0.0) +
@@ -427,7 +466,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       os << "conv " << op.name << " [" << n << "x" << ti.h << "x" << ti.w << "x" << d.cin << "] -> [" << to.h << "x" << to.w << "x" << d.cout
          << "] k" << d.kh << " s" << d.stride << " p" << d.pad << " d" << d.dil << (io.residual ? " +res" : "") << (d.relu ? " relu" : "");
       if (d.tc_ok)
-        os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << d.block_n << " tiles "
+        os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << po.block_n << " tiles "
            << po.geom.num_tiles << " kblocks " << d.taps * d.cchunks;
       os << " | GFLOP " << po.flops * 1e-9 << " MB " << po.bytes * 1e-6;
     } else {
@@ -481,19 +520,20 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
   pa.stem_in = p.has_model ? p.stem_in : nullptr;
   pa.scaled_bgr = unit ? nullptr : p.scaled;
   const uint8_t* frame = unit ? d_bgr : p.scaled;
+  int ei = 0;
+  if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
   if (pa.stem_in || pa.scaled_bgr) { CU_TRY(launch_pre(pa, s)); H->launches++; }
   if (!p.has_model) {
     if (o.frame_rgba) { CU_TRY(launch_frame_rgba(frame, out_px, o.frame_rgba, s)); H->launches++; }
     return Status();
   }
   const DeviceModel& M = *H->model;
-  int ei = 0;
   if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
   for (PlanOp& po : p.ops) {
     const LoweredOp& op = M.lm.ops[po.op];
     if (po.is_conv) {
       const DevConv& d = M.convs[po.op];
-      if (H->cfg.conv_impl == INFUR_CONV_TCGEN05) CU_TRY(conv_tc_launch(d.block_n, po.maps, po.geom, H->num_sms, s));
+      if (H->cfg.conv_impl == INFUR_CONV_TCGEN05) CU_TRY(conv_tc_launch(po.block_n, po.maps, po.geom, H->num_sms, s));
       else CU_TRY(launch_direct_conv(po.direct, s));
     } else {
       const TensorInfo& ti = p.tensors[op.in];
@@ -522,6 +562,7 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
   }
   CU_TRY(launch_post(q, s));
   H->launches++;
+  if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
   (void)op_ms;
   return Status();
 }
@@ -596,7 +637,7 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   io.x = d_x; io.n = n; io.h = h; io.w = w; io.oh = oh; io.ow = ow; io.wgt = d_w; io.bias = d_b; io.residual = d_res; io.y = d_y; io.y_f32 = d_yf;
   io.out_ld = out_ld;
   PlanOp po;
-  if (tc) { if (!(st = setup_conv_tc(d, io, po)).ok()) return st; }
+  if (tc) { if (!(st = setup_conv_tc(d, io, po, d.block_n)).ok()) return st; }
   else setup_direct(d, io, d_wv, po.direct);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -604,7 +645,7 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   cudaError_t err = cudaSuccess;
   for (int r = 0; r < reps && err == cudaSuccess; ++r) {
     if (r == reps - 1) cudaEventRecord(e0, H->stream);
-    err = tc ? conv_tc_launch(d.block_n, po.maps, po.geom, H->num_sms, H->stream) : launch_direct_conv(po.direct, H->stream);
+    err = tc ? conv_tc_launch(po.block_n, po.maps, po.geom, H->num_sms, H->stream) : launch_direct_conv(po.direct, H->stream);
     H->launches++;
   }
   cudaEventRecord(e1, H->stream);

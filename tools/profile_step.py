@@ -52,7 +52,9 @@ def main():
                 mb = float(re.search(r"MB ([0-9.e+-]+)", ln).group(1))
                 tot_ms += t; tot_fl += gf
                 print(f"{t:8.3f} ms {gf / t if t else 0:8.1f} TF/s {mb / t if t else 0:8.1f} GB/s | {ln}")
-            print(f"total {tot_ms:.3f} ms per step of {B} frames -> {B / tot_ms * 1e3:.1f} frames/s (network only), {tot_fl / tot_ms:.1f} TFLOP/s")
+            print(f"{ms[len(lines)]:8.3f} ms pre-kernel (Scale + normalise) | {ms[len(lines) + 1]:8.3f} ms post-kernel (upsample + ColorCode)")
+            tot_ms += ms[len(lines)] + ms[len(lines) + 1]
+            print(f"total {tot_ms:.3f} ms per step of {B} frames -> {B / tot_ms * 1e3:.1f} frames/s (whole path), {tot_fl / tot_ms:.1f} TFLOP/s")
         stream = torch.cuda.ExternalStream(h.compute_stream())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         K = max(a.steps, 3)
