@@ -205,6 +205,97 @@ __global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
   }
 }
 
+// Strip variant of K5 for k <= KMAX classes (the network path): one warp = 32 output columns x kPostStripRows rows,
+// lane = column.  The horizontally interpolated logits of the two low-res rows the current output row blends
+// (top[k], bot[k]) live in registers and are refreshed only when the low-res row pair changes (every 8 output
+// rows at the network's x8 upsample); when the pair slides down by one, bot becomes top without a reload.  Same
+// f32 operations in the same order as post_kernel / the oracle, hence the same bits.
+constexpr int kPostStripRows = 64;
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) post_strip_kernel(PostArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x = blockIdx.x * 32 + lane;
+  const int Y0 = (blockIdx.y * 4 + warp) * kPostStripRows;
+  const int img = blockIdx.z;
+  if (Y0 >= a.oh) return;
+  const int Y1 = min(Y0 + kPostStripRows, a.oh);
+  const bool xin = x < a.ow;
+  const int xi = xin ? x : a.ow - 1;
+  const int c0 = __ldg(a.x0 + xi), c1 = __ldg(a.x1 + xi);
+  const float wx0 = __ldg(a.lx0 + xi), wx1 = __ldg(a.lx1 + xi);
+  const int kq = (a.k + 3) >> 2;
+  float top[KMAX], bot[KMAX];
+  auto load_row = [&](int r, float* dst) {
+    const float4* p0 = reinterpret_cast<const float4*>(a.lowres + (((size_t)img * a.lh + r) * a.lw + c0) * a.ldk);
+    const float4* p1 = reinterpret_cast<const float4*>(a.lowres + (((size_t)img * a.lh + r) * a.lw + c1) * a.ldk);
+#pragma unroll
+    for (int q = 0; q < KMAX / 4; ++q) {
+      if (q < kq) {
+        const float4 u = __ldg(p0 + q), v = __ldg(p1 + q);
+        dst[4 * q + 0] = __fadd_rn(__fmul_rn(wx0, u.x), __fmul_rn(wx1, v.x));
+        dst[4 * q + 1] = __fadd_rn(__fmul_rn(wx0, u.y), __fmul_rn(wx1, v.y));
+        dst[4 * q + 2] = __fadd_rn(__fmul_rn(wx0, u.z), __fmul_rn(wx1, v.z));
+        dst[4 * q + 3] = __fadd_rn(__fmul_rn(wx0, u.w), __fmul_rn(wx1, v.w));
+      }
+    }
+  };
+  int cur0 = -1, cur1 = -1;
+  const size_t plane = (size_t)a.oh * a.ow;
+  for (int y = Y0; y < Y1; ++y) {
+    const int r0 = __ldg(a.y0 + y), r1 = __ldg(a.y1 + y);   // warp-uniform
+    if (r0 != cur0) {
+      if (r0 == cur1) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) top[k] = bot[k];
+      } else {
+        load_row(r0, top);
+      }
+      cur0 = r0;
+    }
+    if (r1 != cur1) {
+      if (r1 == cur0) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) bot[k] = top[k];
+      } else {
+        load_row(r1, bot);
+      }
+      cur1 = r1;
+    }
+    const float wy0 = __ldg(a.ly0 + y), wy1 = __ldg(a.ly1 + y);
+    int k_max = 0;
+    float c_max = 0.f;
+    const size_t pix = (size_t)y * a.ow + x;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < a.k) {
+        const float v = __fadd_rn(__fmul_rn(wy0, top[k]), __fmul_rn(wy1, bot[k]));
+        if (a.logits && xin) a.logits[((size_t)img * a.k + k) * plane + pix] = v;
+        if (v > c_max) { k_max = k; c_max = v; }
+      }
+    }
+    if (!xin) continue;
+    const float av = __fmul_rn(c_max, 255.0f);
+    const int alpha = av >= 255.0f ? 255 : (int)av;  // c_max >= 0 always; trunc toward zero, saturate
+    const uint32_t col = __ldg(a.color_lut + (k_max % 20) * 256 + alpha);
+    const size_t gp = (size_t)img * plane + pix;
+    if (a.class_map) a.class_map[gp] = (uint8_t)k_max;
+    a.decoded[gp] = col;
+    if (a.frame_bgr && (a.blended || a.frame_rgba)) {
+      const uint8_t* f = a.frame_bgr + gp * 3;
+      const uint32_t fb = f[0], fg = f[1], fr = f[2];
+      if (a.frame_rgba) a.frame_rgba[gp] = fr | (fg << 8) | (fb << 16) | 0xff000000u;
+      if (a.blended) {
+        const uint32_t ia = 255u - (col >> 24);
+        const uint32_t r = min(255u, (col & 0xff) + (fr * ia + 127u) / 255u);
+        const uint32_t g = min(255u, ((col >> 8) & 0xff) + (fg * ia + 127u) / 255u);
+        const uint32_t b = min(255u, ((col >> 16) & 0xff) + (fb * ia + 127u) / 255u);
+        a.blended[gp] = r | (g << 8) | (b << 16) | 0xff000000u;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) color_code_kernel(const float* __restrict__ hm, int k, size_t npix, const uint32_t* __restrict__ lut,
                                                           uint32_t* __restrict__ rgba, uint8_t* __restrict__ class_map) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,6 +383,12 @@ size_t post_smem_bytes(const PostArgs& a) {
 }
 
 cudaError_t launch_post(const PostArgs& a, cudaStream_t s) {
+  if (a.k <= 32 && a.ldk % 4 == 0 && a.ldk >= ((a.k + 3) & ~3)) {
+    dim3 grid((a.ow + 31) / 32, (a.oh + 4 * kPostStripRows - 1) / (4 * kPostStripRows), a.n);
+    if (a.k <= 24) post_strip_kernel<24><<<grid, 128, 0, s>>>(a);
+    else post_strip_kernel<32><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+  }
   const size_t smem = post_smem_bytes(a);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   static size_t configured = 0;
