@@ -404,6 +404,125 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 7x7 / stride 2 / pad 3 stem on 3 input channels (ORT Conv of `conv1`, inside session.run predict_onnx.rs:138).
+// Input: padded NHWC4 fp16 (kernels.h).  Output tile = 128 consecutive pixels of one output row.  For filter row
+// ky the implicit-GEMM operand A[m][k] (m = output pixel, k = 4 * (kx + 1) + channel, 32 wide) is the fp16 at
+// byte 16 m + 2 k of input row 2 oy + ky starting at pixel 2 ox0: consecutive output pixels read windows that
+// start two pixels = 16 bytes apart, which is exactly the row pitch of an un-swizzled UMMA core matrix.  So the
+// 7 raw input row segments (2176 B each, one TMA box) ARE the A operands: 14 tcgen05.mma (M128 N64 K16) per tile
+// read them through overlapping core-matrix descriptors, no im2col copy anywhere.  Weights (28 KB) stay in smem
+// for the whole persistent CTA.  Epilogue = the TMA-store epilogue above (one 64-channel chunk per tile).
+constexpr int kStemRowBytes = kStemRowGroups * 128;          // 2176
+constexpr int kStemStageBytes = 16384;                       // 7 rows x 2176 = 15232 B used
+constexpr int kStemTxBytes = 7 * kStemRowBytes;
+constexpr int kStemStages = 8;
+constexpr int kStemSmemBytes = kStemStages * kStemStageBytes + 2 * kEpiBufBytes + kStemWBytes + 1024 + kBarBytes;
+
+__global__ void __launch_bounds__(kThreads, 1)
+stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
+  constexpr int BLOCK_N = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + kStemStages * kStemStageBytes;
+  const uint32_t w_base = epi_base + 2 * kEpiBufBytes;
+  const uint32_t bar_base = w_base + kStemWBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  EpiBars eb;
+  eb.res = bar_base + 8u * (2 * kMaxStages + 4);
+  eb.ready = eb.res + 8u * kMaxEpiBufs;
+  eb.free_ = eb.ready + 8u * kMaxEpiBufs;
+  const uint32_t tmem_ptr_addr = eb.free_ + 8u * kMaxEpiBufs;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && ptx::elect_one()) { ptx::prefetch_tmap(&maps.a[0]); ptx::prefetch_tmap(&maps.c); }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < kStemStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), kEpiWarps); }
+    for (int s = 0; s < kMaxEpiBufs; ++s) {
+      ptx::mbar_init(eb.res + 8u * s, 1);
+      ptx::mbar_init(eb.ready + 8u * s, kEpiWarps);
+      ptx::mbar_init(eb.free_ + 8u * s, 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_addr, 2 * BLOCK_N);
+    ptx::tmem_relinquish();
+  }
+  {  // weights: global (already in smem order) -> smem, once per CTA
+    const uint4* src = reinterpret_cast<const uint4*>(g.stem_w);
+    for (int i = threadIdx.x; i < kStemWBytes / 16; i += kThreads) {
+      const uint4 v = __ldg(src + i);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_base + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    ptx::fence_proxy_async_smem();   // generic writes -> visible to the tensor core's async-proxy reads
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(g, tile);
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        ptx::mbar_expect_tx(full_bar(stage), (uint32_t)kStemTxBytes);
+        // row groups of 64 fp16 = 16 pixels: output pixel ox0 starts at input pixel 2 ox0 = group ox0 / 8
+        ptx::tma_load_4d(smem_base + stage * kStemStageBytes, &maps.a[0], full_bar(stage), 0, tc.ox0 >> 3, 2 * tc.oy0, tc.img);
+        if (++stage == kStemStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+        const uint32_t a_addr = smem_base + stage * kStemStageBytes;
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t a_desc = ptx::make_smem_desc_noswz(a_addr + ky * kStemRowBytes + kk * 32, 16, 128);
+            const uint64_t b_desc = ptx::make_smem_desc_noswz(w_base + ky * 4096 + kk * 2048, 1024, 128);
+            ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, (ky | kk) != 0);
+          }
+        }
+        ptx::umma_commit(empty_bar(stage));
+        ptx::umma_commit(tfull_bar(as));
+        if (++stage == kStemStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == kDmaWarp) {
+    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false>(maps, g, eb, epi_base);
+  } else if (warp >= kEpiWarp0) {
+    epilogue_tma<BLOCK_N, false>(g, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
 template <int BLOCK_N>
 cudaError_t launch_one(const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream) {
   const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
@@ -430,10 +549,18 @@ cudaError_t conv_tc_init() {
   if ((e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream) {
+  if (g.stem) {
+    const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
+    if (grid <= 0) return cudaSuccess;
+    if (block_n != 64 || g.store_mode != 1 || g.bw_log2 != 7) return cudaErrorInvalidValue;
+    stem_tc_kernel<<<grid, kThreads, kStemSmemBytes, stream>>>(maps, g);
+    return cudaGetLastError();
+  }
   switch (block_n) {
     case 32: return launch_one<32>(maps, g, num_sms, stream);
     case 64: return launch_one<64>(maps, g, num_sms, stream);

@@ -17,6 +17,8 @@
 namespace infur {
 
 constexpr int kMaxTaps = 49;
+constexpr int kStemWBytes = 7 * 4 * 64 * 8 * 2;   // 28 KB
+constexpr int kStemRowGroups = 17;                // 17 x 128 B = 272 input pixels feed 128 output pixels
 constexpr int kMaxViews = 4;
 
 struct ConvTcGeom {
@@ -28,6 +30,8 @@ struct ConvTcGeom {
   int32_t relu;
   int32_t store_mode;         // 0: per-thread vector stores (f32 head); 1: smem-staged TMA store; 2: + TMA residual prefetch
   int32_t stages, epi_bufs;   // smem pipeline depth and epilogue chunk buffers (0 / 2 / 4), see conv_tc_stages
+  int32_t stem;               // 1: 7x7/s2 RGB stem through stem_tc_kernel (maps.a[0] = row-group view of the padded NHWC4 input)
+  const __half* stem_w;       // stem weights in smem order [7 ky][4 k-cores][64 cout][8], kStemWBytes
   const float* bias;          // [tiles_n * BLOCK_N]
   const __half* residual;     // NHWC like out, or nullptr
   __half* out;                // fp16 NHWC, or nullptr when out_f32 is used

@@ -37,14 +37,14 @@ static EncodeTiledFn get_encode_tiled() {
 }
 
 static Status make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                            const uint32_t* box) {
+                            const uint32_t* box, bool swizzle128 = true) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return Status::error(INFUR_E_RUNTIME, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     std::ostringstream os;
@@ -63,6 +63,12 @@ DeviceModel::~DeviceModel() { if (arena) cudaFree(arena); }
 Plan::~Plan() { for (void* p : owned) cudaFree(p); }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// Stem weights in the order stem_tc_kernel keeps them in smem: [ky][k / 8][cout][k % 8] with k = 4 * (kx + 1) + ci
+// (an un-swizzled K-major UMMA operand: 8-row core matrices 128 B apart along cout, 1024 B apart along k).
+static inline size_t stem_w_index(int co, int ky, int kx, int ci) {
+  const int k = 4 * (kx + 1) + ci;
+  return (((size_t)ky * 4 + (k >> 3)) * 64 + co) * 8 + (k & 7);
+}
 static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
 
 // ------------------------------------------------------------------------------------------------
@@ -145,7 +151,7 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
           for (int ky = 0; ky < 7; ++ky)
             for (int kx = 0; kx < 7; ++kx)
               for (int ci = 0; ci < 3; ++ci)
-                w16[((size_t)co * 7 + ky) * 64 + (kx + 1) * 4 + ci] = __float2half_rn(c.weight[(((size_t)co * 7 + ky) * 7 + kx) * 3 + ci]);
+                w16[stem_w_index(co, ky, kx, ci)] = __float2half_rn(c.weight[(((size_t)co * 7 + ky) * 7 + kx) * 3 + ci]);
         __half* wv = reinterpret_cast<__half*>(host.data() + d.wv_off);
         for (size_t j = 0; j < c.weight.size(); ++j) wv[j] = __float2half_rn(c.weight[j]);
       } else {
@@ -202,17 +208,20 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   g.stages = conv_tc_stages(block_n, g.epi_bufs);
   g.bias = io.bias; g.residual = io.residual; g.out = io.y; g.out_f32 = io.y_f32;
   Status st;
-  const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  const uint32_t box[4] = {64, (uint32_t)(d.stem ? 128 : bw), (uint32_t)(d.stem ? 1 : bh), 1};
   if (d.stem) {
+    // stem_tc_kernel: tile = 128 pixels of one output row; A = 7 raw input row segments (conv_tc.cu)
+    g.stem = 1; g.stem_w = io.wgt;
+    g.bw_log2 = 7;
+    g.tiles_x = (io.ow + 127) / 128; g.tiles_y = io.oh; g.tiles_n = 1;
+    g.num_tiles = io.n * g.tiles_x * g.tiles_y;
     const int pitch = stem_pitch_px(io.w), rows = stem_rows(io.h);
-    for (int p = 0; p < 2; ++p) {
-      const uint64_t dims[4] = {64, (uint64_t)io.ow, (uint64_t)((rows - p + 1) / 2), (uint64_t)io.n};
-      const uint64_t strides[3] = {16, (uint64_t)pitch * 8 * 2, (uint64_t)rows * pitch * 8};
-      st = make_tmap_f16(&po.maps.a[p], io.x + (size_t)p * pitch * 4, 4, dims, strides, box);
-      if (!st.ok()) return st;
-    }
-    po.maps.a[2] = po.maps.a[0]; po.maps.a[3] = po.maps.a[0];
-    for (int ky = 0; ky < 7; ++ky) { g.tap_view[ky] = (int8_t)(ky & 1); g.tap_dx[ky] = 0; g.tap_dy[ky] = (int16_t)(ky >> 1); }
+    const uint64_t dims[4] = {64, (uint64_t)(pitch / 16), (uint64_t)rows, (uint64_t)io.n};
+    const uint64_t strides[3] = {128, (uint64_t)pitch * 8, (uint64_t)rows * pitch * 8};
+    const uint32_t abox[4] = {64, (uint32_t)kStemRowGroups, 7, 1};
+    st = make_tmap_f16(&po.maps.a[0], io.x, 4, dims, strides, abox, false);
+    if (!st.ok()) return st;
+    po.maps.a[1] = po.maps.a[0]; po.maps.a[2] = po.maps.a[0]; po.maps.a[3] = po.maps.a[0];
   } else {
     const int s = d.stride;
     bool have[4] = {false, false, false, false};
@@ -242,12 +251,14 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
         g.tap_dx[t] = (int16_t)qx;
       }
   }
-  {
+  if (!d.stem) {
     const uint64_t dims[2] = {(uint64_t)d.kdim, (uint64_t)d.cout_pad};
     const uint64_t strides[1] = {(uint64_t)d.kdim * 2};
     const uint32_t bbox[2] = {64, (uint32_t)block_n};
     st = make_tmap_f16(&po.maps.b, io.wgt, 2, dims, strides, bbox);
     if (!st.ok()) return st;
+  } else {
+    po.maps.b = po.maps.a[0];
   }
   po.maps.c = po.maps.b; po.maps.r = po.maps.b;
   if (g.store_mode != 0) {
@@ -596,7 +607,7 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
     for (int co = 0; co < c.cout; ++co)
       for (int ky = 0; ky < 7; ++ky)
         for (int kx = 0; kx < 7; ++kx)
-          for (int ci = 0; ci < 3; ++ci) wp[((size_t)co * 7 + ky) * 64 + (kx + 1) * 4 + ci] = wh[(((size_t)co * 7 + ky) * 7 + kx) * 3 + ci];
+          for (int ci = 0; ci < 3; ++ci) wp[stem_w_index(co, ky, kx, ci)] = wh[(((size_t)co * 7 + ky) * 7 + kx) * 3 + ci];
   } else if (d.tc_ok) {
     for (size_t j = 0; j < wcount; ++j) wp[j] = wh[j];
   }

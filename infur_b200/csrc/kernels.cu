@@ -4,6 +4,8 @@
 // reference's order.
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace infur {
 
 namespace {
@@ -212,8 +214,8 @@ __global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
 // f32 operations in the same order as post_kernel / the oracle, hence the same bits.
 constexpr int kPostStripRows = 64;
 
-template <int KMAX>
-__global__ void __launch_bounds__(128) post_strip_kernel(PostArgs a) {
+template <int KMAX, int MINB>
+__global__ void __launch_bounds__(128, MINB) post_strip_kernel(PostArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x = blockIdx.x * 32 + lane;
   const int Y0 = (blockIdx.y * 4 + warp) * kPostStripRows;
@@ -263,17 +265,30 @@ __global__ void __launch_bounds__(128) post_strip_kernel(PostArgs a) {
       cur1 = r1;
     }
     const float wy0 = __ldg(a.ly0 + y), wy1 = __ldg(a.ly1 + y);
-    int k_max = 0;
-    float c_max = 0.f;
+    // ColorCode's scan (strict '>', first maximum wins, start (0, 0.0)) split into 4 contiguous class blocks that
+    // run as independent dependency chains and are merged left to right with the same strict '>': identical result
+    // (blocks 1..3 start from -inf, which no value -- and no NaN -- fails to beat or tie exactly as in one chain).
+    constexpr int KB = KMAX / 4;
+    int bk[4] = {0, KB, 2 * KB, 3 * KB};
+    float bv[4] = {0.f, -INFINITY, -INFINITY, -INFINITY};
     const size_t pix = (size_t)y * a.ow + x;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < a.k) {
-        const float v = __fadd_rn(__fmul_rn(wy0, top[k]), __fmul_rn(wy1, bot[k]));
-        if (a.logits && xin) a.logits[((size_t)img * a.k + k) * plane + pix] = v;
-        if (v > c_max) { k_max = k; c_max = v; }
+    for (int i = 0; i < KB; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = j * KB + i;
+        if (k < a.k) {
+          const float v = __fadd_rn(__fmul_rn(wy0, top[k]), __fmul_rn(wy1, bot[k]));
+          if (a.logits && xin) a.logits[((size_t)img * a.k + k) * plane + pix] = v;
+          if (v > bv[j]) { bk[j] = k; bv[j] = v; }
+        }
       }
     }
+    int k_max = bk[0];
+    float c_max = bv[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+      if (bv[j] > c_max) { k_max = bk[j]; c_max = bv[j]; }
     if (!xin) continue;
     const float av = __fmul_rn(c_max, 255.0f);
     const int alpha = av >= 255.0f ? 255 : (int)av;  // c_max >= 0 always; trunc toward zero, saturate
@@ -385,8 +400,9 @@ size_t post_smem_bytes(const PostArgs& a) {
 cudaError_t launch_post(const PostArgs& a, cudaStream_t s) {
   if (a.k <= 32 && a.ldk % 4 == 0 && a.ldk >= ((a.k + 3) & ~3)) {
     dim3 grid((a.ow + 31) / 32, (a.oh + 4 * kPostStripRows - 1) / (4 * kPostStripRows), a.n);
-    if (a.k <= 24) post_strip_kernel<24><<<grid, 128, 0, s>>>(a);
-    else post_strip_kernel<32><<<grid, 128, 0, s>>>(a);
+    static const int minb = getenv("INFUR_POST_MINB") ? atoi(getenv("INFUR_POST_MINB")) : 2;
+    if (a.k <= 24) { if (minb == 3) post_strip_kernel<24, 3><<<grid, 128, 0, s>>>(a); else post_strip_kernel<24, 2><<<grid, 128, 0, s>>>(a); }
+    else post_strip_kernel<32, 2><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
   }
   const size_t smem = post_smem_bytes(a);

@@ -8,10 +8,12 @@
 namespace infur {
 
 // Stem input layout: NHWC with C padded 3 -> 4 (R,G,B,0 fp16), a zero border of kStemPadTop rows above /
-// below and kStemPadLeft pixels left, so that the 7x7/s2 stem reads 16-pixel windows without a bounds test.
+// below and kStemPadLeft pixels left (and at least 16 zero pixels right), so that the 7x7/s2 stem reads 8-pixel
+// windows without a bounds test.  The row pitch is a multiple of 16 pixels (128 B): the stem kernel fetches
+// whole 128-byte groups of a row with TMA.
 constexpr int kStemPadTop = 3;
 constexpr int kStemPadLeft = 4;
-inline int stem_pitch_px(int w) { return ((w + kStemPadLeft + 16 + 1) / 2) * 2; }
+inline int stem_pitch_px(int w) { return ((w + kStemPadLeft + 16 + 15) / 16) * 16; }
 inline int stem_rows(int h) { return h + 2 * kStemPadTop + 1; }
 
 struct PreArgs {

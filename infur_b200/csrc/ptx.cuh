@@ -155,6 +155,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// Shared-memory matrix descriptor without swizzle ("interleave" layout), K-major: the operand is a grid of core
+// matrices of 8 rows x 16 bytes whose rows are 16 bytes apart; lbo = byte distance between core matrices that
+// are adjacent in K, sbo = byte distance between adjacent 8-row groups (M / N direction).  Nothing requires
+// core matrices to be disjoint: lbo = 16, sbo = 128 makes element (row m, k) = fp16 at byte 16 m + 2 k of the
+// buffer, a Toeplitz view of one contiguous line (used by the stem convolution).
+__device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: fp16 A and B (both K-major), f32 accumulate, M x N tile.
 //   [4,6) D format 1 = f32   [7,10) A format 0 = f16   [10,13) B format 0 = f16
 //   [15] A major 0 = K   [16] B major 0 = K   [17,23) N >> 3   [24,29) M >> 4
