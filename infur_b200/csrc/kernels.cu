@@ -4,8 +4,6 @@
 // reference's order.
 #include "kernels.h"
 
-#include <cstdlib>
-
 namespace infur {
 
 namespace {
@@ -207,15 +205,17 @@ __global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
   }
 }
 
-// Strip variant of K5 for k <= KMAX classes (the network path): one warp = 32 output columns x kPostStripRows rows,
-// lane = column.  The horizontally interpolated logits of the two low-res rows the current output row blends
-// (top[k], bot[k]) live in registers and are refreshed only when the low-res row pair changes (every 8 output
-// rows at the network's x8 upsample); when the pair slides down by one, bot becomes top without a reload.  Same
-// f32 operations in the same order as post_kernel / the oracle, hence the same bits.
+// Strip variant of K5 for a compile-time class count K (the network path, K = 21): one warp = 32 output columns x
+// kPostStripRows rows, lane = column.  The horizontally interpolated logits of the two low-res rows the current
+// output row blends (top[k], bot[k]) live in registers and are refreshed only when the low-res row pair changes
+// (every 8 output rows at the network's x8 upsample); when the pair slides down by one, bot becomes top without a
+// reload.  Same f32 operations in the same order as post_kernel / the oracle, hence the same bits.
 constexpr int kPostStripRows = 64;
 
-template <int KMAX, int MINB>
-__global__ void __launch_bounds__(128, MINB) post_strip_kernel(PostArgs a) {
+template <int K>
+__global__ void __launch_bounds__(128, 3) post_strip_kernel(PostArgs a) {
+  constexpr int KQ = (K + 3) / 4;     // float4 per low-res pixel that carry classes
+  constexpr int KP = KQ * 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x = blockIdx.x * 32 + lane;
   const int Y0 = (blockIdx.y * 4 + warp) * kPostStripRows;
@@ -226,20 +226,17 @@ __global__ void __launch_bounds__(128, MINB) post_strip_kernel(PostArgs a) {
   const int xi = xin ? x : a.ow - 1;
   const int c0 = __ldg(a.x0 + xi), c1 = __ldg(a.x1 + xi);
   const float wx0 = __ldg(a.lx0 + xi), wx1 = __ldg(a.lx1 + xi);
-  const int kq = (a.k + 3) >> 2;
-  float top[KMAX], bot[KMAX];
+  float top[KP], bot[KP];
   auto load_row = [&](int r, float* dst) {
     const float4* p0 = reinterpret_cast<const float4*>(a.lowres + (((size_t)img * a.lh + r) * a.lw + c0) * a.ldk);
     const float4* p1 = reinterpret_cast<const float4*>(a.lowres + (((size_t)img * a.lh + r) * a.lw + c1) * a.ldk);
 #pragma unroll
-    for (int q = 0; q < KMAX / 4; ++q) {
-      if (q < kq) {
-        const float4 u = __ldg(p0 + q), v = __ldg(p1 + q);
-        dst[4 * q + 0] = __fadd_rn(__fmul_rn(wx0, u.x), __fmul_rn(wx1, v.x));
-        dst[4 * q + 1] = __fadd_rn(__fmul_rn(wx0, u.y), __fmul_rn(wx1, v.y));
-        dst[4 * q + 2] = __fadd_rn(__fmul_rn(wx0, u.z), __fmul_rn(wx1, v.z));
-        dst[4 * q + 3] = __fadd_rn(__fmul_rn(wx0, u.w), __fmul_rn(wx1, v.w));
-      }
+    for (int q = 0; q < KQ; ++q) {
+      const float4 u = __ldg(p0 + q), v = __ldg(p1 + q);
+      dst[4 * q + 0] = __fadd_rn(__fmul_rn(wx0, u.x), __fmul_rn(wx1, v.x));
+      dst[4 * q + 1] = __fadd_rn(__fmul_rn(wx0, u.y), __fmul_rn(wx1, v.y));
+      dst[4 * q + 2] = __fadd_rn(__fmul_rn(wx0, u.z), __fmul_rn(wx1, v.z));
+      dst[4 * q + 3] = __fadd_rn(__fmul_rn(wx0, u.w), __fmul_rn(wx1, v.w));
     }
   };
   int cur0 = -1, cur1 = -1;
@@ -249,7 +246,7 @@ __global__ void __launch_bounds__(128, MINB) post_strip_kernel(PostArgs a) {
     if (r0 != cur0) {
       if (r0 == cur1) {
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) top[k] = bot[k];
+        for (int k = 0; k < KP; ++k) top[k] = bot[k];
       } else {
         load_row(r0, top);
       }
@@ -258,37 +255,43 @@ __global__ void __launch_bounds__(128, MINB) post_strip_kernel(PostArgs a) {
     if (r1 != cur1) {
       if (r1 == cur0) {
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) bot[k] = top[k];
+        for (int k = 0; k < KP; ++k) bot[k] = top[k];
       } else {
         load_row(r1, bot);
       }
       cur1 = r1;
     }
     const float wy0 = __ldg(a.ly0 + y), wy1 = __ldg(a.ly1 + y);
-    // ColorCode's scan (strict '>', first maximum wins, start (0, 0.0)) split into 4 contiguous class blocks that
+    // ColorCode's scan (strict '>', first maximum wins, start (0, 0.0)) split into 3 contiguous class blocks that
     // run as independent dependency chains and are merged left to right with the same strict '>': identical result
-    // (blocks 1..3 start from -inf, which no value -- and no NaN -- fails to beat or tie exactly as in one chain).
-    constexpr int KB = KMAX / 4;
-    int bk[4] = {0, KB, 2 * KB, 3 * KB};
-    float bv[4] = {0.f, -INFINITY, -INFINITY, -INFINITY};
+    // (blocks 1, 2 start from -inf, which no value beats or ties differently than in one chain; a NaN never wins
+    // either way).  The running maximum is fmaxf (keeps the old value on NaN and on ties, like a failed '>').
+    constexpr int KB = (K + 2) / 3;
+    int bk[3] = {0, KB, 2 * KB};
+    float bv[3] = {0.f, -INFINITY, -INFINITY};
     const size_t pix = (size_t)y * a.ow + x;
 #pragma unroll
     for (int i = 0; i < KB; ++i) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 3; ++j) {
         const int k = j * KB + i;
-        if (k < a.k) {
+        if (k < K) {
           const float v = __fadd_rn(__fmul_rn(wy0, top[k]), __fmul_rn(wy1, bot[k]));
-          if (a.logits && xin) a.logits[((size_t)img * a.k + k) * plane + pix] = v;
-          if (v > bv[j]) { bk[j] = k; bv[j] = v; }
+          if (a.logits && xin) a.logits[((size_t)img * K + k) * plane + pix] = v;
+          const bool gt = v > bv[j];
+          bk[j] = gt ? k : bk[j];
+          bv[j] = fmaxf(bv[j], v);
         }
       }
     }
     int k_max = bk[0];
     float c_max = bv[0];
 #pragma unroll
-    for (int j = 1; j < 4; ++j)
-      if (bv[j] > c_max) { k_max = bk[j]; c_max = bv[j]; }
+    for (int j = 1; j < 3; ++j) {
+      const bool gt = bv[j] > c_max;
+      k_max = gt ? bk[j] : k_max;
+      c_max = fmaxf(c_max, bv[j]);
+    }
     if (!xin) continue;
     const float av = __fmul_rn(c_max, 255.0f);
     const int alpha = av >= 255.0f ? 255 : (int)av;  // c_max >= 0 always; trunc toward zero, saturate
@@ -398,11 +401,9 @@ size_t post_smem_bytes(const PostArgs& a) {
 }
 
 cudaError_t launch_post(const PostArgs& a, cudaStream_t s) {
-  if (a.k <= 32 && a.ldk % 4 == 0 && a.ldk >= ((a.k + 3) & ~3)) {
+  if (a.k == 21 && a.ldk % 4 == 0 && a.ldk >= 24) {   // the 21 VOC classes of fcn-resnet50; other K: generic kernel below
     dim3 grid((a.ow + 31) / 32, (a.oh + 4 * kPostStripRows - 1) / (4 * kPostStripRows), a.n);
-    static const int minb = getenv("INFUR_POST_MINB") ? atoi(getenv("INFUR_POST_MINB")) : 2;
-    if (a.k <= 24) { if (minb == 3) post_strip_kernel<24, 3><<<grid, 128, 0, s>>>(a); else post_strip_kernel<24, 2><<<grid, 128, 0, s>>>(a); }
-    else post_strip_kernel<32, 2><<<grid, 128, 0, s>>>(a);
+    post_strip_kernel<21><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
   }
   const size_t smem = post_smem_bytes(a);
