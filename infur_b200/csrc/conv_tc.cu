@@ -288,7 +288,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = g.num_taps * g.cchunks;
+  const int num_kb = g.num_kb;
 
   if (warp == 0 && ptx::elect_one()) {
     for (int v = 0; v < kMaxViews; ++v) ptx::prefetch_tmap(&maps.a[v]);
@@ -336,7 +336,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
         for (int tap = 0; tap < g.num_taps; ++tap) {
           const CUtensorMap* am = &maps.a[g.tap_view[tap]];
           const int x = ox0 + g.tap_dx[tap], y = oy0 + g.tap_dy[tap];
-          for (int cc = 0; cc < g.cchunks; ++cc, ++kb) {
+          const int ncc = g.tap_cc[tap];
+          for (int cc = 0; cc < ncc; ++cc, ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * C::kStageBytes;
             ptx::mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);

@@ -16,7 +16,7 @@
 
 namespace infur {
 
-constexpr int kMaxTaps = 49;
+constexpr int kMaxTaps = 50;   // 7x7 + one fused shortcut tap
 constexpr int kStemWBytes = 7 * 4 * 64 * 8 * 2;   // 28 KB
 constexpr int kStemRowGroups = 17;                // 17 x 128 B = 272 input pixels feed 128 output pixels
 constexpr int kMaxViews = 4;
@@ -25,7 +25,7 @@ struct ConvTcGeom {
   int32_t n_img, oh, ow;
   int32_t bw_log2;            // tile is (1 << bw_log2) wide, 128 >> bw_log2 high
   int32_t tiles_x, tiles_y, tiles_n, num_tiles;
-  int32_t num_taps, cchunks;  // K blocks = num_taps * cchunks, 64 input channels each
+  int32_t num_taps, num_kb;   // K blocks = sum over taps of tap_cc[tap], 64 input channels each
   int32_t out_ld;             // elements between consecutive output pixels
   int32_t relu;
   int32_t store_mode;         // 0: per-thread vector stores (f32 head); 1: smem-staged TMA store; 2: + TMA residual prefetch
@@ -37,6 +37,7 @@ struct ConvTcGeom {
   __half* out;                // fp16 NHWC, or nullptr when out_f32 is used
   float* out_f32;             // f32 NHWC (logit head)
   int8_t tap_view[kMaxTaps + 3];
+  uint8_t tap_cc[kMaxTaps + 3];  // 64-channel chunks of each tap (a fused shortcut tap may differ from the main taps)
   int16_t tap_dx[kMaxTaps + 1];
   int16_t tap_dy[kMaxTaps + 1];
 };

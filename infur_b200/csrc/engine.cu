@@ -74,6 +74,8 @@ static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((
 // ------------------------------------------------------------------------------------------------
 // Model: classify each conv, pack weights into one device arena.
 
+static bool skip_fusion_env() { const char* e = getenv("INFUR_B200_NO_SHORTCUT_FUSION"); return e && e[0] == '1'; }
+
 static void classify_conv(const ConvOp& c, bool reads_input, bool is_head, DevConv& d) {
   d.cin = c.cin; d.cout = c.cout; d.kh = c.kh; d.kw = c.kw; d.stride = c.stride; d.pad = c.pad; d.dil = c.dil; d.relu = c.relu;
   d.stem = false; d.tc_ok = false;
@@ -89,10 +91,11 @@ static void classify_conv(const ConvOp& c, bool reads_input, bool is_head, DevCo
     d.tc_ok = d.why_not.empty();
     return;
   }
-  d.taps = c.kh * c.kw; d.cchunks = c.cin / 64; d.kdim = d.taps * c.cin;
+  d.taps = c.kh * c.kw; d.cchunks = c.cin / 64; d.kdim = d.taps * c.cin + c.cin2;
+  d.cin2 = c.in2 >= 0 ? c.cin2 : 0; d.stride2 = c.stride2;
   if (c.cin % 64 != 0) d.why_not = "cin is not a multiple of 64";
   else if (c.stride != 1 && c.stride != 2) d.why_not = "stride must be 1 or 2";
-  else if (d.taps > kMaxTaps) d.why_not = "more than 49 filter taps";
+  else if (d.taps + (d.cin2 ? 1 : 0) > kMaxTaps) d.why_not = "more than 49 filter taps";
   d.tc_ok = d.why_not.empty();
 }
 
@@ -101,6 +104,7 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
   dm->lm = std::move(lm);
   LoweredModel& m = dm->lm;
   if (m.heads.empty()) return Status::error(INFUR_E_MODEL_LOAD, "model has no output head");
+  if (cfg.conv_impl == INFUR_CONV_TCGEN05 && !skip_fusion_env()) fuse_projection_shortcuts(m);
   dm->out_head = 0;                                   // the reference consumes out[0] only (app.rs:116)
   dm->aux_head = m.heads.size() > 1 ? 1 : -1;
   // ops needed for the computed heads
@@ -117,6 +121,7 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
     dm->needed[p] = 1;
     stack.push_back(m.ops[p].in);
     if (m.ops[p].kind == OpKind::Conv && m.ops[p].conv.residual >= 0) stack.push_back(m.ops[p].conv.residual);
+    if (m.ops[p].kind == OpKind::Conv && m.ops[p].conv.in2 >= 0) stack.push_back(m.ops[p].conv.in2);
   }
   std::vector<char> is_head_tensor(m.num_tensors, 0);
   for (auto& h : m.heads) is_head_tensor[h.tensor] = 1;
@@ -155,14 +160,19 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
         __half* wv = reinterpret_cast<__half*>(host.data() + d.wv_off);
         for (size_t j = 0; j < c.weight.size(); ++j) wv[j] = __float2half_rn(c.weight[j]);
       } else {
-        for (size_t j = 0; j < c.weight.size(); ++j) w16[j] = __float2half_rn(c.weight[j]);  // [cout][kh][kw][cin] == [cout][kdim]
+        // [cout][kh][kw][cin] (+ [cout][cin2] of a fused shortcut) == [cout][kdim]
+        const size_t k1 = (size_t)c.kh * c.kw * c.cin;
+        for (int co = 0; co < c.cout; ++co) {
+          for (size_t j = 0; j < k1; ++j) w16[(size_t)co * d.kdim + j] = __float2half_rn(c.weight[(size_t)co * k1 + j]);
+          for (int j = 0; j < d.cin2; ++j) w16[(size_t)co * d.kdim + k1 + j] = __float2half_rn(c.weight2[(size_t)co * d.cin2 + j]);
+        }
       }
       float* b = reinterpret_cast<float*>(host.data() + d.b_off);
       for (int co = 0; co < c.cout; ++co) b[co] = c.bias[co];
     }
     CU_TRY(cudaMemcpy(dm->arena, host.data(), off, cudaMemcpyHostToDevice));
   }
-  for (auto& op : m.ops) { std::vector<float>().swap(op.conv.weight); }
+  for (auto& op : m.ops) { std::vector<float>().swap(op.conv.weight); std::vector<float>().swap(op.conv.weight2); }
   out = std::move(dm);
   return Status();
 }
@@ -177,6 +187,8 @@ struct ConvIO {
   const __half* wgt = nullptr; // [cout_pad][kdim]
   const float* bias = nullptr;
   const __half* residual = nullptr;
+  const __half* x2 = nullptr;  // fused shortcut source [n][h2][w2][cin2]
+  int h2 = 0, w2 = 0;
   __half* y = nullptr;
   float* y_f32 = nullptr;
   int out_ld = 0;
@@ -201,7 +213,7 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   g.tiles_x = (io.ow + bw - 1) / bw; g.tiles_y = (io.oh + bh - 1) / bh;
   g.tiles_n = d.cout_pad / block_n;
   g.num_tiles = io.n * g.tiles_x * g.tiles_y * g.tiles_n;
-  g.num_taps = d.taps; g.cchunks = d.cchunks;
+  g.num_taps = d.taps + (d.cin2 ? 1 : 0); g.num_kb = d.taps * d.cchunks + d.cin2 / 64;
   g.out_ld = io.out_ld; g.relu = d.relu ? 1 : 0;
   g.store_mode = io.y_f32 ? 0 : (io.residual ? 2 : 1);
   g.epi_bufs = g.store_mode == 0 ? 0 : (g.store_mode == 1 ? 2 : 4);
@@ -249,7 +261,19 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
         g.tap_view[t] = (int8_t)(have[py * s + px] ? py * s + px : first);
         g.tap_dy[t] = (int16_t)(have[py * s + px] ? qy : 30000);
         g.tap_dx[t] = (int16_t)qx;
+        g.tap_cc[t] = (uint8_t)d.cchunks;
       }
+    if (d.cin2) {
+      // fused projection shortcut: one more tap reading the block input through its own (strided) view.  The main
+      // convolution is 1x1 / stride 1 (fuse_projection_shortcuts), so view 1 is free.
+      const int s2 = d.stride2;
+      const uint64_t dims[4] = {(uint64_t)d.cin2, (uint64_t)((io.w2 + s2 - 1) / s2), (uint64_t)((io.h2 + s2 - 1) / s2), (uint64_t)io.n};
+      const uint64_t strides[3] = {(uint64_t)s2 * d.cin2 * 2, (uint64_t)s2 * io.w2 * d.cin2 * 2, (uint64_t)io.h2 * io.w2 * d.cin2 * 2};
+      st = make_tmap_f16(&po.maps.a[1], io.x2, 4, dims, strides, box);
+      if (!st.ok()) return st;
+      const int t = d.taps;
+      g.tap_view[t] = 1; g.tap_dx[t] = 0; g.tap_dy[t] = 0; g.tap_cc[t] = (uint8_t)(d.cin2 / 64);
+    }
   }
   if (!d.stem) {
     const uint64_t dims[2] = {(uint64_t)d.kdim, (uint64_t)d.cout_pad};
@@ -411,6 +435,13 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       if (tr.h != to.h || tr.w != to.w || tr.c != to.c) return Status::error(INFUR_E_SHAPE, "Invalid input shape: residual size mismatch at '" + op.name + "'");
       last_use[op.conv.residual] = (int)i;
     }
+    if (op.kind == OpKind::Conv && op.conv.in2 >= 0) {
+      const TensorInfo& t2 = p.tensors[op.conv.in2];
+      const int s2 = op.conv.stride2;
+      if ((t2.h - 1) / s2 + 1 != to.h || (t2.w - 1) / s2 + 1 != to.w || t2.c != op.conv.cin2)
+        return Status::error(INFUR_E_SHAPE, "Invalid input shape: shortcut size mismatch at '" + op.name + "'");
+      last_use[op.conv.in2] = (int)i;
+    }
     if (op.kind == OpKind::MaxPool && ti.c % 8 != 0) return Status::error(INFUR_E_UNSUPPORTED, "MaxPool needs channels % 8 == 0");
   }
   for (auto& hd : m.heads) last_use[hd.tensor] = 1 << 30;
@@ -445,7 +476,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
     to.ptr = pool[pick].ptr;
     auto release = [&](int t) { if (t >= 0 && tensor_buf[t] >= 0 && last_use[t] == (int)i) pool[tensor_buf[t]].free_ = true; };
     release(op.in);
-    if (op.kind == OpKind::Conv) release(op.conv.residual);
+    if (op.kind == OpKind::Conv) { release(op.conv.residual); release(op.conv.in2); }
   }
   // ---- ops
   for (size_t i = 0; i < m.ops.size(); ++i) {
@@ -464,6 +495,10 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       io.wgt = reinterpret_cast<const __half*>(M->arena + d.w_off);
       io.bias = reinterpret_cast<const float*>(M->arena + d.b_off);
       io.residual = op.conv.residual >= 0 ? reinterpret_cast<const __half*>(p.tensors[op.conv.residual].ptr) : nullptr;
+      if (op.conv.in2 >= 0) {
+        const TensorInfo& t2 = p.tensors[op.conv.in2];
+        io.x2 = reinterpret_cast<const __half*>(t2.ptr); io.h2 = t2.h; io.w2 = t2.w;
+      }
       if (to.f32) io.y_f32 = reinterpret_cast<float*>(to.ptr); else io.y = reinterpret_cast<__half*>(to.ptr);
       io.out_ld = to.ld;
       if (d.tc_ok) { if (!(st = setup_conv_tc(d, io, po, d.block_n)).ok()) return st; }
@@ -471,14 +506,14 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
         if (!(st = tune_block_n(H, d, io, po)).ok()) return st;
       }
       setup_direct(d, io, reinterpret_cast<const __half*>(M->arena + d.wv_off), po.direct);
-      po.flops = 2.0 * n * to.h * to.w * (double)d.cout * d.kh * d.kw * d.cin;
+      po.flops = 2.0 * n * to.h * to.w * (double)d.cout * (d.kh * d.kw * d.cin + d.cin2);
       po.bytes = (double)n * ti.h * ti.w * d.cin * 2 + (double)to.bytes + (io.residual ? (double)n * to.h * to.w * to.c * 2 : 0.0) +
-                 (double)d.cout * d.kh * d.kw * d.cin * 2;
+                 (double)d.cout * (d.kh * d.kw * d.cin + d.cin2) * 2 + (io.x2 ? (double)n * io.h2 * io.w2 * d.cin2 * 2 : 0.0);
       os << "conv " << op.name << " [" << n << "x" << ti.h << "x" << ti.w << "x" << d.cin << "] -> [" << to.h << "x" << to.w << "x" << d.cout
-         << "] k" << d.kh << " s" << d.stride << " p" << d.pad << " d" << d.dil << (io.residual ? " +res" : "") << (d.relu ? " relu" : "");
+         << "] k" << d.kh << " s" << d.stride << " p" << d.pad << " d" << d.dil << (io.residual ? " +res" : "") << (d.cin2 ? " +shortcut1x1" : "") << (d.relu ? " relu" : "");
       if (d.tc_ok)
         os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << po.block_n << " tiles "
-           << po.geom.num_tiles << " kblocks " << d.taps * d.cchunks;
+           << po.geom.num_tiles << " kblocks " << po.geom.num_kb;
       os << " | GFLOP " << po.flops * 1e-9 << " MB " << po.bytes * 1e-6;
     } else {
       po.flops = 0;

@@ -32,6 +32,7 @@ struct DevConv {
   bool tc_ok = false;      // expressible by the tcgen05 kernel
   std::string why_not;     // reason when !tc_ok
   int block_n = 0, cout_pad = 0, taps = 0, cchunks = 0, kdim = 0;
+  int cin2 = 0, stride2 = 1;  // fused projection shortcut (ConvOp::in2): one extra tap of cin2 channels
   size_t w_off = 0;        // fp16 [cout_pad][kdim] for the tcgen05 kernel (byte offset into the arena)
   size_t wv_off = 0;       // fp16 [cout][kh][kw][cin] for the validation kernel (== w_off unless stem)
   size_t b_off = 0;        // f32 [cout_pad]

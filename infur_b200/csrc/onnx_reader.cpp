@@ -410,6 +410,37 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
   m.heads = ordered;
 }
 
+int fuse_projection_shortcuts(LoweredModel& m) {
+  int fused = 0;
+  for (size_t i = 0; i < m.ops.size(); ++i) {
+    LoweredOp& op = m.ops[i];
+    if (op.kind != OpKind::Conv) continue;
+    ConvOp& c = op.conv;
+    if (c.residual < 0 || c.in2 >= 0 || c.kh != 1 || c.kw != 1 || c.stride != 1 || c.pad != 0 || c.cin % 64 != 0) continue;
+    // producer of the residual: a bare 1x1 convolution whose output nobody else reads
+    int pj = -1, uses = 0;
+    for (size_t j = 0; j < m.ops.size(); ++j) {
+      if (m.ops[j].out == c.residual) pj = (int)j;
+      if (m.ops[j].in == c.residual) ++uses;
+      if (m.ops[j].kind == OpKind::Conv && (m.ops[j].conv.residual == c.residual || m.ops[j].conv.in2 == c.residual)) ++uses;
+    }
+    for (auto& h : m.heads) if (h.tensor == c.residual) ++uses;
+    if (pj < 0 || pj >= (int)i || uses != 1 || m.ops[pj].kind != OpKind::Conv) continue;
+    const ConvOp& d = m.ops[pj].conv;
+    if (d.kh != 1 || d.kw != 1 || d.pad != 0 || d.relu || d.residual >= 0 || d.in2 >= 0 || d.cout != c.cout || d.cin % 64 != 0 ||
+        (d.stride != 1 && d.stride != 2))
+      continue;
+    c.in2 = m.ops[pj].in; c.cin2 = d.cin; c.stride2 = d.stride; c.weight2 = d.weight;
+    for (int co = 0; co < c.cout; ++co) c.bias[co] += d.bias[co];
+    c.residual = -1;
+    op.name += " + " + m.ops[pj].name;
+    m.ops.erase(m.ops.begin() + pj);
+    --i;
+    ++fused;
+  }
+  return fused;
+}
+
 std::string describe(const LoweredModel& m) {
   std::ostringstream os;
   os << "inputs:";

@@ -73,6 +73,10 @@ struct ConvOp {
   int residual = -1;                 // tensor id added before the ReLU, or -1
   std::vector<float> weight;         // [cout][kh][kw][cin]  (OHWI, f32; packed to fp16 at upload)
   std::vector<float> bias;           // [cout]
+  // Fused projection shortcut (fuse_projection_shortcuts): a second 1x1 / pad 0 convolution with stride `stride2`
+  // over tensor `in2` accumulated into the same output: out = act(conv(in) + conv2(in2) + bias), bias = b + b2.
+  int in2 = -1, cin2 = 0, stride2 = 1;
+  std::vector<float> weight2;        // [cout][cin2]
 };
 
 struct LoweredOp {
@@ -117,6 +121,10 @@ struct ModelError : public std::exception {
 
 // Throws ModelError.
 void lower_model(const OnnxGraph& g, LoweredModel& m);
+// ResNet blocks with a projection shortcut compute relu(conv3(y) + downsample(x)): two 1x1 convolutions summed.
+// This pass turns each such pair into ONE convolution with two sources (one accumulator, K = cin3 + cin_down),
+// removing the shortcut tensor's round trip through memory.  Returns the number of pairs fused.
+int fuse_projection_shortcuts(LoweredModel& m);
 std::string describe(const LoweredModel& m);
 
 }  // namespace infur

@@ -56,7 +56,7 @@ def _h(x: torch.Tensor) -> torch.Tensor:
 def forward_lowres_fp16emu(model, x_nchw: np.ndarray, head: str = "out") -> np.ndarray:
     """Same network with the product's rounding points emulated: BN folded into the conv,
     weights and every stored activation rounded to fp16, accumulation and bias/residual/ReLU in
-    fp32, final logits kept in fp32."""
+    fp32, projection shortcuts summed into conv3 unrounded, final logits kept in fp32."""
     model.eval()
     bb = model.backbone
 
@@ -77,7 +77,9 @@ def forward_lowres_fp16emu(model, x_nchw: np.ndarray, head: str = "out") -> np.n
         for blk in getattr(bb, lname):
             idt = x
             if blk.downsample is not None:
-                idt = cbr(x, blk.downsample[0], blk.downsample[1], relu=False)
+                # the product fuses the projection shortcut into conv3's accumulator (one f32 sum), so the shortcut
+                # is never rounded to fp16 on its own
+                idt = cbr(x, blk.downsample[0], blk.downsample[1], relu=False, round_out=False)
             y = cbr(x, blk.conv1, blk.bn1)
             y = cbr(y, blk.conv2, blk.bn2)
             x = cbr(y, blk.conv3, blk.bn3, relu=True, res=idt)
