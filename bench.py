@@ -160,17 +160,23 @@ def run_reference(args, rank: int, world: int):
             oracle.color_code_image(out[0].numpy())
             oracle.frame_rgba(scaled)
 
-    for i in range(args.warmup):
+    for i in range(min(args.warmup, 2)):
         one(i)
+    # bounded sample: one frame per step, at most --cpu-budget-s seconds of CPU work in total
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        one(i)
+    done = 0
+    while done < args.steps:
+        one(done)
+        done += 1
+        if time.perf_counter() - t0 > args.cpu_budget_s and done >= 3:
+            break
     dt = time.perf_counter() - t0
-    fps = args.steps / dt
-    sample = f"{args.steps} single 1920x1080 frames (one frame per step), torch-CPU fp32 FCN-ResNet50 both heads + numpy Scale/ColorCode"
+    fps = done / dt
+    args.steps_timed = done
+    sample = f"{done} single 1920x1080 frames (one frame per step; {args.steps} requested, bounded to {args.cpu_budget_s:.0f} s), torch-CPU fp32 FCN-ResNet50 both heads + numpy Scale/ColorCode"
     print(json.dumps({
         "impl": "reference", "metric": "1080p frames/sec through FCN-ResNet50", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "steps_timed": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "1080p synthetic stream, FCN-ResNet50 (seeded synthetic weights), scale 1.0; CPU restatement of the reference's "
                                "onnxruntime path (the reference itself cannot be built here: no Rust/onnxruntime/model file)", "frames_per_step": 1},
@@ -367,6 +373,7 @@ def main():
     ap.add_argument("--ring-depth", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=90.0, help="--impl reference: stop after this many seconds of timed CPU work")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

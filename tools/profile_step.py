@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--steps", type=int, default=0)
     ap.add_argument("--kind", default="fcn50")
+    ap.add_argument("--cuda-profiler", action="store_true", help="bracket the back-to-back steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     a = ap.parse_args()
     import torch
 
@@ -57,12 +58,17 @@ def main():
             print(f"total {tot_ms:.3f} ms per step of {B} frames -> {B / tot_ms * 1e3:.1f} frames/s (whole path), {tot_fl / tot_ms:.1f} TFLOP/s")
         stream = torch.cuda.ExternalStream(h.compute_stream())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        K = max(a.steps, 3)
+        K = max(a.steps, 3) if not a.cuda_profiler else max(a.steps, 1)
+        if a.cuda_profiler:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         e0.record(stream)
         for _ in range(K):
             h.advance_device(d.data_ptr(), B, W, H, d_class.data_ptr(), d_rgba.data_ptr())
         e1.record(stream)
         stream.synchronize()
+        if a.cuda_profiler:
+            torch.cuda.profiler.stop()
         t = e0.elapsed_time(e1) / K
         print(f"back-to-back: {t:.3f} ms per step -> {B / t * 1e3:.1f} frames/s")
 
