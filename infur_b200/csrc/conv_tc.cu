@@ -62,6 +62,22 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcGeom& g, int tile) 
   return t;
 }
 
+// Static persistent schedules: which linear tile (m * tiles_n + nt) a CTA works on in its it-th round, -1 = done.
+struct Sched1 {   // one CTA per tile
+  int first, step, total;
+  __device__ __forceinline__ int tile(int it) const { const int t = first + it * step; return t < total ? t : -1; }
+  __device__ __forceinline__ int count() const { return first < total ? (total - first + step - 1) / step : 0; }
+};
+struct Sched2 {   // one CTA pair per (two consecutive M tiles, one N tile); an odd last M tile pairs with a tile outside the batch
+  int cluster, nclusters, rank, tiles_n, num_work;
+  __device__ __forceinline__ int tile(int it) const {
+    const int w = cluster + it * nclusters;
+    if (w >= num_work) return -1;
+    return (2 * (w / tiles_n) + rank) * tiles_n + w % tiles_n;
+  }
+  __device__ __forceinline__ int count() const { return cluster < num_work ? (num_work - cluster + nclusters - 1) / nclusters : 0; }
+};
+
 // Direct-store epilogue (f32 logit head): thread = output pixel, 32 channels at a time.
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int quad, int lane,
@@ -146,16 +162,16 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 // announces its part through the chunk_ready mbarrier and moves on.
 struct EpiBars { uint32_t res, ready, free_; };
 
-template <int BLOCK_N, bool HAS_RES>
-__device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, const EpiBars eb,
-                                             uint32_t epi_base, int ew, int lane) {
+template <int BLOCK_N, bool HAS_RES, class Sched, bool PAIR = false>
+__device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sched, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                             const EpiBars eb, uint32_t epi_base, int ew, int lane) {
   constexpr int CH = BLOCK_N / 64;            // chunks per tile
   constexpr int EB = HAS_RES ? 4 : 2;         // smem chunk buffers
   const int quad = ew & 3, half = ew >> 2;
   const int row = quad * 32 + lane;
   const uint32_t sw = (uint32_t)(row & 7);
   int q = 0, it = 0;
-  for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+  for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
     const int n0 = (tile % g.tiles_n) * BLOCK_N;
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -176,10 +192,13 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, uint32_t tmem_
       uint32_t acc[32];
       ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), acc);
       ptx::tmem_ld_wait();
-      if (c == CH - 1) {   // accumulator stage fully read: hand it back to the MMA warp
+      if (c == CH - 1) {   // accumulator stage fully read: hand it back to the MMA warp (of the leader CTA in a pair)
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty0 + 8u * as);
+        if (lane == 0) {
+          if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(tempty0 + 8u * as, 0));
+          else ptx::mbar_arrive(tempty0 + 8u * as);
+        }
       }
       uint4 res[4];
       if (HAS_RES) {
@@ -230,14 +249,13 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, uint32_t tmem_
 // The single thread that owns every bulk copy of the epilogue: stores chunk q when all eight warps have
 // written it, then (one store later, so it never waits on the store it just issued) recycles the previous
 // buffer: HAS_RES -> prefetch the residual of chunk q-1+EB into it, else -> mark it free.
-template <int BLOCK_N, bool HAS_RES>
-__device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvTcGeom& g, const EpiBars eb, uint32_t epi_base) {
+template <int BLOCK_N, bool HAS_RES, class Sched>
+__device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvTcGeom& g, const Sched sched, const EpiBars eb, uint32_t epi_base) {
   constexpr int CH = BLOCK_N / 64;
   constexpr int EB = HAS_RES ? 4 : 2;
-  const int my_tiles = (int)blockIdx.x < g.num_tiles ? (g.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int total = my_tiles * CH;
+  const int total = sched.count() * CH;
   auto issue_res = [&](int qq) {
-    const TileCoord tc = decode_tile(g, (int)blockIdx.x + (qq / CH) * (int)gridDim.x);
+    const TileCoord tc = decode_tile(g, sched.tile(qq / CH));
     const int b = qq % EB;
     ptx::mbar_expect_tx(eb.res + 8u * b, (uint32_t)kEpiBufBytes);
     ptx::tma_load_4d(epi_base + b * kEpiBufBytes, &maps.r, eb.res + 8u * b, tc.nt * BLOCK_N + (qq % CH) * 64, tc.ox0, tc.oy0, tc.img);
@@ -245,8 +263,8 @@ __device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvT
   if (HAS_RES) {
     for (int p = 0; p < EB && p < total; ++p) issue_res(p);
   }
-  int q = 0;
-  for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+  int q = 0, it = 0;
+  for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
     const TileCoord tc = decode_tile(g, tile);
     for (int c = 0; c < CH; ++c, ++q) {
       const int b = q % EB;
@@ -382,8 +400,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     // ===================== epilogue DMA =====================
     if constexpr (BLOCK_N >= 64) {
       if (ptx::elect_one()) {
-        if (g.store_mode == 1) epilogue_dma<BLOCK_N, false>(maps, g, eb, epi_base);
-        else if (g.store_mode == 2) epilogue_dma<BLOCK_N, true>(maps, g, eb, epi_base);
+        const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
+        if (g.store_mode == 1) epilogue_dma<BLOCK_N, false>(maps, g, sched, eb, epi_base);
+        else if (g.store_mode == 2) epilogue_dma<BLOCK_N, true>(maps, g, sched, eb, epi_base);
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -392,8 +411,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     if (g.store_mode == 0) {
       if (ew < 4) epilogue_direct<BLOCK_N>(g, tmem_base, tfull_bar(0), tempty_bar(0), ew, lane, ew * 32 + lane);
     } else if constexpr (BLOCK_N >= 64) {
-      if (g.store_mode == 1) epilogue_tma<BLOCK_N, false>(g, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-      else epilogue_tma<BLOCK_N, true>(g, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
+      if (g.store_mode == 1) epilogue_tma<BLOCK_N, false>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      else epilogue_tma<BLOCK_N, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
     }
   }
 
@@ -402,6 +422,146 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for 256-wide N tiles: the two CTAs of a cluster compute a 256 (M) x 256 (N)
+// tile.  Each CTA loads its own 128 pixels of A and HALF of the weight tile (128 of the 256 output channels), the
+// leader's single thread issues tcgen05.mma.cta_group::2 (M = 256), which reads A from each CTA's smem and B from
+// both, and each CTA keeps the accumulator of its own 128 pixels in its own TMEM.  Per SM and K block that is
+// 32 KB of operands instead of 48 KB: less L2 -> SM traffic per FLOP and room for 5-6 pipeline stages instead of
+// 3-4.  Everything after the accumulator (epilogue, TMA stores, residual prefetch) is per CTA and unchanged.
+//   full[s]   lives in the leader: its producer arms 64 KB; both CTAs' TMA loads complete_tx on it
+//   empty[s], tmem_full[a]   one per CTA, signalled by the leader's multicast tcgen05.commit
+//   tmem_empty[a]   in the leader, counts the epilogue warps of BOTH CTAs (remote mbarrier arrive)
+constexpr int kPairStageBytes = kABytes + 128 * kBlockK * 2;   // 32 KB
+
+__host__ __device__ constexpr int pair_stages(int epi_bufs) {
+  const int s = (kSmemLimit - 1024 - kBarBytes - epi_bufs * kEpiBufBytes) / kPairStageBytes;
+  return s > kMaxStages ? kMaxStages : s;
+}
+__host__ __device__ constexpr int pair_smem_bytes(int epi_bufs) { return pair_stages(epi_bufs) * kPairStageBytes + epi_bufs * kEpiBufBytes + 1024 + kBarBytes; }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
+  constexpr int BLOCK_N = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const int num_stages = g.stages;
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + num_stages * kPairStageBytes;
+  const uint32_t bar_base = epi_base + g.epi_bufs * kEpiBufBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  EpiBars eb;
+  eb.res = bar_base + 8u * (2 * kMaxStages + 4);
+  eb.ready = eb.res + 8u * kMaxEpiBufs;
+  eb.free_ = eb.ready + 8u * kMaxEpiBufs;
+  const uint32_t tmem_ptr_addr = eb.free_ + 8u * kMaxEpiBufs;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();
+  const Sched2 sched{(int)blockIdx.x >> 1, (int)gridDim.x >> 1, rank, g.tiles_n, g.num_work};
+
+  if (warp == 0 && ptx::elect_one()) {
+    for (int v = 0; v < kMaxViews; ++v) ptx::prefetch_tmap(&maps.a[v]);
+    ptx::prefetch_tmap(&maps.b);
+    ptx::prefetch_tmap(&maps.c);
+    if (g.store_mode == 2) ptx::prefetch_tmap(&maps.r);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < num_stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+    for (int s = 0; s < kMaxEpiBufs; ++s) {
+      ptx::mbar_init(eb.res + 8u * s, 1);
+      ptx::mbar_init(eb.ready + 8u * s, kEpiWarps);
+      ptx::mbar_init(eb.free_ + 8u * s, 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2sm(tmem_ptr_addr, 2 * BLOCK_N);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();      // barrier inits and TMEM of both CTAs are in place before anything crosses the pair
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
+        const TileCoord tc = decode_tile(g, tile);
+        int kb = 0;
+        for (int tap = 0; tap < g.num_taps; ++tap) {
+          const CUtensorMap* am = &maps.a[g.tap_view[tap]];
+          const int x = tc.ox0 + g.tap_dx[tap], y = tc.oy0 + g.tap_dy[tap];
+          const int ncc = g.tap_cc[tap];
+          for (int cc = 0; cc < ncc; ++cc, ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + stage * kPairStageBytes;
+            const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
+            if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2u * (uint32_t)kPairStageBytes);
+            ptx::tma_load_4d_2sm(a_dst, am, lead_full, cc * kBlockK, x, y, tc.img);
+            ptx::tma_load_2d_2sm(a_dst + kABytes, &maps.b, lead_full, kb * kBlockK, tc.nt * BLOCK_N + rank * 128);
+            if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kBlockM, BLOCK_N);
+      const int num_kb = g.num_kb;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);  // the epilogues of BOTH CTAs drained this accumulator stage
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * kPairStageBytes;
+          const uint64_t a_desc = ptx::make_smem_desc(a_addr, 128);
+          const uint64_t b_desc = ptx::make_smem_desc(a_addr + kABytes, 128);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            ptx::umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          ptx::umma_commit_2sm(empty_bar(stage), 3);
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit_2sm(tfull_bar(as), 3);
+      }
+    }
+  } else if (warp == kDmaWarp) {
+    if (ptx::elect_one()) {
+      if (g.store_mode == 1) epilogue_dma<BLOCK_N, false>(maps, g, sched, eb, epi_base);
+      else epilogue_dma<BLOCK_N, true>(maps, g, sched, eb, epi_base);
+    }
+  } else if (warp >= kEpiWarp0) {
+    const int ew = warp - kEpiWarp0;
+    if (g.store_mode == 1) epilogue_tma<BLOCK_N, false, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    else epilogue_tma<BLOCK_N, true, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();      // nobody leaves while the peer may still touch this CTA's smem, barriers or TMEM
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
   }
 }
 
@@ -511,9 +671,10 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       }
     }
   } else if (warp == kDmaWarp) {
-    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false>(maps, g, eb, epi_base);
+    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false>(maps, g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, eb, epi_base);
   } else if (warp >= kEpiWarp0) {
-    epilogue_tma<BLOCK_N, false>(g, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
+    epilogue_tma<BLOCK_N, false>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
+                                 warp - kEpiWarp0, lane);
   }
 
   ptx::tc_fence_before();
@@ -535,6 +696,8 @@ cudaError_t launch_one(const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms,
 
 }  // namespace
 
+int conv_tc_pair_stages(int epi_bufs) { return pair_stages(epi_bufs); }
+
 int conv_tc_stages(int block_n, int epi_bufs) {
   switch (block_n) {
     case 32: return Cfg<32>::stages(epi_bufs);
@@ -551,6 +714,7 @@ cudaError_t conv_tc_init() {
   if ((e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -560,6 +724,13 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     if (grid <= 0) return cudaSuccess;
     if (block_n != 64 || g.store_mode != 1 || g.bw_log2 != 7) return cudaErrorInvalidValue;
     stem_tc_kernel<<<grid, kThreads, kStemSmemBytes, stream>>>(maps, g);
+    return cudaGetLastError();
+  }
+  if (g.pair) {
+    const int clusters = g.num_work < num_sms / 2 ? g.num_work : num_sms / 2;
+    if (clusters <= 0) return cudaSuccess;
+    if (block_n != 256 || g.store_mode == 0 || g.stages != pair_stages(g.epi_bufs)) return cudaErrorInvalidValue;
+    conv_tc_pair_kernel<<<2 * clusters, kThreads, pair_smem_bytes(g.epi_bufs), stream>>>(maps, g);
     return cudaGetLastError();
   }
   switch (block_n) {

@@ -30,6 +30,7 @@ struct ConvTcGeom {
   int32_t relu;
   int32_t store_mode;         // 0: per-thread vector stores (f32 head); 1: smem-staged TMA store; 2: + TMA residual prefetch
   int32_t stages, epi_bufs;   // smem pipeline depth and epilogue chunk buffers (0 / 2 / 4), see conv_tc_stages
+  int32_t pair, num_work;     // 1: conv_tc_pair_kernel (cta_group::2); work items = ceil(M tiles / 2) * tiles_n
   int32_t stem;               // 1: 7x7/s2 RGB stem through stem_tc_kernel (maps.a[0] = row-group view of the padded NHWC4 input)
   const __half* stem_w;       // stem weights in smem order [7 ky][4 k-cores][64 cout][8], kStemWBytes
   const float* bias;          // [tiles_n * BLOCK_N]
@@ -54,5 +55,6 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
 // One-time: opt in to the dynamic shared memory each instantiation needs.
 cudaError_t conv_tc_init();
 int conv_tc_stages(int block_n, int epi_bufs);
+int conv_tc_pair_stages(int epi_bufs);
 
 }  // namespace infur

@@ -76,6 +76,8 @@ static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((
 
 static bool skip_fusion_env() { const char* e = getenv("INFUR_B200_NO_SHORTCUT_FUSION"); return e && e[0] == '1'; }
 
+static bool pair_disabled_env() { const char* e = getenv("INFUR_B200_NO_CTA_PAIR"); return e && e[0] == '1'; }
+
 static void classify_conv(const ConvOp& c, bool reads_input, bool is_head, DevConv& d) {
   d.cin = c.cin; d.cout = c.cout; d.kh = c.kh; d.kw = c.kw; d.stride = c.stride; d.pad = c.pad; d.dil = c.dil; d.relu = c.relu;
   d.stem = false; d.tc_ok = false;
@@ -194,8 +196,8 @@ struct ConvIO {
   int out_ld = 0;
 };
 
-static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int block_n) {
-  po.block_n = block_n;
+static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int block_n, bool pair = false) {
+  po.block_n = block_n; po.pair = pair;
   ConvTcGeom& g = po.geom;
   memset(&g, 0, sizeof(g));
   memset(&po.maps, 0, sizeof(po.maps));
@@ -217,7 +219,9 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   g.out_ld = io.out_ld; g.relu = d.relu ? 1 : 0;
   g.store_mode = io.y_f32 ? 0 : (io.residual ? 2 : 1);
   g.epi_bufs = g.store_mode == 0 ? 0 : (g.store_mode == 1 ? 2 : 4);
-  g.stages = conv_tc_stages(block_n, g.epi_bufs);
+  g.stages = pair ? conv_tc_pair_stages(g.epi_bufs) : conv_tc_stages(block_n, g.epi_bufs);
+  g.pair = pair ? 1 : 0;
+  g.num_work = ((io.n * g.tiles_x * g.tiles_y + 1) / 2) * g.tiles_n;
   g.bias = io.bias; g.residual = io.residual; g.out = io.y; g.out_f32 = io.y_f32;
   Status st;
   const uint32_t box[4] = {64, (uint32_t)(d.stem ? 128 : bw), (uint32_t)(d.stem ? 1 : bh), 1};
@@ -278,7 +282,7 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   if (!d.stem) {
     const uint64_t dims[2] = {(uint64_t)d.kdim, (uint64_t)d.cout_pad};
     const uint64_t strides[1] = {(uint64_t)d.kdim * 2};
-    const uint32_t bbox[2] = {64, (uint32_t)block_n};
+    const uint32_t bbox[2] = {64, (uint32_t)(pair ? 128 : block_n)};   // a CTA pair splits the weight tile between its CTAs
     st = make_tmap_f16(&po.maps.b, io.wgt, 2, dims, strides, bbox);
     if (!st.ok()) return st;
   } else {
@@ -314,36 +318,39 @@ static void setup_direct(const DevConv& d, const ConvIO& io, const __half* wv, D
 // result is bit-identical whichever wins; only time differs: a narrower tile leaves room for more pipeline
 // stages (more HBM bytes in flight for the memory-bound 1x1 convs), a wider one halves the activation re-reads.
 static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO& io, PlanOp& po) {
-  static const int cands[3] = {256, 128, 64};
+  struct Cand { int bn; bool pair; };
+  static const Cand cands[4] = {{256, true}, {256, false}, {128, false}, {64, false}};
   if (d.stem) return Status();
+  const bool allow_pair = !pair_disabled_env();
   cudaEvent_t e0, e1;
   CU_TRY(cudaEventCreate(&e0));
   CU_TRY(cudaEventCreate(&e1));
-  int best_bn = po.block_n;
+  Cand best = {po.block_n, po.pair};
   float best_ms = 1e30f;
   Status st;
   // two interleaved rounds, minimum per candidate: a single short measurement is at the mercy of clock ramps
   for (int round = 0; round < 2 && st.ok(); ++round) {
-    for (int bn : cands) {
-      if (bn > d.block_n || d.cout_pad % bn != 0) continue;
+    for (const Cand& c : cands) {
+      if (c.bn > d.block_n || d.cout_pad % c.bn != 0 || (c.pair && !allow_pair)) continue;
       PlanOp trial;
-      if (!(st = setup_conv_tc(d, io, trial, bn)).ok()) break;
-      cudaError_t e = conv_tc_launch(bn, trial.maps, trial.geom, H->num_sms, H->stream);   // warm-up
+      if (!(st = setup_conv_tc(d, io, trial, c.bn, c.pair)).ok()) break;
+      cudaError_t e = conv_tc_launch(c.bn, trial.maps, trial.geom, H->num_sms, H->stream);   // warm-up
       cudaEventRecord(e0, H->stream);
-      for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = conv_tc_launch(bn, trial.maps, trial.geom, H->num_sms, H->stream);
+      for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = conv_tc_launch(c.bn, trial.maps, trial.geom, H->num_sms, H->stream);
       cudaEventRecord(e1, H->stream);
       if (e == cudaSuccess) e = cudaEventSynchronize(e1);
       H->launches += 3;
       if (e != cudaSuccess) { st = Status::error(INFUR_E_RUNTIME, std::string("autotune: ") + cudaGetErrorString(e)); break; }
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
-      if (ms < best_ms * 0.97f || (bn == best_bn && ms < best_ms)) { best_ms = ms < best_ms ? ms : best_ms; best_bn = bn; }
+      const bool same = c.bn == best.bn && c.pair == best.pair;
+      if (ms < best_ms * 0.97f || (same && ms < best_ms)) { best_ms = ms < best_ms ? ms : best_ms; best = c; }
     }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (!st.ok()) return st;
-  if (best_bn != po.block_n) st = setup_conv_tc(d, io, po, best_bn);
+  if (best.bn != po.block_n || best.pair != po.pair) st = setup_conv_tc(d, io, po, best.bn, best.pair);
   return st;
 }
 
@@ -516,7 +523,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       os << "conv " << op.name << " [" << n << "x" << ti.h << "x" << ti.w << "x" << d.cin << "] -> [" << to.h << "x" << to.w << "x" << d.cout
          << "] k" << d.kh << " s" << d.stride << " p" << d.pad << " d" << d.dil << (io.residual ? " +res" : "") << (d.cin2 ? " +shortcut1x1" : "") << (d.relu ? " relu" : "");
       if (d.tc_ok)
-        os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << po.block_n << " tiles "
+        os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << po.block_n << (po.pair ? " pair" : "") << " tiles "
            << po.geom.num_tiles << " kblocks " << po.geom.num_kb;
       os << " | GFLOP " << po.flops * 1e-9 << " MB " << po.bytes * 1e-6;
     } else {
@@ -634,7 +641,8 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   const bool f32out = y_f32 != nullptr;
   DevConv d;
   classify_conv(c, c.cin == 3, f32out, d);
-  const bool tc = cd->impl == INFUR_CONV_TCGEN05;
+  const bool pair = cd->impl == INFUR_CONV_TCGEN05_PAIR;
+  const bool tc = cd->impl == INFUR_CONV_TCGEN05 || pair;
   if (tc && !d.tc_ok) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: shape not supported by the tcgen05 kernel: " + d.why_not);
   Plan tmp;
   Status st;
@@ -687,7 +695,8 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   io.x = d_x; io.n = n; io.h = h; io.w = w; io.oh = oh; io.ow = ow; io.wgt = d_w; io.bias = d_b; io.residual = d_res; io.y = d_y; io.y_f32 = d_yf;
   io.out_ld = out_ld;
   PlanOp po;
-  if (tc) { if (!(st = setup_conv_tc(d, io, po, d.block_n)).ok()) return st; }
+  if (pair && (d.block_n != 256 || d.stem || f32out)) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the CTA-pair variant needs cout % 256 == 0 and an fp16 output");
+  if (tc) { if (!(st = setup_conv_tc(d, io, po, d.block_n, pair)).ok()) return st; }
   else setup_direct(d, io, d_wv, po.direct);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);

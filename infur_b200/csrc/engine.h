@@ -58,6 +58,7 @@ struct TensorInfo {
 struct PlanOp {
   int op = -1;                 // index into model ops
   int block_n = 0;             // N tile of the tcgen05 kernel chosen for this op
+  bool pair = false;           // CTA-pair (cta_group::2) variant
   bool is_conv = false;
   ConvTcMaps maps;
   ConvTcGeom geom;

@@ -107,6 +107,26 @@ def conv_1x1_s2():
 
 
 @check
+def pair_1x1():
+    _conv_case("pair 1x1 256->256 30x40", 1, 30, 40, 256, 256, 1, 1, 0, 1, impls=(2, 0))
+
+
+@check
+def pair_1x1_res_n3():
+    _conv_case("pair 1x1 128->512 +res 17x23 n3 (odd M tiles)", 3, 17, 23, 128, 512, 1, 1, 0, 1, res=True, impls=(2, 0))
+
+
+@check
+def pair_3x3_d2():
+    _conv_case("pair 3x3 128->256 d2 p2 30x40 n2", 2, 30, 40, 128, 256, 3, 1, 2, 2, impls=(2, 0))
+
+
+@check
+def pair_big():
+    _conv_case("pair 1x1 512->2048 +res 135x240", 1, 135, 240, 512, 2048, 1, 1, 0, 1, res=True, impls=(2, 0))
+
+
+@check
 def conv_head_f32():
     _conv_case("1x1 512->21 f32 30x40", 1, 30, 40, 512, 21, 1, 1, 0, 1, relu=False, f32=True)
 

@@ -34,6 +34,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("name")
     ap.add_argument("--n", type=int, default=8)
+    ap.add_argument("--impl", type=int, default=0, help="0 tcgen05, 2 tcgen05 CTA pair")
     a = ap.parse_args()
     from infur_b200 import processors as P
 
@@ -47,10 +48,10 @@ def main():
     ow = (w + 2 * p - d * (k - 1) - 1) // s + 1
     r = rng.standard_normal((n, oh, ow, cout), dtype=np.float32).astype(np.float16) if res else None
     with P.Handle(max_batch=n) as hd:
-        y, ms = hd.conv_test(x, wt, b, r, s, p, d, relu, timed=True)
+        y, ms = hd.conv_test(x, wt, b, r, s, p, d, relu, impl=a.impl, timed=True)
     fl = 2.0 * n * oh * ow * cout * k * k * cin
     by = x.nbytes + wt.nbytes + y.nbytes + (r.nbytes if res else 0)
-    print(f"{a.name}: {ms:.3f} ms  {fl / ms * 1e-9:.1f} TFLOP/s  {by / ms * 1e-6:.1f} GB/s  (n={n})  checksum {float(np.abs(y[0, :4, :4].astype(np.float32)).sum()):.3f}")
+    print(f"{a.name} impl{a.impl}: {ms:.3f} ms  {fl / ms * 1e-9:.1f} TFLOP/s  {by / ms * 1e-6:.1f} GB/s  (n={n})  checksum {float(np.abs(y[0, :4, :4].astype(np.float32)).sum()):.3f}")
 
 
 if __name__ == "__main__":
