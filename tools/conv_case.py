@@ -24,6 +24,8 @@ CASES = {
     "l4_conv1": (135, 240, 2048, 512, 1, 1, 0, 1, True, False),
     "l4_conv2": (135, 240, 512, 512, 3, 1, 4, 4, True, False),
     "l4_conv3": (135, 240, 512, 2048, 1, 1, 0, 1, True, True),
+    "l4_conv3_nores": (135, 240, 512, 2048, 1, 1, 0, 1, True, False),
+    "l3_conv3_nores": (135, 240, 256, 1024, 1, 1, 0, 1, True, False),
     "l4_down": (135, 240, 1024, 2048, 1, 1, 0, 1, False, False),
     "cls0": (135, 240, 2048, 512, 3, 1, 1, 1, True, False),
     "stem": (1080, 1920, 3, 64, 7, 2, 3, 1, True, False),
