@@ -39,6 +39,8 @@ if ROOT not in sys.path:
 
 W, H = 1920, 1080
 FLOPS_NO_AUX = {(1920, 1080): 2189.025e9}   # 2 x MACs of the 55 convs of the `out` head
+# measured with ncu (profiles/r1_launches_step_b8_1080p.csv): DRAM bytes of all conv launches of one 8-frame step / 51 launches
+CONV_DRAM_BYTES_PER_LAUNCH = 35.0e9 / 51
 
 
 def peaks():
@@ -192,7 +194,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
 
     from infur_b200 import processors as P
-    from infur_b200 import synth
+    from infur_b200 import sharding, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -213,18 +215,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     h = P.Handle(device=local_rank, max_batch=B, ring_depth=args.ring_depth)
     # weights: rank 0 packs + uploads, every other rank receives the packed arena over NCCL (init only)
-    h.model_load(path, skip_weights=(rank != 0))
-    if world > 1:
-        nbytes = h.weights_size()
-        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            h.weights_export(blob.data_ptr(), nbytes)
-        torch.cuda.synchronize()
-        dist.broadcast(blob, 0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            h.weights_import(blob.data_ptr(), nbytes)
-        del blob
+    sharding.load_model_sharded(h, path, rank, world, dev)
     h.scale_control(1.0)
 
     # synthetic frames: nsets batches of B distinct frames per rank (input set 4 x 8 x 6.2 MB = 199 MB > 126 MB L2;
@@ -322,7 +313,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         roofline = {
             "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv+bias+ReLU(+residual)), all %d launches of one step" % n_conv,
             "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": CONV_DRAM_BYTES_PER_LAUNCH,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of one step (8 frames) / launches, from "
+                            "profiles/r1_launches_step_b8_1080p.csv; algorithmic bytes per launch = 8 x 3546.9 MB (layer-wise, shortcuts fused) / launches",
+            "algorithmic_bytes_per_launch": B * 3546.9e6 / n_conv,
             "flops_per_launch_avg": flops / n_conv, "ms_per_launch_avg": conv_ms / n_conv, "ms_all_launches": conv_ms,
             "peak_source": pk["source"] + " (sustained cuBLAS bf16: the kernel is timed inside a long step)",
         }
@@ -350,9 +344,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                    "in an opset-12 .onnx), scale 1.0, out head only, class map + premultiplied RGBA out",
                        "frames_per_step_per_gpu": B, "width": W, "height": H, "ring_depth": depth, "sharding": "frames by rank, no collective",
                        "l2": "inputs cycle through 4 x 8 distinct frames (199 MB) and each step streams > 30 GB of activations: larger than L2"},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * W * H * 3, "d2h_bytes_per_step": B * W * H * 5,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": world * B * W * H * 3, "d2h_bytes_per_step": world * B * W * H * 5,
                     "api": "infur_b200_ring_acquire/submit/wait, host memcpy into the pinned slot inside the timed region"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_other_kernels": other, "cpu_baseline": cpu,
+            "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline, "roofline_other_kernels": other, "cpu_baseline": cpu,
             "single_frame": {"workload": "configs[1]: one 1080p frame, synchronous infur_b200_advance, host buffers", "ms": 1e3 * float(np.median(lat))},
         }
     h.close()

@@ -28,6 +28,7 @@ E_TICKET = 12
 
 CONV_TCGEN05 = 0
 CONV_VALIDATE = 1
+CONV_TCGEN05_PAIR = 2   # conv_test only
 LOAD_DEFAULT = 0
 LOAD_SKIP_WEIGHTS = 1
 

@@ -61,3 +61,32 @@ def test_conv_tc_vs_torch(handle, case):
     if n * oh * ow * cout * cin * k * k < 3e9:
         yv = handle.conv_test(x, wt, b, r, stride, pad, dil, relu, impl=L.CONV_VALIDATE, f32_out=f32)
         assert (np.abs(yv.astype(np.float32) - ref) <= tol).all()
+
+
+PAIR_CASES = [
+    # the CTA-pair (cta_group::2) variant: cout % 256 == 0; odd numbers of M tiles exercise the dummy half of the last pair
+    (1, 30, 40, 256, 256, 1, 1, 0, 1, True, False),
+    (3, 17, 23, 128, 512, 1, 1, 0, 1, True, True),
+    (2, 30, 40, 128, 256, 3, 1, 2, 2, True, False),
+    (1, 60, 80, 256, 512, 1, 2, 0, 1, False, False),
+    (1, 9, 11, 64, 256, 3, 1, 1, 1, True, True),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: "pair_n%d_%dx%d_c%d-%d_k%d_s%d_p%d_d%d" % c[:9])
+def test_conv_pair_bit_identical_to_single_cta(handle, case):
+    """Every N-tile / CTA-pair choice the autotuner may make accumulates each output element's K blocks in the same
+    order, so the variants must agree BIT FOR BIT (that is what makes the plan-time choice invisible in results)."""
+    n, h, w, cin, cout, k, stride, pad, dil, relu, res = case
+    rng = np.random.default_rng(abs(hash(case)) % 2**31)
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float16)
+    wt = (rng.standard_normal((cout, k, k, cin)) * (2.0 / (cin * k * k)) ** 0.5).astype(np.float16)
+    b = rng.standard_normal(cout).astype(np.float32)
+    oh = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    ow = (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    r = rng.standard_normal((n, oh, ow, cout)).astype(np.float16) if res else None
+    ref = ref_conv(x, wt, b, r, stride, pad, dil, relu)
+    y1 = handle.conv_test(x, wt, b, r, stride, pad, dil, relu, impl=L.CONV_TCGEN05)
+    y2 = handle.conv_test(x, wt, b, r, stride, pad, dil, relu, impl=L.CONV_TCGEN05_PAIR)
+    assert (y1.view(np.uint16) == y2.view(np.uint16)).all()
+    assert (np.abs(y2.astype(np.float32) - ref) <= 2e-3 + 4e-3 * np.abs(ref)).all()
