@@ -43,7 +43,9 @@ enum {
   INFUR_E_BUFFER_TOO_SMALL = 9,   /* C analogue of "stage re-allocates Out on size change" (processing.rs:260-268) */
   INFUR_E_NO_DEVICE = 10,
   INFUR_E_UNSUPPORTED = 11,
-  INFUR_E_TICKET = 12
+  INFUR_E_TICKET = 12,
+  INFUR_E_STREAM_END = 13         /* read_exact hit EOF (ff-video/src/decoder.rs:156-162): the caller classifies it as FinishedNormally /
+                                   * ExactReadError from the decoder process' exit status, exactly as the reference does */
 };
 
 enum { INFUR_RESIZE_NEAREST = 0 /* fr::ResizeAlg::Nearest, processing.rs:189 (the reference's only mode) */ };
@@ -161,6 +163,15 @@ typedef struct infur_b200_slot {
 
 /* Next free slot sized for n frames of w x h; INFUR_E_TICKET when all ring_depth slots are in flight. */
 int32_t infur_b200_ring_acquire(infur_b200_handle* h, uint32_t n, uint32_t w, uint32_t hgt, infur_b200_slot* slot);
+/* Frame source -> pinned memory without a staging copy (FFMpegDecoder::read_frame, ff-video/src/decoder.rs:150-165, for a
+ * whole slot): reads up to the slot's n frames of w*h*3 bytes each from file descriptor `fd` (the rawvideo bgr24 pipe of
+ * decoder.rs:51-75) straight into the slot's pinned input buffer, `read_exact` per frame (short reads and EINTR are retried).
+ * *frames_read = complete frames now in the slot; the slot's frame count shrinks to it (a slot left with 0 frames is released).
+ * Returns INFUR_OK when all n frames arrived, INFUR_E_STREAM_END when EOF came first (*partial_bytes = bytes of an incomplete
+ * last frame, 0 = EOF exactly on a frame boundary), INFUR_E_RUNTIME on an I/O error.  Frame ids stay with the caller
+ * (1-based counter, decoder.rs:163-164). */
+int32_t infur_b200_ring_read(infur_b200_handle* h, uint64_t ticket, int32_t fd, uint32_t* frames_read, size_t* partial_bytes);
+
 /* Enqueue H2D copy, the whole path, and the D2H copies of the slot; returns immediately. */
 int32_t infur_b200_ring_submit(infur_b200_handle* h, uint64_t ticket);
 /* Block until the slot's results are in pinned memory; tickets complete in submission order. */

@@ -25,6 +25,7 @@ E_BUFFER_TOO_SMALL = 9
 E_NO_DEVICE = 10
 E_UNSUPPORTED = 11
 E_TICKET = 12
+E_STREAM_END = 13
 
 CONV_TCGEN05 = 0
 CONV_VALIDATE = 1
@@ -89,6 +90,7 @@ SYMBOLS = {
     "infur_b200_advance": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(Out)]),
     "infur_b200_advance_batch": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(Out)]),
     "infur_b200_ring_acquire": (C.c_int32, [_H, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Slot)]),
+    "infur_b200_ring_read": (C.c_int32, [_H, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]),
     "infur_b200_ring_submit": (C.c_int32, [_H, C.c_uint64]),
     "infur_b200_ring_wait": (C.c_int32, [_H, C.c_uint64, C.POINTER(Slot)]),
     "infur_b200_advance_device": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -1,6 +1,9 @@
 // extern "C" surface of libinfur_b200.so -- see include/infur_b200.h for the contract of each entry point
 // and the reference item it mirrors.
+#include <unistd.h>
+
 #include <algorithm>
+#include <cerrno>
 #include <cstdio>
 #include <cstring>
 #include <sstream>
@@ -366,6 +369,34 @@ int32_t infur_b200_ring_acquire(infur_b200_handle* h, uint32_t n, uint32_t w, ui
 static RingSlot* find_slot(infur_b200_handle* h, uint64_t ticket) {
   for (auto& r : h->ring) if (r.state != 0 && r.ticket == ticket) return &r;
   return nullptr;
+}
+
+int32_t infur_b200_ring_read(infur_b200_handle* h, uint64_t ticket, int32_t fd, uint32_t* frames_read, size_t* partial_bytes) {
+  if (!h || !frames_read) return INFUR_E_INVALID_ARG;
+  *frames_read = 0;
+  if (partial_bytes) *partial_bytes = 0;
+  RingSlot* s = find_slot(h, ticket);
+  if (!s || s->state != 1) return fail(h, INFUR_E_TICKET, "ring_read: unknown ticket or slot already submitted");
+  const size_t frame_bytes = (size_t)s->w * s->h * 3;
+  int32_t rc = INFUR_OK;
+  uint32_t got = 0;
+  for (; got < s->n && rc == INFUR_OK; ++got) {
+    uint8_t* dst = s->h_in + (size_t)got * frame_bytes;
+    size_t have = 0;
+    while (have < frame_bytes) {   // read_exact
+      const ssize_t r = ::read(fd, dst + have, frame_bytes - have);
+      if (r > 0) { have += (size_t)r; continue; }
+      if (r < 0 && errno == EINTR) continue;
+      if (r == 0) { rc = INFUR_E_STREAM_END; if (partial_bytes) *partial_bytes = have; h->last_error = "failed to fill whole buffer"; }
+      else rc = fail(h, INFUR_E_RUNTIME, std::string("ring_read: ") + strerror(errno));
+      break;
+    }
+    if (rc != INFUR_OK) break;
+  }
+  *frames_read = got;
+  if (got == 0) s->state = 0;   // nothing to process: the slot goes back to the ring
+  else s->n = got;
+  return rc;
 }
 
 int32_t infur_b200_ring_submit(infur_b200_handle* h, uint64_t ticket) {

@@ -33,6 +33,7 @@ constexpr int kDmaWarp = 3;
 constexpr int kMaxStages = 8;
 constexpr int kEpiBufBytes = kBlockM * 64 * 2;      // one 64-channel output chunk: 128 rows x 128 B
 constexpr int kMaxEpiBufs = 4;
+constexpr int kMaxAcc = 4;
 constexpr int kSmemLimit = 232448;                  // 227 KB per CTA
 constexpr int kBarBytes = 512;
 
@@ -40,7 +41,8 @@ template <int BLOCK_N>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulator stages; power of two
+  static constexpr int kAcc = BLOCK_N >= 256 ? 2 : 4;     // TMEM accumulator stages: as many 128 x BLOCK_N f32 tiles as fit in 512 columns (max 4)
+  static constexpr int kTmemCols = kAcc * BLOCK_N;        // power of two, 128 .. 512
   // epilogue buffers: 0 (direct stores), 2 (TMA store), 4 (TMA store + TMA residual prefetch)
   static constexpr int stages(int epi_bufs) {
     int s = (kSmemLimit - 1024 - kBarBytes - epi_bufs * kEpiBufBytes) / kStageBytes;
@@ -79,7 +81,7 @@ struct Sched2 {   // one CTA pair per (two consecutive M tiles, one N tile); an 
 };
 
 // Direct-store epilogue (f32 logit head): thread = output pixel, 32 channels at a time.
-template <int BLOCK_N>
+template <int BLOCK_N, int ACC>
 __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int quad, int lane,
                                                 int row) {
   const int bw_log2 = g.bw_log2;
@@ -91,8 +93,8 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
     const bool valid = ox < g.ow && oy < g.oh;
     const size_t pix = ((size_t)tc.img * g.oh + oy) * g.ow + ox;
     const int n0 = tc.nt * BLOCK_N;
-    const int as = it & 1;
-    const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+    const int as = it % ACC;
+    const uint32_t aphase = (uint32_t)(it / ACC) & 1u;
     ptx::mbar_wait(tfull0 + 8u * as, aphase);
     ptx::tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
@@ -162,7 +164,7 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 // announces its part through the chunk_ready mbarrier and moves on.
 struct EpiBars { uint32_t res, ready, free_; };
 
-template <int BLOCK_N, bool HAS_RES, class Sched, bool PAIR = false>
+template <int BLOCK_N, int ACC, bool HAS_RES, class Sched, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sched, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                              const EpiBars eb, uint32_t epi_base, int ew, int lane) {
   constexpr int CH = BLOCK_N / 64;            // chunks per tile
@@ -173,8 +175,8 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
   int q = 0, it = 0;
   for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
     const int n0 = (tile % g.tiles_n) * BLOCK_N;
-    const int as = it & 1;
-    const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+    const int as = it % ACC;
+    const uint32_t aphase = (uint32_t)(it / ACC) & 1u;
     ptx::mbar_wait(tfull0 + 8u * as, aphase);
     ptx::tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + half * 32);
@@ -297,9 +299,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + kMaxAcc + s); };
   EpiBars eb;
-  eb.res = bar_base + 8u * (2 * kMaxStages + 4);
+  eb.res = bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc);
   eb.ready = eb.res + 8u * kMaxEpiBufs;
   eb.free_ = eb.ready + 8u * kMaxEpiBufs;
   const uint32_t tmem_ptr_addr = eb.free_ + 8u * kMaxEpiBufs;
@@ -316,7 +318,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < num_stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), g.store_mode == 0 ? 4 : kEpiWarps); }
+    for (int s = 0; s < C::kAcc; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), g.store_mode == 0 ? 4 : kEpiWarps); }
     for (int s = 0; s < kMaxEpiBufs; ++s) {
       ptx::mbar_init(eb.res + 8u * s, 1);
       ptx::mbar_init(eb.ready + 8u * s, kEpiWarps);
@@ -370,12 +372,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BLOCK_N);
+      constexpr int ACC = C::kAcc;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const int as = it % ACC;
+        const uint32_t aphase = (uint32_t)(it / ACC) & 1u;
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue drained this accumulator stage
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
@@ -409,11 +412,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     // ===================== epilogue =====================
     const int ew = warp - kEpiWarp0;         // ew % 4 == warp % 4: the TMEM lane quadrant this warp may read
     if (g.store_mode == 0) {
-      if (ew < 4) epilogue_direct<BLOCK_N>(g, tmem_base, tfull_bar(0), tempty_bar(0), ew, lane, ew * 32 + lane);
+      if (ew < 4) epilogue_direct<BLOCK_N, C::kAcc>(g, tmem_base, tfull_bar(0), tempty_bar(0), ew, lane, ew * 32 + lane);
     } else if constexpr (BLOCK_N >= 64) {
       const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
-      if (g.store_mode == 1) epilogue_tma<BLOCK_N, false>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-      else epilogue_tma<BLOCK_N, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      if (g.store_mode == 1) epilogue_tma<BLOCK_N, C::kAcc, false>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      else epilogue_tma<BLOCK_N, C::kAcc, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
     }
   }
 
@@ -446,6 +449,7 @@ __host__ __device__ constexpr int pair_smem_bytes(int epi_bufs) { return pair_st
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   constexpr int BLOCK_N = 256;
+  constexpr int ACC = 2;
   extern __shared__ uint8_t smem_raw[];
   const int num_stages = g.stages;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -454,9 +458,9 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + kMaxAcc + s); };
   EpiBars eb;
-  eb.res = bar_base + 8u * (2 * kMaxStages + 4);
+  eb.res = bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc);
   eb.ready = eb.res + 8u * kMaxEpiBufs;
   eb.free_ = eb.ready + 8u * kMaxEpiBufs;
   const uint32_t tmem_ptr_addr = eb.free_ + 8u * kMaxEpiBufs;
@@ -474,7 +478,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < num_stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+    for (int s = 0; s < ACC; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 2 * kEpiWarps); }
     for (int s = 0; s < kMaxEpiBufs; ++s) {
       ptx::mbar_init(eb.res + 8u * s, 1);
       ptx::mbar_init(eb.ready + 8u * s, kEpiWarps);
@@ -526,8 +530,8 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
       uint32_t phase = 0;
       int it = 0;
       for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const int as = it % ACC;
+        const uint32_t aphase = (uint32_t)(it / ACC) & 1u;
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);  // the epilogues of BOTH CTAs drained this accumulator stage
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
@@ -553,8 +557,8 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
     }
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;
-    if (g.store_mode == 1) epilogue_tma<BLOCK_N, false, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-    else epilogue_tma<BLOCK_N, true, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    if (g.store_mode == 1) epilogue_tma<BLOCK_N, ACC, false, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    else epilogue_tma<BLOCK_N, ACC, true, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
   }
 
   ptx::tc_fence_before();
@@ -583,6 +587,7 @@ constexpr int kStemSmemBytes = kStemStages * kStemStageBytes + 2 * kEpiBufBytes 
 __global__ void __launch_bounds__(kThreads, 1)
 stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   constexpr int BLOCK_N = 64;
+  constexpr int ACC = 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + kStemStages * kStemStageBytes;
@@ -591,9 +596,9 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + kMaxAcc + s); };
   EpiBars eb;
-  eb.res = bar_base + 8u * (2 * kMaxStages + 4);
+  eb.res = bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc);
   eb.ready = eb.res + 8u * kMaxEpiBufs;
   eb.free_ = eb.ready + 8u * kMaxEpiBufs;
   const uint32_t tmem_ptr_addr = eb.free_ + 8u * kMaxEpiBufs;
@@ -603,7 +608,7 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   if (warp == 0 && ptx::elect_one()) { ptx::prefetch_tmap(&maps.a[0]); ptx::prefetch_tmap(&maps.c); }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < kStemStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), kEpiWarps); }
+    for (int s = 0; s < ACC; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), kEpiWarps); }
     for (int s = 0; s < kMaxEpiBufs; ++s) {
       ptx::mbar_init(eb.res + 8u * s, 1);
       ptx::mbar_init(eb.ready + 8u * s, kEpiWarps);
@@ -612,7 +617,7 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_ptr_addr, 2 * BLOCK_N);
+    ptx::tmem_alloc(tmem_ptr_addr, ACC * BLOCK_N);
     ptx::tmem_relinquish();
   }
   {  // weights: global (already in smem order) -> smem, once per CTA
@@ -649,8 +654,8 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const int as = it % ACC;
+        const uint32_t aphase = (uint32_t)(it / ACC) & 1u;
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
@@ -673,7 +678,7 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   } else if (warp == kDmaWarp) {
     if (ptx::elect_one()) epilogue_dma<BLOCK_N, false>(maps, g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, eb, epi_base);
   } else if (warp >= kEpiWarp0) {
-    epilogue_tma<BLOCK_N, false>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
+    epilogue_tma<BLOCK_N, ACC, false>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
                                  warp - kEpiWarp0, lane);
   }
 
@@ -681,7 +686,7 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    ptx::tmem_dealloc(tmem_base, ACC * BLOCK_N);
   }
 }
 

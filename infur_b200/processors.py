@@ -341,6 +341,14 @@ class Handle:
         view = np.ctypeslib.as_array(C.cast(s.bgr_in, C.POINTER(C.c_uint8)), shape=(n, h, w, 3)) if n * w * h else np.zeros((n, h, w, 3), np.uint8)
         return s.ticket, view
 
+    def ring_read(self, ticket: int, fd: int):
+        """Fill the slot from file descriptor ``fd`` (raw bgr24 frames).  Returns (frames_read, partial_bytes, ended)."""
+        got, part = C.c_uint32(), C.c_size_t()
+        rc = self.lib.infur_b200_ring_read(self._h, ticket, fd, C.byref(got), C.byref(part))
+        if rc not in (L.OK, L.E_STREAM_END):
+            self._check(rc)
+        return got.value, part.value, rc == L.E_STREAM_END
+
     def ring_submit(self, ticket: int):
         self._check(self.lib.infur_b200_ring_submit(self._h, ticket))
 

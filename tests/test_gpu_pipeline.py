@@ -153,3 +153,22 @@ def test_switch_scale_sizes(handle, tiny):
         assert g.size == size and g.decoded_buffer.shape[:2] == (size[1], size[0])
         assert not pipe.is_dirty()
     pipe.control(("Scale", 1.0))
+
+
+def test_config5_4k_scale_half_vs_one(handle, tiny):
+    """configs[4] analogue on one GPU: a 3840x2160 frame at scale 0.5 (nearest 2x+1 -> 1920x1080) against the oracle,
+    including the blended overlay; and the same frame at scale 1.0 only for sizes (the oracle at 4K is too slow here)."""
+    path, model = tiny
+    pipe = P.GpuPipeline(handle)
+    pipe.control(("Model", path))
+    frame = synth.synth_frame(3840, 2160, 1)
+    pipe.control(("Scale", 0.5))
+    g = pipe.advance(P.Frame(7, frame))
+    ref = fcn.pipeline(model, frame, 0.5, emulate_fp16=True)
+    assert g.size == [1920, 1080] and (g.buffer == ref["frame_rgba"]).all()
+    check_against_oracle(g.class_map, g.decoded_buffer, ref, 0.995)
+    assert (g.blended == oracle.blend_over(g.decoded_buffer, g.buffer)).all()   # overlay: exact given the mask
+    pipe.control(("Scale", 1.0))
+    g1 = pipe.advance(P.Frame(8, frame))
+    assert g1.size == [3840, 2160] and g1.class_map.shape == (2160, 3840)
+    assert (g1.buffer == oracle.frame_rgba(frame)).all()
