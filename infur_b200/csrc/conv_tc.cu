@@ -218,27 +218,29 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
         const uint32_t addr = rowp + (((uint32_t)(half * 4 + j) ^ sw) << 4);
         const float4 bl = bias[2 * j], bh = bias[2 * j + 1];
         float v[8];
-        v[0] = __uint_as_float(acc[8 * j + 0]) + bl.x; v[1] = __uint_as_float(acc[8 * j + 1]) + bl.y;
-        v[2] = __uint_as_float(acc[8 * j + 2]) + bl.z; v[3] = __uint_as_float(acc[8 * j + 3]) + bl.w;
-        v[4] = __uint_as_float(acc[8 * j + 4]) + bh.x; v[5] = __uint_as_float(acc[8 * j + 5]) + bh.y;
-        v[6] = __uint_as_float(acc[8 * j + 6]) + bh.z; v[7] = __uint_as_float(acc[8 * j + 7]) + bh.w;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[8 * j + t]);
+        // + bias: packed f32x2 adds (FADD2); + residual: f32 + f16 mixed adds (FHADD), no unpacking; both round like
+        // the scalar f32 operations they replace
+        ptx::add_f32x2(v[0], v[1], bl.x, bl.y); ptx::add_f32x2(v[2], v[3], bl.z, bl.w);
+        ptx::add_f32x2(v[4], v[5], bh.x, bh.y); ptx::add_f32x2(v[6], v[7], bh.z, bh.w);
         if (HAS_RES) {
-          const __half2* h = reinterpret_cast<const __half2*>(&res[j]);
+          const uint32_t rw[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 f = __half22float2(h[t]);
-            v[2 * t] += f.x;
-            v[2 * t + 1] += f.y;
+            v[2 * t] = ptx::add_f32_f16(v[2 * t], (unsigned short)(rw[t] & 0xffffu));
+            v[2 * t + 1] = ptx::add_f32_f16(v[2 * t + 1], (unsigned short)(rw[t] >> 16));
           }
-        }
-        if (g.relu) {
-#pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
         }
         uint4 o;
         __half2* h = reinterpret_cast<__half2*>(&o);
 #pragma unroll
         for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+        if (g.relu) {   // rounding is monotonic and keeps 0, so ReLU after the fp16 rounding equals ReLU before it
+          const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h[t] = __hmax2(h[t], z);
+        }
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
       }
       ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA store

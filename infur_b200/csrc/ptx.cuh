@@ -97,6 +97,20 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                : "memory");
 }
 
+// ---- packed / mixed-precision adds (sm_100) -------------------------------------------------
+// (a0, a1) += (b0, b1) as one FADD2; each lane rounds like a scalar add.rn.f32
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+// c + float(h) in one FHADD (the fp16 operand is converted exactly, one rounding)
+__device__ __forceinline__ float add_f32_f16(float c, unsigned short h) {
+  float d;
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
