@@ -542,6 +542,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
   p.lowres = reinterpret_cast<float*>(th.ptr); p.lh = th.h; p.lw = th.w; p.k = hd.num_classes; p.ldk = th.ld;
   if (H->cfg.compute_aux && M->aux_head >= 0) p.aux_lowres = reinterpret_cast<float*>(p.tensors[m.heads[M->aux_head].tensor].ptr);
   if (!(st = build_bilinear(p, p.lh, p.lw)).ok()) return st;
+  if (p.k == 21 && !(st = dev_alloc(p, &p.top_code, (size_t)n * p.lh * p.lw)).ok()) return st;
   out = std::move(pl);
   return Status();
 }
@@ -607,7 +608,7 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
   q.y0 = p.y0; q.y1 = p.y1; q.ly0 = p.ly0; q.ly1 = p.ly1; q.x0 = p.x0; q.x1 = p.x1; q.lx0 = p.lx0; q.lx1 = p.lx1;
   q.color_lut = H->d_color_lut; q.frame_bgr = frame;
   q.class_map = o.class_map; q.decoded = o.decoded; q.blended = o.blended; q.frame_rgba = o.frame_rgba; q.logits = o.logits;
-  q.max_lr = p.max_lr; q.max_lc = p.max_lc;
+  q.max_lr = p.max_lr; q.max_lc = p.max_lc; q.top_code = p.top_code;
   if (!q.decoded) q.decoded = p.d_decoded;
   if (o.aux_logits && p.aux_lowres) {
     // debug path: the aux head through the same post kernel first; only its logits are kept
@@ -618,7 +619,7 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
     H->launches++;
   }
   CU_TRY(launch_post(q, s));
-  H->launches++;
+  H->launches += (q.top_code && q.k == 21) ? 2 : 1;
   if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
   (void)op_ms;
   return Status();

@@ -84,6 +84,7 @@ struct Plan {
   uint8_t* scaled = nullptr;     // Scale output when factor != 1
   float* lowres = nullptr;       // [n][lh][lw][ldk]
   float* aux_lowres = nullptr;
+  int32_t* top_code = nullptr;   // post-kernel fast-path scratch [n][lh][lw]
   int max_lr = 0, max_lc = 0;
   // staging for the host-buffer entry points
   uint8_t* d_in = nullptr;

@@ -212,6 +212,48 @@ __global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
 // reload.  Same f32 operations in the same order as post_kernel / the oracle, hence the same bits.
 constexpr int kPostStripRows = 64;
 
+// alpha = trunc(sat(c * 255)), colour from the premultiplied table, class byte, optional blend / frame RGBA
+__device__ __forceinline__ void post_emit(const PostArgs& a, int img, size_t plane, size_t pix, int k_max, float c_max) {
+  const float av = __fmul_rn(c_max, 255.0f);
+  const int alpha = av >= 255.0f ? 255 : (int)av;  // c_max >= 0 always; trunc toward zero, saturate
+  const uint32_t col = __ldg(a.color_lut + (k_max % 20) * 256 + alpha);
+  const size_t gp = (size_t)img * plane + pix;
+  if (a.class_map) a.class_map[gp] = (uint8_t)k_max;
+  a.decoded[gp] = col;
+  if (a.frame_bgr && (a.blended || a.frame_rgba)) {
+    const uint8_t* f = a.frame_bgr + gp * 3;
+    const uint32_t fb = f[0], fg = f[1], fr = f[2];
+    if (a.frame_rgba) a.frame_rgba[gp] = fr | (fg << 8) | (fb << 16) | 0xff000000u;
+    if (a.blended) {
+      const uint32_t ia = 255u - (col >> 24);
+      const uint32_t r = min(255u, (col & 0xff) + (fr * ia + 127u) / 255u);
+      const uint32_t g = min(255u, ((col >> 8) & 0xff) + (fg * ia + 127u) / 255u);
+      const uint32_t b = min(255u, ((col >> 16) & 0xff) + (fb * ia + 127u) / 255u);
+      a.blended[gp] = r | (g << 8) | (b << 16) | 0xff000000u;
+    }
+  }
+}
+
+// Pre-pass of the fast path below: per low-res pixel the strict first-maximum class k* of its K logits, kept only
+// when it beats every other class by a margin far above the rounding error of the interpolation
+// (1e-4 * (1 + |v1| + |v2|) vs. a few f32 ulp); -1 otherwise.
+template <int K>
+__global__ void __launch_bounds__(256) lowres_top_kernel(const float* __restrict__ lowres, int ldk, size_t npix, int32_t* __restrict__ code) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float* p = lowres + i * ldk;
+  int k1 = 0;
+  float v1 = p[0], v2 = -INFINITY;
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    const float v = p[k];
+    if (v > v1) { v2 = v1; v1 = v; k1 = k; }
+    else if (v > v2 || !(v2 == v2)) v2 = v;
+  }
+  const bool safe = (v1 - v2) > 1e-4f * (1.f + fabsf(v1) + fabsf(v2));   // false for NaN / inf oddities: those pixels take the full path
+  code[i] = safe ? k1 : -1;
+}
+
 template <int K>
 __global__ void __launch_bounds__(128, 3) post_strip_kernel(PostArgs a) {
   constexpr int KQ = (K + 3) / 4;     // float4 per low-res pixel that carry classes
@@ -241,8 +283,36 @@ __global__ void __launch_bounds__(128, 3) post_strip_kernel(PostArgs a) {
   };
   int cur0 = -1, cur1 = -1;
   const size_t plane = (size_t)a.oh * a.ow;
+  // fast path state (per lane, refreshed when the low-res row pair changes)
+  int f0 = -2, f1 = -2, fk = -1;
+  float ft = 0.f, fb = 0.f;
   for (int y = Y0; y < Y1; ++y) {
     const int r0 = __ldg(a.y0 + y), r1 = __ldg(a.y1 + y);   // warp-uniform
+    if (a.top_code && !a.logits) {
+      // Fast path: when ONE class wins all four low-res pixels a lane's output pixel blends, by a safe margin, it wins
+      // the blend too (each interpolation step is monotone in its inputs, and the margin dwarfs the rounding error),
+      // so only that class needs interpolating -- with the very same operations, hence the same bits.
+      if (r0 != f0 || r1 != f1) {
+        f0 = r0; f1 = r1;
+        const size_t b0 = ((size_t)img * a.lh + r0) * a.lw, b1 = ((size_t)img * a.lh + r1) * a.lw;
+        const int k00 = __ldg(a.top_code + b0 + c0), k01 = __ldg(a.top_code + b0 + c1);
+        const int k10 = __ldg(a.top_code + b1 + c0), k11 = __ldg(a.top_code + b1 + c1);
+        fk = (k00 >= 0 && k00 == k01 && k00 == k10 && k00 == k11) ? k00 : -1;
+        if (fk >= 0) {
+          ft = __fadd_rn(__fmul_rn(wx0, __ldg(a.lowres + (b0 + c0) * a.ldk + fk)), __fmul_rn(wx1, __ldg(a.lowres + (b0 + c1) * a.ldk + fk)));
+          fb = __fadd_rn(__fmul_rn(wx0, __ldg(a.lowres + (b1 + c0) * a.ldk + fk)), __fmul_rn(wx1, __ldg(a.lowres + (b1 + c1) * a.ldk + fk)));
+        }
+      }
+      if (__all_sync(0xffffffffu, fk >= 0)) {
+        const float wy0 = __ldg(a.ly0 + y), wy1 = __ldg(a.ly1 + y);
+        const float v = __fadd_rn(__fmul_rn(wy0, ft), __fmul_rn(wy1, fb));
+        const bool pos = v > 0.f;                       // the scan starts from (class 0, 0.0): nothing <= 0 replaces it
+        const int k_max = pos ? fk : 0;
+        const float c_max = pos ? v : 0.f;
+        if (xin) post_emit(a, img, plane, (size_t)y * a.ow + x, k_max, c_max);
+        continue;
+      }
+    }
     if (r0 != cur0) {
       if (r0 == cur1) {
 #pragma unroll
@@ -292,25 +362,7 @@ __global__ void __launch_bounds__(128, 3) post_strip_kernel(PostArgs a) {
       k_max = gt ? bk[j] : k_max;
       c_max = fmaxf(c_max, bv[j]);
     }
-    if (!xin) continue;
-    const float av = __fmul_rn(c_max, 255.0f);
-    const int alpha = av >= 255.0f ? 255 : (int)av;  // c_max >= 0 always; trunc toward zero, saturate
-    const uint32_t col = __ldg(a.color_lut + (k_max % 20) * 256 + alpha);
-    const size_t gp = (size_t)img * plane + pix;
-    if (a.class_map) a.class_map[gp] = (uint8_t)k_max;
-    a.decoded[gp] = col;
-    if (a.frame_bgr && (a.blended || a.frame_rgba)) {
-      const uint8_t* f = a.frame_bgr + gp * 3;
-      const uint32_t fb = f[0], fg = f[1], fr = f[2];
-      if (a.frame_rgba) a.frame_rgba[gp] = fr | (fg << 8) | (fb << 16) | 0xff000000u;
-      if (a.blended) {
-        const uint32_t ia = 255u - (col >> 24);
-        const uint32_t r = min(255u, (col & 0xff) + (fr * ia + 127u) / 255u);
-        const uint32_t g = min(255u, ((col >> 8) & 0xff) + (fg * ia + 127u) / 255u);
-        const uint32_t b = min(255u, ((col >> 16) & 0xff) + (fb * ia + 127u) / 255u);
-        a.blended[gp] = r | (g << 8) | (b << 16) | 0xff000000u;
-      }
-    }
+    if (xin) post_emit(a, img, plane, pix, k_max, c_max);
   }
 }
 
@@ -402,6 +454,10 @@ size_t post_smem_bytes(const PostArgs& a) {
 
 cudaError_t launch_post(const PostArgs& a, cudaStream_t s) {
   if (a.k == 21 && a.ldk % 4 == 0 && a.ldk >= 24) {   // the 21 VOC classes of fcn-resnet50; other K: generic kernel below
+    if (a.top_code) {
+      const size_t npix = (size_t)a.n * a.lh * a.lw;
+      lowres_top_kernel<21><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(a.lowres, a.ldk, npix, a.top_code);
+    }
     dim3 grid((a.ow + 31) / 32, (a.oh + 4 * kPostStripRows - 1) / (4 * kPostStripRows), a.n);
     post_strip_kernel<21><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();

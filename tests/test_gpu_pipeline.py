@@ -172,3 +172,19 @@ def test_config5_4k_scale_half_vs_one(handle, tiny):
     g1 = pipe.advance(P.Frame(8, frame))
     assert g1.size == [3840, 2160] and g1.class_map.shape == (2160, 3840)
     assert (g1.buffer == oracle.frame_rgba(frame)).all()
+
+
+@pytest.mark.parametrize("w,h", [(320, 240), (200, 136), (1920, 1080)])
+def test_post_fast_path_is_bit_identical(handle, tiny, w, h):
+    """The post-kernel interpolates only the winning class wherever one class wins all four low-res neighbours by a safe
+    margin.  Asking for the full-resolution logits disables that fast path, so the two calls must agree bit for bit."""
+    path, _ = tiny
+    handle.model_load(path)
+    handle.scale_control(1.0)
+    frame = synth.synth_frame(w, h, 3)
+    fast = handle.advance(frame, 1, want=("class_map", "decoded_rgba", "blended_rgba"))
+    full = handle.advance(frame, 1, want=("class_map", "decoded_rgba", "blended_rgba", "logits_f32"))
+    assert (fast["class_map"] == full["class_map"]).all()
+    assert (fast["decoded_rgba"] == full["decoded_rgba"]).all()
+    assert (fast["blended_rgba"] == full["blended_rgba"]).all()
+    assert len(np.unique(fast["class_map"])) >= 3          # a map with real class boundaries, not a constant
