@@ -61,7 +61,7 @@ typedef struct infur_b200_config {
   int32_t compute_aux;   /* also evaluate the `aux` head (the reference's caller discards it, app.rs:116) */
   int32_t blend;         /* also produce blended_rgba (new feature; gui.rs:324-329 "todo: blend somehow?") */
   int32_t conv_impl;     /* INFUR_CONV_TCGEN05 */
-  int32_t use_cuda_graph;/* capture the per-shape forward into a CUDA graph */
+  int32_t use_cuda_graph;/* reserved, must be 0 (the ~54 launches of a frame are hidden behind > 2 ms of kernels) */
   int32_t autotune;      /* time the N-tile candidates of every convolution once per (shape, batch) plan and keep the fastest
                           * (default 1; results are bit-identical for every choice) */
 } infur_b200_config;

@@ -58,6 +58,7 @@ int32_t infur_b200_create(const infur_b200_config* cfg, infur_b200_handle** out)
   }
   if (c.resize_mode != INFUR_RESIZE_NEAREST) return fail(nullptr, INFUR_E_UNSUPPORTED, "create: only INFUR_RESIZE_NEAREST (the reference's mode) is implemented");
   if (c.conv_impl != INFUR_CONV_TCGEN05 && c.conv_impl != INFUR_CONV_VALIDATE) return fail(nullptr, INFUR_E_INVALID_ARG, "create: unknown conv_impl");
+  if (c.use_cuda_graph != 0) return fail(nullptr, INFUR_E_UNSUPPORTED, "create: use_cuda_graph is reserved and must be 0");
   if (c.max_batch < 1 || c.max_batch > 64 || c.ring_depth < 1 || c.ring_depth > 16) return fail(nullptr, INFUR_E_INVALID_ARG, "create: max_batch must be 1..64, ring_depth 1..16");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(nullptr, INFUR_E_NO_DEVICE, "no CUDA device: this library has no CPU fallback"); }
