@@ -50,7 +50,8 @@ enum {
 
 enum { INFUR_RESIZE_NEAREST = 0 /* fr::ResizeAlg::Nearest, processing.rs:189 (the reference's only mode) */ };
 enum { INFUR_CONV_TCGEN05 = 0, INFUR_CONV_VALIDATE = 1 /* slow CUDA-core kernel, validation only; never selected implicitly */,
-       INFUR_CONV_TCGEN05_PAIR = 2 /* conv_test only: force the CTA-pair (cta_group::2) variant of the tcgen05 kernel */ };
+       INFUR_CONV_TCGEN05_PAIR = 2 /* conv_test only: force the CTA-pair (cta_group::2) variant of the tcgen05 kernel */,
+       INFUR_CONV_TCGEN05_HALO = 3 /* conv_test only: force the halo-patch variant (3x3 / stride 1 convolutions) */ };
 
 typedef struct infur_b200_config {
   uint32_t struct_size;  /* sizeof(infur_b200_config) */

@@ -30,6 +30,7 @@ E_STREAM_END = 13
 CONV_TCGEN05 = 0
 CONV_VALIDATE = 1
 CONV_TCGEN05_PAIR = 2   # conv_test only
+CONV_TCGEN05_HALO = 3   # conv_test only
 LOAD_DEFAULT = 0
 LOAD_SKIP_WEIGHTS = 1
 

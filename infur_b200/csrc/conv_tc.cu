@@ -164,11 +164,11 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 // announces its part through the chunk_ready mbarrier and moves on.
 struct EpiBars { uint32_t res, ready, free_; };
 
-template <int BLOCK_N, int ACC, bool HAS_RES, class Sched, bool PAIR = false>
+template <int BLOCK_N, int ACC, bool HAS_RES, class Sched, bool PAIR = false, int EB = 4>
 __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sched, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                              const EpiBars eb, uint32_t epi_base, int ew, int lane) {
   constexpr int CH = BLOCK_N / 64;            // chunks per tile
-  constexpr int EB = HAS_RES ? 4 : 2;         // smem chunk buffers
+  static_assert(!HAS_RES || EB == 4, "the residual prefetch uses four chunk buffers");
   const int quad = ew & 3, half = ew >> 2;
   const int row = quad * 32 + lane;
   const uint32_t sw = (uint32_t)(row & 7);
@@ -253,10 +253,9 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
 // The single thread that owns every bulk copy of the epilogue: stores chunk q when all eight warps have
 // written it, then (one store later, so it never waits on the store it just issued) recycles the previous
 // buffer: HAS_RES -> prefetch the residual of chunk q-1+EB into it, else -> mark it free.
-template <int BLOCK_N, bool HAS_RES, class Sched>
+template <int BLOCK_N, bool HAS_RES, class Sched, int EB = 4>
 __device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvTcGeom& g, const Sched sched, const EpiBars eb, uint32_t epi_base) {
   constexpr int CH = BLOCK_N / 64;
-  constexpr int EB = HAS_RES ? 4 : 2;
   const int total = sched.count() * CH;
   auto issue_res = [&](int qq) {
     const TileCoord tc = decode_tile(g, sched.tile(qq / CH));
@@ -275,13 +274,16 @@ __device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvT
       ptx::mbar_wait(eb.ready + 8u * b, (uint32_t)(q / EB) & 1u);
       ptx::tma_store_4d(&maps.c, epi_base + b * kEpiBufBytes, tc.nt * BLOCK_N + c * 64, tc.ox0, tc.oy0, tc.img);
       ptx::tma_store_commit();
-      if (q >= 1) {
-        ptx::tma_store_wait_read<1>();          // the store of chunk q-1 has left its buffer
-        if (HAS_RES) {
+      if (HAS_RES) {
+        if (q >= 1) {
+          ptx::tma_store_wait_read<1>();          // the store of chunk q-1 has left its buffer
           if (q - 1 + EB < total) issue_res(q - 1 + EB);
-        } else {
-          ptx::mbar_arrive(eb.free_ + 8u * ((q - 1) % EB));
         }
+      } else if (q >= EB - 1) {
+        // up to EB-1 stores stay in flight; the one issued EB-1 chunks ago has been read out of smem by now (its
+        // completion is slow to observe, ~1 us, which is why a single store in flight throttled the epilogue)
+        ptx::tma_store_wait_read<EB - 1>();
+        ptx::mbar_arrive(eb.free_ + 8u * ((q - (EB - 1)) % EB));
       }
     }
   }
@@ -339,7 +341,6 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
   const int bw_log2 = g.bw_log2;
-  const int bw = 1 << bw_log2;
   const int bh = kBlockM >> bw_log2;
 
   if (warp == 0) {
@@ -354,20 +355,20 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
         const int ty = m % g.tiles_y;
         const int img = m / g.tiles_y;
         const int ox0 = tx << bw_log2, oy0 = ty * bh;
-        int kb = 0;
-        for (int tap = 0; tap < g.num_taps; ++tap) {
-          const CUtensorMap* am = &maps.a[g.tap_view[tap]];
-          const int x = ox0 + g.tap_dx[tap], y = oy0 + g.tap_dy[tap];
-          const int ncc = g.tap_cc[tap];
-          for (int cc = 0; cc < ncc; ++cc, ++kb) {
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = smem_base + stage * C::kStageBytes;
-            ptx::mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
-            ptx::tma_load_4d(a_dst, am, full_bar(stage), cc * kBlockK, x, y, img);
-            ptx::tma_load_2d(a_dst + kABytes, &maps.b, full_bar(stage), kb * kBlockK, nt * BLOCK_N);
-            if (++stage == num_stages) { stage = 0; phase ^= 1u; }
-          }
-        }
+        // K order: for every 64-channel chunk all filter taps (chunk-major: the same order in every kernel variant, so
+        // each output element accumulates identically whichever variant the autotuner picks), then a fused shortcut tap
+        auto load_kblock = [&](int tap, int cc, int kcoord) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * C::kStageBytes;
+          ptx::mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
+          ptx::tma_load_4d(a_dst, &maps.a[g.tap_view[tap]], full_bar(stage), cc * kBlockK, ox0 + g.tap_dx[tap], oy0 + g.tap_dy[tap], img);
+          ptx::tma_load_2d(a_dst + kABytes, &maps.b, full_bar(stage), kcoord, nt * BLOCK_N);
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        };
+        for (int cc = 0; cc < g.cchunks; ++cc)
+          for (int tap = 0; tap < g.main_taps; ++tap) load_kblock(tap, cc, (tap * g.cchunks + cc) * kBlockK);
+        for (int tap = g.main_taps; tap < g.num_taps; ++tap)
+          for (int cc = 0; cc < g.tap_cc[tap]; ++cc) load_kblock(tap, cc, (g.main_taps * g.cchunks + cc) * kBlockK);
       }
     }
   } else if (warp == 1) {
@@ -406,8 +407,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     if constexpr (BLOCK_N >= 64) {
       if (ptx::elect_one()) {
         const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
-        if (g.store_mode == 1) epilogue_dma<BLOCK_N, false>(maps, g, sched, eb, epi_base);
-        else if (g.store_mode == 2) epilogue_dma<BLOCK_N, true>(maps, g, sched, eb, epi_base);
+        if (g.store_mode == 1) {
+          if (g.epi_bufs == 4) epilogue_dma<BLOCK_N, false, Sched1, 4>(maps, g, sched, eb, epi_base);
+          else epilogue_dma<BLOCK_N, false, Sched1, 2>(maps, g, sched, eb, epi_base);
+        } else if (g.store_mode == 2) epilogue_dma<BLOCK_N, true>(maps, g, sched, eb, epi_base);
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -417,8 +420,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       if (ew < 4) epilogue_direct<BLOCK_N, C::kAcc>(g, tmem_base, tfull_bar(0), tempty_bar(0), ew, lane, ew * 32 + lane);
     } else if constexpr (BLOCK_N >= 64) {
       const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
-      if (g.store_mode == 1) epilogue_tma<BLOCK_N, C::kAcc, false>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-      else epilogue_tma<BLOCK_N, C::kAcc, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      if (g.store_mode == 1) {
+        if (g.epi_bufs == 4) epilogue_tma<BLOCK_N, C::kAcc, false, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+        else epilogue_tma<BLOCK_N, C::kAcc, false, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      } else epilogue_tma<BLOCK_N, C::kAcc, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
     }
   }
 
@@ -506,21 +511,19 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
       int it = 0;
       for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
         const TileCoord tc = decode_tile(g, tile);
-        int kb = 0;
-        for (int tap = 0; tap < g.num_taps; ++tap) {
-          const CUtensorMap* am = &maps.a[g.tap_view[tap]];
-          const int x = tc.ox0 + g.tap_dx[tap], y = tc.oy0 + g.tap_dy[tap];
-          const int ncc = g.tap_cc[tap];
-          for (int cc = 0; cc < ncc; ++cc, ++kb) {
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = smem_base + stage * kPairStageBytes;
-            const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
-            if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2u * (uint32_t)kPairStageBytes);
-            ptx::tma_load_4d_2sm(a_dst, am, lead_full, cc * kBlockK, x, y, tc.img);
-            ptx::tma_load_2d_2sm(a_dst + kABytes, &maps.b, lead_full, kb * kBlockK, tc.nt * BLOCK_N + rank * 128);
-            if (++stage == num_stages) { stage = 0; phase ^= 1u; }
-          }
-        }
+        auto load_kblock = [&](int tap, int cc, int kcoord) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * kPairStageBytes;
+          const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
+          if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2u * (uint32_t)kPairStageBytes);
+          ptx::tma_load_4d_2sm(a_dst, &maps.a[g.tap_view[tap]], lead_full, cc * kBlockK, tc.ox0 + g.tap_dx[tap], tc.oy0 + g.tap_dy[tap], tc.img);
+          ptx::tma_load_2d_2sm(a_dst + kABytes, &maps.b, lead_full, kcoord, tc.nt * BLOCK_N + rank * 128);
+          if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        };
+        for (int cc = 0; cc < g.cchunks; ++cc)      // chunk-major K order, see conv_tc_kernel
+          for (int tap = 0; tap < g.main_taps; ++tap) load_kblock(tap, cc, (tap * g.cchunks + cc) * kBlockK);
+        for (int tap = g.main_taps; tap < g.num_taps; ++tap)
+          for (int cc = 0; cc < g.tap_cc[tap]; ++cc) load_kblock(tap, cc, (g.main_taps * g.cchunks + cc) * kBlockK);
       }
     }
   } else if (warp == 1) {
@@ -554,12 +557,12 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
     }
   } else if (warp == kDmaWarp) {
     if (ptx::elect_one()) {
-      if (g.store_mode == 1) epilogue_dma<BLOCK_N, false>(maps, g, sched, eb, epi_base);
-      else epilogue_dma<BLOCK_N, true>(maps, g, sched, eb, epi_base);
+      if (g.store_mode == 1) epilogue_dma<BLOCK_N, false, Sched2, 4>(maps, g, sched, eb, epi_base);
+      else epilogue_dma<BLOCK_N, true, Sched2, 4>(maps, g, sched, eb, epi_base);
     }
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;
-    if (g.store_mode == 1) epilogue_tma<BLOCK_N, ACC, false, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    if (g.store_mode == 1) epilogue_tma<BLOCK_N, ACC, false, Sched2, true, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
     else epilogue_tma<BLOCK_N, ACC, true, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
   }
 
@@ -568,6 +571,155 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo variant for 3x3 / stride 1 convolutions (pad = dilation d in {1, 2, 4}).  The tap-wise kernels above fetch the
+// activation tile nine times, once per filter tap, shifted by the tap offset: 9 x 16 KB through the L2 -> SM port
+// per 64-channel chunk.  Here the tile's HALO PATCH ((16 + 2d) rows x 16 pixels x 64 channels) is fetched ONCE per
+// chunk, and the nine taps are nine UMMA descriptors into it: with an 8-pixel-wide x 16-row output tile, accumulator
+// row m = 8 py + px, an 8-row core-matrix group is one patch row, so start address = patch + ((ky d) * 16 + kx d) * 128 B
+// and stride-between-groups = one patch row (2 KB) select exactly the shifted window.  The 128B swizzle is a function of
+// the shared-memory ADDRESS bits (that is what lets TMA and UMMA agree on it), so a window that starts at any 128-byte
+// row reads back what TMA wrote -- verified on hardware with the descriptor's base-offset field left 0 (setting it to
+// (start >> 7) & 7 gives wrong results).  Weights stream through their own ring, one (tap, chunk) tile per stage.
+constexpr int kHaloPatchPx = 16;                    // patch pitch in pixels: 8 + 2d <= 16, and a multiple of the 8-row swizzle atom
+constexpr int kHaloPatchBytesMax = kHaloPatchPx * 24 * 128;   // d = 4: 24 rows -> 48 KB
+constexpr int kHaloMaxBStages = 12;
+
+template <int BLOCK_N>
+struct HaloCfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kAcc = BLOCK_N >= 256 ? 2 : 4;
+  static constexpr int kTmemCols = kAcc * BLOCK_N;
+  __host__ __device__ static constexpr int b_stages() {
+    int s = (kSmemLimit - 1024 - kBarBytes - 2 * kHaloPatchBytesMax - 4 * kEpiBufBytes) / kBBytes;
+    return s > kHaloMaxBStages ? kHaloMaxBStages : s;
+  }
+  __host__ __device__ static constexpr int smem_bytes() { return 2 * kHaloPatchBytesMax + b_stages() * kBBytes + 4 * kEpiBufBytes + 1024 + kBarBytes; }
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
+  using C = HaloCfg<BLOCK_N>;
+  constexpr int ACC = C::kAcc;
+  constexpr int BS = C::b_stages();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + 2 * kHaloPatchBytesMax;
+  const uint32_t epi_base = b_base + BS * C::kBBytes;
+  const uint32_t bar_base = epi_base + 4 * kEpiBufBytes;
+  // barriers: b_full[12], b_empty[12], a_full[2], a_empty[2], tmem_full[4], tmem_empty[4], epilogue (res, ready, free) x 4
+  auto bfull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (kHaloMaxBStages + s); };
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + s); };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + 2 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + 4 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + 4 + kMaxAcc + s); };
+  EpiBars eb;
+  eb.res = bar_base + 8u * (2 * kHaloMaxBStages + 4 + 2 * kMaxAcc);
+  eb.ready = eb.res + 8u * kMaxEpiBufs;
+  eb.free_ = eb.ready + 8u * kMaxEpiBufs;
+  const uint32_t tmem_ptr_addr = eb.free_ + 8u * kMaxEpiBufs;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int d = g.halo_dil;
+  const uint32_t patch_bytes = (uint32_t)(kHaloPatchPx * (16 + 2 * d) * 128);
+  const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
+
+  if (warp == 0 && ptx::elect_one()) { ptx::prefetch_tmap(&maps.a[0]); ptx::prefetch_tmap(&maps.b); ptx::prefetch_tmap(&maps.c); }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < BS; ++s) { ptx::mbar_init(bfull_bar(s), 1); ptx::mbar_init(bempty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(afull_bar(s), 1); ptx::mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < ACC; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), kEpiWarps); }
+    for (int s = 0; s < kMaxEpiBufs; ++s) {
+      ptx::mbar_init(eb.res + 8u * s, 1);
+      ptx::mbar_init(eb.ready + 8u * s, kEpiWarps);
+      ptx::mbar_init(eb.free_ + 8u * s, 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_addr, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      int bs = 0, au = 0;          // B ring position, patch use counter
+      uint32_t bphase = 0;
+      int it = 0;
+      for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
+        const TileCoord tc = decode_tile(g, tile);
+        for (int cc = 0; cc < g.cchunks; ++cc, ++au) {
+          const int ab = au & 1;
+          ptx::mbar_wait(aempty_bar(ab), ((uint32_t)(au >> 1) & 1u) ^ 1u);
+          ptx::mbar_expect_tx(afull_bar(ab), patch_bytes);
+          ptx::tma_load_4d(smem_base + ab * kHaloPatchBytesMax, &maps.a[0], afull_bar(ab), cc * kBlockK, tc.ox0 - d, tc.oy0 - d, tc.img);
+          for (int tap = 0; tap < 9; ++tap) {
+            ptx::mbar_wait(bempty_bar(bs), bphase ^ 1u);
+            ptx::mbar_expect_tx(bfull_bar(bs), (uint32_t)C::kBBytes);
+            ptx::tma_load_2d(b_base + bs * C::kBBytes, &maps.b, bfull_bar(bs), (tap * g.cchunks + cc) * kBlockK, tc.nt * BLOCK_N);
+            if (++bs == BS) { bs = 0; bphase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BLOCK_N);
+      int bs = 0, au = 0;
+      uint32_t bphase = 0;
+      int it = 0;
+      for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
+        const int as = it % ACC;
+        const uint32_t aphase = (uint32_t)(it / ACC) & 1u;
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int cc = 0; cc < g.cchunks; ++cc, ++au) {
+          const int ab = au & 1;
+          ptx::mbar_wait(afull_bar(ab), (uint32_t)(au >> 1) & 1u);
+          const uint32_t patch = smem_base + ab * kHaloPatchBytesMax;
+          for (int tap = 0; tap < 9; ++tap) {
+            ptx::mbar_wait(bfull_bar(bs), bphase);
+            ptx::tc_fence_after();
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            const uint32_t a_addr = patch + (uint32_t)((ky * d * kHaloPatchPx + kx * d) * 128);
+            const uint64_t a_desc = ptx::make_smem_desc_sw128(a_addr, kHaloPatchPx * 128);
+            const uint64_t b_desc = ptx::make_smem_desc(b_base + bs * C::kBBytes, 128);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              ptx::umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (cc | tap | k) != 0);
+            ptx::umma_commit(bempty_bar(bs));
+            if (++bs == BS) { bs = 0; bphase ^= 1u; }
+          }
+          ptx::umma_commit(aempty_bar(ab));
+        }
+        ptx::umma_commit(tfull_bar(as));
+      }
+    }
+  } else if (warp == kDmaWarp) {
+    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false, Sched1, 4>(maps, g, sched, eb, epi_base);
+  } else if (warp >= kEpiWarp0) {
+    epilogue_tma<BLOCK_N, ACC, false, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -584,7 +736,7 @@ constexpr int kStemRowBytes = kStemRowGroups * 128;          // 2176
 constexpr int kStemStageBytes = 16384;                       // 7 rows x 2176 = 15232 B used
 constexpr int kStemTxBytes = 7 * kStemRowBytes;
 constexpr int kStemStages = 8;
-constexpr int kStemSmemBytes = kStemStages * kStemStageBytes + 2 * kEpiBufBytes + kStemWBytes + 1024 + kBarBytes;
+constexpr int kStemSmemBytes = kStemStages * kStemStageBytes + 4 * kEpiBufBytes + kStemWBytes + 1024 + kBarBytes;
 
 __global__ void __launch_bounds__(kThreads, 1)
 stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
@@ -593,7 +745,7 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + kStemStages * kStemStageBytes;
-  const uint32_t w_base = epi_base + 2 * kEpiBufBytes;
+  const uint32_t w_base = epi_base + 4 * kEpiBufBytes;
   const uint32_t bar_base = w_base + kStemWBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -678,9 +830,9 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       }
     }
   } else if (warp == kDmaWarp) {
-    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false>(maps, g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, eb, epi_base);
+    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false, Sched1, 4>(maps, g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, eb, epi_base);
   } else if (warp >= kEpiWarp0) {
-    epilogue_tma<BLOCK_N, ACC, false>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
+    epilogue_tma<BLOCK_N, ACC, false, Sched1, false, 4>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
                                  warp - kEpiWarp0, lane);
   }
 
@@ -721,6 +873,9 @@ cudaError_t conv_tc_init() {
   if ((e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::smem_bytes())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<128>::smem_bytes())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<256>::smem_bytes())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   return cudaSuccess;
 }
@@ -731,6 +886,18 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     if (grid <= 0) return cudaSuccess;
     if (block_n != 64 || g.store_mode != 1 || g.bw_log2 != 7) return cudaErrorInvalidValue;
     stem_tc_kernel<<<grid, kThreads, kStemSmemBytes, stream>>>(maps, g);
+    return cudaGetLastError();
+  }
+  if (g.halo) {
+    const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
+    if (grid <= 0) return cudaSuccess;
+    if (g.store_mode != 1 || g.bw_log2 != 3 || g.main_taps != 9 || g.num_taps != 9) return cudaErrorInvalidValue;
+    switch (block_n) {
+      case 64: conv_halo_kernel<64><<<grid, kThreads, HaloCfg<64>::smem_bytes(), stream>>>(maps, g); break;
+      case 128: conv_halo_kernel<128><<<grid, kThreads, HaloCfg<128>::smem_bytes(), stream>>>(maps, g); break;
+      case 256: conv_halo_kernel<256><<<grid, kThreads, HaloCfg<256>::smem_bytes(), stream>>>(maps, g); break;
+      default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
   }
   if (g.pair) {

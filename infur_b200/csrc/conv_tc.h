@@ -26,11 +26,13 @@ struct ConvTcGeom {
   int32_t bw_log2;            // tile is (1 << bw_log2) wide, 128 >> bw_log2 high
   int32_t tiles_x, tiles_y, tiles_n, num_tiles;
   int32_t num_taps, num_kb;   // K blocks = sum over taps of tap_cc[tap], 64 input channels each
+  int32_t main_taps, cchunks; // the kh*kw filter taps all have `cchunks` 64-channel chunks; taps beyond them are fused shortcut taps
   int32_t out_ld;             // elements between consecutive output pixels
   int32_t relu;
   int32_t store_mode;         // 0: per-thread vector stores (f32 head); 1: smem-staged TMA store; 2: + TMA residual prefetch
   int32_t stages, epi_bufs;   // smem pipeline depth and epilogue chunk buffers (0 / 2 / 4), see conv_tc_stages
   int32_t pair, num_work;     // 1: conv_tc_pair_kernel (cta_group::2); work items = ceil(M tiles / 2) * tiles_n
+  int32_t halo, halo_dil;     // 1: conv_halo_kernel (3x3 / stride 1 / pad = dilation = halo_dil): maps.a[0] has a halo-patch box
   int32_t stem;               // 1: 7x7/s2 RGB stem through stem_tc_kernel (maps.a[0] = row-group view of the padded NHWC4 input)
   const __half* stem_w;       // stem weights in smem order [7 ky][4 k-cores][64 cout][8], kStemWBytes
   const float* bias;          // [tiles_n * BLOCK_N]

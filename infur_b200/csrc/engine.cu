@@ -76,6 +76,7 @@ static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((
 
 static bool skip_fusion_env() { const char* e = getenv("INFUR_B200_NO_SHORTCUT_FUSION"); return e && e[0] == '1'; }
 
+static bool halo_disabled_env() { const char* e = getenv("INFUR_B200_NO_HALO"); return e && e[0] == '1'; }
 static bool pair_disabled_env() { const char* e = getenv("INFUR_B200_NO_CTA_PAIR"); return e && e[0] == '1'; }
 
 static void classify_conv(const ConvOp& c, bool reads_input, bool is_head, DevConv& d) {
@@ -196,8 +197,12 @@ struct ConvIO {
   int out_ld = 0;
 };
 
-static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int block_n, bool pair = false) {
-  po.block_n = block_n; po.pair = pair;
+enum { kVarPlain = 0, kVarPair = 1, kVarHalo = 2 };
+static bool halo_ok(const DevConv& d) { return !d.stem && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad == d.dil && (d.dil == 1 || d.dil == 2 || d.dil == 4) && d.cin2 == 0; }
+
+static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int block_n, int variant = kVarPlain) {
+  const bool pair = variant == kVarPair, halo = variant == kVarHalo;
+  po.block_n = block_n; po.pair = pair; po.variant = variant;
   ConvTcGeom& g = po.geom;
   memset(&g, 0, sizeof(g));
   memset(&po.maps, 0, sizeof(po.maps));
@@ -210,17 +215,24 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
     const long cost = (long)((io.ow + bw - 1) / bw) * ((io.oh + bh - 1) / bh);
     if (best < 0 || cost < best_cost) { best = l2; best_cost = cost; }
   }
+  if (halo) best = 3;   // 8 wide x 16 high: an 8-row core-matrix group = one patch row (conv_halo_kernel)
   g.bw_log2 = best;
   const int bw = 1 << best, bh = 128 >> best;
   g.tiles_x = (io.ow + bw - 1) / bw; g.tiles_y = (io.oh + bh - 1) / bh;
   g.tiles_n = d.cout_pad / block_n;
   g.num_tiles = io.n * g.tiles_x * g.tiles_y * g.tiles_n;
   g.num_taps = d.taps + (d.cin2 ? 1 : 0); g.num_kb = d.taps * d.cchunks + d.cin2 / 64;
+  g.main_taps = d.taps; g.cchunks = d.cchunks;
   g.out_ld = io.out_ld; g.relu = d.relu ? 1 : 0;
   g.store_mode = io.y_f32 ? 0 : (io.residual ? 2 : 1);
-  g.epi_bufs = g.store_mode == 0 ? 0 : (g.store_mode == 1 ? 2 : 4);
+  // chunk buffers of the epilogue: 4 whenever the smem pipeline keeps >= 4 stages beside them, or the K loop is so short
+  // (<= 8 blocks) that the epilogue, not the operand pipeline, sets the pace; else 2
+  g.epi_bufs = g.store_mode == 0 ? 0 : 4;
+  if (g.store_mode == 1 && !pair && !halo && !d.stem && conv_tc_stages(block_n, 4) < 4 && g.num_kb > 8) g.epi_bufs = 2;
   g.stages = pair ? conv_tc_pair_stages(g.epi_bufs) : conv_tc_stages(block_n, g.epi_bufs);
   g.pair = pair ? 1 : 0;
+  g.halo = halo ? 1 : 0; g.halo_dil = d.dil;
+  if (halo) { if (!halo_ok(d) || io.y_f32 || io.residual) return Status::error(INFUR_E_UNSUPPORTED, "halo variant: needs a 3x3 / stride 1 / pad = dilation convolution without residual"); g.stages = 0; }
   g.num_work = ((io.n * g.tiles_x * g.tiles_y + 1) / 2) * g.tiles_n;
   g.bias = io.bias; g.residual = io.residual; g.out = io.y; g.out_f32 = io.y_f32;
   Status st;
@@ -238,6 +250,14 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
     st = make_tmap_f16(&po.maps.a[0], io.x, 4, dims, strides, abox, false);
     if (!st.ok()) return st;
     po.maps.a[1] = po.maps.a[0]; po.maps.a[2] = po.maps.a[0]; po.maps.a[3] = po.maps.a[0];
+  } else if (halo) {
+    const uint64_t dims[4] = {(uint64_t)d.cin, (uint64_t)io.w, (uint64_t)io.h, (uint64_t)io.n};
+    const uint64_t strides[3] = {(uint64_t)d.cin * 2, (uint64_t)io.w * d.cin * 2, (uint64_t)io.h * io.w * d.cin * 2};
+    const uint32_t pbox[4] = {64, 16, (uint32_t)(16 + 2 * d.dil), 1};   // halo patch: 16 px pitch x (16 + 2d) rows
+    st = make_tmap_f16(&po.maps.a[0], io.x, 4, dims, strides, pbox);
+    if (!st.ok()) return st;
+    po.maps.a[1] = po.maps.a[0]; po.maps.a[2] = po.maps.a[0]; po.maps.a[3] = po.maps.a[0];
+    for (int t = 0; t < 9; ++t) g.tap_cc[t] = (uint8_t)d.cchunks;
   } else {
     const int s = d.stride;
     bool have[4] = {false, false, false, false};
@@ -318,22 +338,23 @@ static void setup_direct(const DevConv& d, const ConvIO& io, const __half* wv, D
 // result is bit-identical whichever wins; only time differs: a narrower tile leaves room for more pipeline
 // stages (more HBM bytes in flight for the memory-bound 1x1 convs), a wider one halves the activation re-reads.
 static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO& io, PlanOp& po) {
-  struct Cand { int bn; bool pair; };
-  static const Cand cands[4] = {{256, true}, {256, false}, {128, false}, {64, false}};
+  struct Cand { int bn; int var; };
+  static const Cand cands[7] = {{256, kVarPair}, {256, kVarPlain}, {128, kVarPlain}, {64, kVarPlain}, {256, kVarHalo}, {128, kVarHalo}, {64, kVarHalo}};
   if (d.stem) return Status();
   const bool allow_pair = !pair_disabled_env();
   cudaEvent_t e0, e1;
   CU_TRY(cudaEventCreate(&e0));
   CU_TRY(cudaEventCreate(&e1));
-  Cand best = {po.block_n, po.pair};
+  const bool allow_halo = halo_ok(d) && !io.residual && !io.y_f32 && !halo_disabled_env();
+  Cand best = {po.block_n, po.variant};
   float best_ms = 1e30f;
   Status st;
   // two interleaved rounds, minimum per candidate: a single short measurement is at the mercy of clock ramps
   for (int round = 0; round < 2 && st.ok(); ++round) {
     for (const Cand& c : cands) {
-      if (c.bn > d.block_n || d.cout_pad % c.bn != 0 || (c.pair && !allow_pair)) continue;
+      if (c.bn > d.block_n || d.cout_pad % c.bn != 0 || (c.var == kVarPair && !allow_pair) || (c.var == kVarHalo && !allow_halo)) continue;
       PlanOp trial;
-      if (!(st = setup_conv_tc(d, io, trial, c.bn, c.pair)).ok()) break;
+      if (!(st = setup_conv_tc(d, io, trial, c.bn, c.var)).ok()) break;
       cudaError_t e = conv_tc_launch(c.bn, trial.maps, trial.geom, H->num_sms, H->stream);   // warm-up
       cudaEventRecord(e0, H->stream);
       for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = conv_tc_launch(c.bn, trial.maps, trial.geom, H->num_sms, H->stream);
@@ -343,14 +364,14 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
       if (e != cudaSuccess) { st = Status::error(INFUR_E_RUNTIME, std::string("autotune: ") + cudaGetErrorString(e)); break; }
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
-      const bool same = c.bn == best.bn && c.pair == best.pair;
+      const bool same = c.bn == best.bn && c.var == best.var;
       if (ms < best_ms * 0.97f || (same && ms < best_ms)) { best_ms = ms < best_ms ? ms : best_ms; best = c; }
     }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (!st.ok()) return st;
-  if (best.bn != po.block_n || best.pair != po.pair) st = setup_conv_tc(d, io, po, best.bn, best.pair);
+  if (best.bn != po.block_n || best.var != po.variant) st = setup_conv_tc(d, io, po, best.bn, best.var);
   return st;
 }
 
@@ -523,7 +544,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       os << "conv " << op.name << " [" << n << "x" << ti.h << "x" << ti.w << "x" << d.cin << "] -> [" << to.h << "x" << to.w << "x" << d.cout
          << "] k" << d.kh << " s" << d.stride << " p" << d.pad << " d" << d.dil << (io.residual ? " +res" : "") << (d.cin2 ? " +shortcut1x1" : "") << (d.relu ? " relu" : "");
       if (d.tc_ok)
-        os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << po.block_n << (po.pair ? " pair" : "") << " tiles "
+        os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << po.block_n << (po.variant == kVarPair ? " pair" : (po.variant == kVarHalo ? " halo" : "")) << " tiles "
            << po.geom.num_tiles << " kblocks " << po.geom.num_kb;
       os << " | GFLOP " << po.flops * 1e-9 << " MB " << po.bytes * 1e-6;
     } else {
@@ -643,7 +664,8 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   DevConv d;
   classify_conv(c, c.cin == 3, f32out, d);
   const bool pair = cd->impl == INFUR_CONV_TCGEN05_PAIR;
-  const bool tc = cd->impl == INFUR_CONV_TCGEN05 || pair;
+  const bool halo = cd->impl == INFUR_CONV_TCGEN05_HALO;
+  const bool tc = cd->impl == INFUR_CONV_TCGEN05 || pair || halo;
   if (tc && !d.tc_ok) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: shape not supported by the tcgen05 kernel: " + d.why_not);
   Plan tmp;
   Status st;
@@ -697,7 +719,8 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   io.out_ld = out_ld;
   PlanOp po;
   if (pair && (d.block_n != 256 || d.stem || f32out)) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the CTA-pair variant needs cout % 256 == 0 and an fp16 output");
-  if (tc) { if (!(st = setup_conv_tc(d, io, po, d.block_n, pair)).ok()) return st; }
+  if (halo && !halo_ok(d)) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the halo variant needs a 3x3 / stride 1 / pad = dilation convolution");
+  if (tc) { if (!(st = setup_conv_tc(d, io, po, d.block_n, pair ? kVarPair : (halo ? kVarHalo : kVarPlain))).ok()) return st; }
   else setup_direct(d, io, d_wv, po.direct);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -59,6 +59,7 @@ struct PlanOp {
   int op = -1;                 // index into model ops
   int block_n = 0;             // N tile of the tcgen05 kernel chosen for this op
   bool pair = false;           // CTA-pair (cta_group::2) variant
+  int variant = 0;             // 0 plain, 1 CTA pair, 2 halo patch (3x3)
   bool is_conv = false;
   ConvTcMaps maps;
   ConvTcGeom geom;

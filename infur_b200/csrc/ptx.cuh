@@ -223,6 +223,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// 128B-swizzled K-major descriptor with an explicit stride between 8-row groups.  The start address may be any
+// 128-byte row of a swizzled buffer: the swizzle is applied to address bits, not to the row index inside the operand.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // Shared-memory matrix descriptor without swizzle ("interleave" layout), K-major: the operand is a grid of core
 // matrices of 8 rows x 16 bytes whose rows are 16 bytes apart; lbo = byte distance between core matrices that
 // are adjacent in K, sbo = byte distance between adjacent 8-row groups (M / N direction).  Nothing requires

@@ -90,3 +90,29 @@ def test_conv_pair_bit_identical_to_single_cta(handle, case):
     y2 = handle.conv_test(x, wt, b, r, stride, pad, dil, relu, impl=L.CONV_TCGEN05_PAIR)
     assert (y1.view(np.uint16) == y2.view(np.uint16)).all()
     assert (np.abs(y2.astype(np.float32) - ref) <= 2e-3 + 4e-3 * np.abs(ref)).all()
+
+
+HALO_CASES = [
+    # the halo-patch variant (3x3 / stride 1 / pad = dilation): image edges, all three dilations of the network, ragged sizes
+    (1, 30, 40, 64, 64, 1),
+    (2, 30, 40, 128, 128, 2),
+    (1, 17, 23, 128, 256, 4),
+    (3, 5, 7, 64, 128, 1),
+    (1, 33, 9, 64, 64, 2),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=lambda c: "halo_n%d_%dx%d_c%d-%d_d%d" % c)
+def test_conv_halo_bit_identical_to_tapwise(handle, case):
+    """The halo variant fetches each activation patch once and reads the nine taps through shifted UMMA descriptors;
+    K blocks are accumulated in the same (chunk-major) order as in the tap-wise kernel, so the outputs agree bit for bit."""
+    n, h, w, cin, cout, d = case
+    rng = np.random.default_rng(abs(hash(case)) % 2**31)
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float16)
+    wt = (rng.standard_normal((cout, 3, 3, cin)) * (2.0 / (cin * 9)) ** 0.5).astype(np.float16)
+    b = rng.standard_normal(cout).astype(np.float32)
+    ref = ref_conv(x, wt, b, None, 1, d, d, True)
+    y1 = handle.conv_test(x, wt, b, None, 1, d, d, True, impl=L.CONV_TCGEN05)
+    y3 = handle.conv_test(x, wt, b, None, 1, d, d, True, impl=L.CONV_TCGEN05_HALO)
+    assert (y1.view(np.uint16) == y3.view(np.uint16)).all()
+    assert (np.abs(y3.astype(np.float32) - ref) <= 2e-3 + 4e-3 * np.abs(ref)).all()

@@ -127,6 +127,21 @@ def pair_big():
 
 
 @check
+def halo_3x3():
+    _conv_case("halo 3x3 64->64 p1 30x40", 1, 30, 40, 64, 64, 3, 1, 1, 1, impls=(3, 0))
+
+
+@check
+def halo_3x3_d2():
+    _conv_case("halo 3x3 128->128 d2 p2 30x40 n2", 2, 30, 40, 128, 128, 3, 1, 2, 2, impls=(3, 0))
+
+
+@check
+def halo_3x3_d4():
+    _conv_case("halo 3x3 128->256 d4 p4 17x23", 1, 17, 23, 128, 256, 3, 1, 4, 4, impls=(3, 0))
+
+
+@check
 def conv_head_f32():
     _conv_case("1x1 512->21 f32 30x40", 1, 30, 40, 512, 21, 1, 1, 0, 1, relu=False, f32=True)
 

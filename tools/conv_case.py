@@ -18,6 +18,8 @@ CASES = {
     "l1_conv3": (270, 480, 64, 256, 1, 1, 0, 1, True, True),
     "l1_down": (270, 480, 64, 256, 1, 1, 0, 1, False, False),
     "l2_conv3": (135, 240, 128, 512, 1, 1, 0, 1, True, True),
+    "l1_conv2": (270, 480, 64, 64, 3, 1, 1, 1, True, False),
+    "l2_conv2": (135, 240, 128, 128, 3, 1, 1, 1, True, False),
     "l3_conv1": (135, 240, 1024, 256, 1, 1, 0, 1, True, False),
     "l3_conv2": (135, 240, 256, 256, 3, 1, 2, 2, True, False),
     "l3_conv3": (135, 240, 256, 1024, 1, 1, 0, 1, True, True),
@@ -36,7 +38,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("name")
     ap.add_argument("--n", type=int, default=8)
-    ap.add_argument("--impl", type=int, default=0, help="0 tcgen05, 2 tcgen05 CTA pair")
+    ap.add_argument("--impl", type=int, default=0, help="0 tcgen05, 2 CTA pair, 3 halo patch (3x3)")
     a = ap.parse_args()
     from infur_b200 import processors as P
 
