@@ -80,6 +80,10 @@ int32_t infur_b200_create(const infur_b200_config* cfg, infur_b200_handle** out)
   for (int i = 0; i < 768; ++i) lut_h[i] = __float2half_rn(lut_f[i]);
   h->color_lut.resize(20 * 256 * 4);
   build_color_lut(h->color_lut.data());
+  __half lut_u8[768];
+  for (int i = 0; i < 768; ++i) lut_u8[i] = __float2half_rn((float)(i & 255));   // 0..255 are exact in fp16
+  if (cudaMalloc(&h->d_lut_u8, sizeof(lut_u8)) != cudaSuccess) return bail("cudaMalloc of lookup tables failed");
+  cudaMemcpy(h->d_lut_u8, lut_u8, sizeof(lut_u8), cudaMemcpyHostToDevice);
   if (cudaMalloc(&h->d_lut_f, sizeof(lut_f)) != cudaSuccess || cudaMalloc(&h->d_lut_h, sizeof(lut_h)) != cudaSuccess ||
       cudaMalloc(&h->d_color_lut, h->color_lut.size()) != cudaSuccess)
     return bail("cudaMalloc of lookup tables failed");
@@ -117,6 +121,7 @@ void infur_b200_destroy(infur_b200_handle* h) {
   h->model.reset();
   if (h->d_lut_f) cudaFree(h->d_lut_f);
   if (h->d_lut_h) cudaFree(h->d_lut_h);
+  if (h->d_lut_u8) cudaFree(h->d_lut_u8);
   if (h->d_color_lut) cudaFree(h->d_color_lut);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->h2d) cudaStreamDestroy(h->h2d);

@@ -595,7 +595,10 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
   PreArgs pa;
   memset(&pa, 0, sizeof(pa));
   pa.src = d_bgr; pa.n = p.n; pa.h = p.h; pa.w = p.w; pa.oh = p.oh; pa.ow = p.ow;
-  pa.xmap = p.xmap; pa.ymap = p.ymap; pa.lut_h = H->d_lut_h;
+  pa.xmap = p.xmap; pa.ymap = p.ymap;
+  // Float models: RGB + torchvision normalisation; Uint8 models: the raw bytes in B,G,R order (predict_onnx.rs:103-137,296-306)
+  const bool u8_model = p.has_model && !H->model->lm.io.float_input;
+  pa.lut_h = u8_model ? H->d_lut_u8 : H->d_lut_h; pa.bgr_order = u8_model ? 1 : 0;
   pa.stem_in = p.has_model ? p.stem_in : nullptr;
   pa.scaled_bgr = unit ? nullptr : p.scaled;
   const uint8_t* frame = unit ? d_bgr : p.scaled;

@@ -134,6 +134,7 @@ struct infur_b200_handle {
   bool dirty = true;
   float* d_lut_f = nullptr;
   __half* d_lut_h = nullptr;
+  __half* d_lut_u8 = nullptr;    // identity table for Uint8-input models (predict_onnx.rs:117-122: raw bytes, B,G,R order)
   uint32_t* d_color_lut = nullptr;
   std::vector<uint8_t> color_lut;
   std::unique_ptr<infur::DeviceModel> model;

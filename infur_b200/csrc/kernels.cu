@@ -31,8 +31,9 @@ __global__ void __launch_bounds__(256) pre_generic_kernel(PreArgs a, int stem_pi
     q[0] = b; q[1] = g; q[2] = r;
   }
   if (a.stem_in) {
-    __half2 rg = __halves2half2(lut[r], lut[256 + g]);
-    __half2 b0 = __halves2half2(lut[512 + b], __ushort_as_half((unsigned short)0));
+    const uint8_t c0 = a.bgr_order ? b : r, c2 = a.bgr_order ? r : b;
+    __half2 rg = __halves2half2(lut[c0], lut[256 + g]);
+    __half2 b0 = __halves2half2(lut[512 + c2], __ushort_as_half((unsigned short)0));
     uint2 v;
     v.x = *reinterpret_cast<uint32_t*>(&rg);
     v.y = *reinterpret_cast<uint32_t*>(&b0);
@@ -59,8 +60,9 @@ __global__ void __launch_bounds__(256) pre_unit_vec4_kernel(PreArgs a, int stem_
   uint32_t o[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __half2 rg = __halves2half2(lut[rr[i]], lut[256 + gg[i]]);
-    __half2 b0 = __halves2half2(lut[512 + bb[i]], __ushort_as_half((unsigned short)0));
+    const uint8_t c0 = a.bgr_order ? bb[i] : rr[i], c2 = a.bgr_order ? rr[i] : bb[i];
+    __half2 rg = __halves2half2(lut[c0], lut[256 + gg[i]]);
+    __half2 b0 = __halves2half2(lut[512 + c2], __ushort_as_half((unsigned short)0));
     o[2 * i] = *reinterpret_cast<uint32_t*>(&rg);
     o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&b0);
   }

@@ -22,7 +22,8 @@ struct PreArgs {
   int oh, ow;            // size after Scale
   const int32_t* xmap;   // [ow] nearest source column (nullptr = identity)
   const int32_t* ymap;   // [oh]
-  const __half* lut_h;   // [3][256] fp16, channel order R,G,B
+  const __half* lut_h;   // [3][256] fp16, one table per network input channel
+  int bgr_order;         // 0: network channels = (R, G, B) of the pixel (Float models); 1: (B, G, R) as stored (Uint8 models)
   __half* stem_in;       // [n][stem_rows(oh)][stem_pitch_px(ow)][4] fp16, or nullptr
   uint8_t* scaled_bgr;   // [n][oh][ow][3], or nullptr
 };

@@ -250,8 +250,6 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
   else if (in0.elem_type == 2) m.io.float_input = false;
   else throw ModelError(INFUR_E_MODEL_INPUT_FORMAT, std::string("only Float (f32) and Uint8 (u8) input supported, got ") + dtype_name(in0.elem_type));
   m.io.rgb = m.io.float_input;  // Model::control (:296-301): Float -> RGB + torchvision norm, else BGR
-  if (!m.io.nchw || !m.io.float_input)
-    throw ModelError(INFUR_E_MODEL_LOAD, "only NCHW Float32 image models run on the GPU path so far (NHWC / Uint8 inputs: see DESIGN.md 'next')");
 
   // ---- pass 1: aliases, compute-node list, consumer counts
   static const std::set<std::string> shape_ops = {"Shape", "Gather", "Unsqueeze", "Concat", "Slice", "Cast", "Constant", "Squeeze", "Floor", "Mul", "Div"};
@@ -263,8 +261,23 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
   };
   std::vector<const OnnxNode*> compute;
   std::set<std::string> shape_values;  // outputs of the size-computing subgraph
+  // Input adapters of NHWC / Uint8 models (infer_img_pre_proc's other conventions, predict_onnx.rs:240-262): ONNX Conv is
+  // NCHW / float only, so such a model starts with Transpose(perm 0,3,1,2) and / or Cast(to FLOAT) on its input.  Both are
+  // no-ops here: the engine's activation layout is its own (NHWC fp16) and the pre-kernel produces the values directly.
+  std::set<std::string> input_chain = {in0.name};
   for (auto& n : g.nodes) {
     if (n.op == "Identity") { if (n.in.size() == 1 && n.out.size() == 1) alias[n.out[0]] = n.in[0]; continue; }
+    if ((n.op == "Cast" || n.op == "Transpose") && n.in.size() == 1 && n.out.size() == 1 && input_chain.count(resolve(n.in[0])) &&
+        !(n.op == "Cast" && shape_values.count(n.in[0]))) {
+      if (n.op == "Cast" && attr_i(n, "to", 0) != 1) throw ModelError(INFUR_E_MODEL_LOAD, "Cast '" + n.name + "' on the model input must convert to FLOAT");
+      if (n.op == "Transpose") {
+        auto perm = attr_ints(n, "perm", {});
+        if (m.io.nchw || perm != std::vector<int64_t>{0, 3, 1, 2}) throw ModelError(INFUR_E_MODEL_LOAD, "Transpose '" + n.name + "' on the model input must be NHWC -> NCHW (perm 0,3,1,2)");
+      }
+      alias[n.out[0]] = n.in[0];
+      input_chain.insert(n.out[0]);
+      continue;
+    }
     if (n.op == "Conv" || n.op == "Relu" || n.op == "Add" || n.op == "MaxPool" || n.op == "Resize") { compute.push_back(&n); continue; }
     if (shape_ops.count(n.op)) {
       // only allowed when it does not touch an activation except through Shape

@@ -51,7 +51,7 @@ def synth_frame(w: int, h: int, index: int = 0, seed: int = 1234) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------- weights
-def build_fcn(seed: int = 0, layers=(3, 4, 6, 3), num_classes: int = 21, aux: bool = True, calib_hw=(96, 128)):
+def build_fcn(seed: int = 0, layers=(3, 4, 6, 3), num_classes: int = 21, aux: bool = True, calib_hw=(96, 128), uint8_input: bool = False):
     """torchvision FCN-ResNet (Bottleneck, stride-8 dilated backbone) with seeded synthetic weights.
 
     ``layers=(3,4,6,3)`` is FCN-ResNet50 (torchvision segmentation/fcn.py:102-114,168);
@@ -91,10 +91,13 @@ def build_fcn(seed: int = 0, layers=(3, 4, 6, 3), num_classes: int = 21, aux: bo
         # calibrate BN running statistics on one synthetic frame (one train-mode pass, momentum 1)
         h, w = calib_hw
         bgr = synth_frame(w, h, index=0, seed=4321)
-        x = torch.from_numpy(bgr[:, :, ::-1].astype(np.float32) / 255.0)
-        mean = torch.tensor([0.485, 0.456, 0.406])
-        std = torch.tensor([0.229, 0.224, 0.225])
-        x = ((x - mean) / std).permute(2, 0, 1)[None]
+        if uint8_input:   # a Uint8 model sees the raw bytes in B,G,R order (infur/src/predict_onnx.rs:117-122,296-301)
+            x = torch.from_numpy(bgr.astype(np.float32)).permute(2, 0, 1)[None]
+        else:
+            x = torch.from_numpy(bgr[:, :, ::-1].astype(np.float32) / 255.0)
+            mean = torch.tensor([0.485, 0.456, 0.406])
+            std = torch.tensor([0.229, 0.224, 0.225])
+            x = ((x - mean) / std).permute(2, 0, 1)[None]
         for m in model.modules():
             if isinstance(m, nn.BatchNorm2d):
                 m.momentum = 1.0
@@ -108,7 +111,7 @@ def build_fcn(seed: int = 0, layers=(3, 4, 6, 3), num_classes: int = 21, aux: bo
     return model
 
 
-def export_onnx(model, path: str, hw=(64, 64)) -> str:
+def export_onnx(model, path: str, hw=(64, 64), nhwc: bool = False, uint8_input: bool = False) -> str:
     """Write ``model`` as an opset-12 ONNX file with inputs/outputs named like the zoo file
     (``input`` -> ``out``, ``aux``; infur/src/gui.rs:229-233 prints exactly these names)."""
     import torch
@@ -119,12 +122,35 @@ def export_onnx(model, path: str, hw=(64, 64)) -> str:
     has_aux = getattr(model, "aux_classifier", None) is not None
     names = ["out", "aux"] if has_aux else ["out"]
     dyn = {n: {0: "batch", 2: "height", 3: "width"} for n in ["input"] + names}
+    example = torch.zeros(1, 3, hw[0], hw[1])
+    if nhwc or uint8_input:
+        # the other input conventions infer_img_pre_proc accepts (predict_onnx.rs:240-262): NHWC layout and / or Uint8 values;
+        # ONNX Conv is NCHW float, so the exported graph starts with Transpose / Cast on the input
+        class Adapter(torch.nn.Module):
+            def __init__(self, net):
+                super().__init__()
+                self.net = net
+
+            def forward(self, x):
+                if nhwc:
+                    x = x.permute(0, 3, 1, 2)
+                if uint8_input:
+                    x = x.float()
+                r = self.net(x)
+                return (r["out"], r["aux"]) if has_aux else r["out"]
+
+        model = Adapter(model).eval()
+        if nhwc:
+            example = example.permute(0, 2, 3, 1).contiguous()
+            dyn["input"] = {0: "batch", 1: "height", 2: "width"}
+        if uint8_input:
+            example = example.to(torch.uint8)
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     tmp = path + ".tmp%d" % os.getpid()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         torch.onnx.export(
-            model, (torch.zeros(1, 3, hw[0], hw[1]),), tmp, opset_version=12, dynamo=False,
+            model, (example,), tmp, opset_version=12, dynamo=False,
             input_names=["input"], output_names=names, dynamic_axes=dyn,
         )
     os.replace(tmp, path)
@@ -136,13 +162,15 @@ def fixture_path(kind: str = "fcn50", seed: int = 0) -> str:
     return os.path.join(root, f"{kind}_seed{seed}.onnx")
 
 
-_LAYERS = {"fcn50": (3, 4, 6, 3), "fcn_tiny": (1, 1, 1, 1)}
+_LAYERS = {"fcn50": (3, 4, 6, 3), "fcn_tiny": (1, 1, 1, 1), "fcn_tiny_u8_nhwc": (1, 1, 1, 1), "fcn_tiny_f32_nhwc": (1, 1, 1, 1)}
 
 
 def ensure_fixture(kind: str = "fcn50", seed: int = 0):
-    """Return (path, torch_model); the ``.onnx`` file is (re)generated when missing."""
-    model = build_fcn(seed=seed, layers=_LAYERS[kind])
+    """Return (path, torch_model); the ``.onnx`` file is (re)generated when missing.  ``*_u8_nhwc`` / ``*_f32_nhwc`` are the
+    tiny network behind a Uint8 / Float NHWC input (the returned torch model is always the plain NCHW float network)."""
+    u8, nhwc = "_u8" in kind, "_nhwc" in kind
+    model = build_fcn(seed=seed, layers=_LAYERS[kind], uint8_input=u8)
     path = fixture_path(kind, seed)
     if not os.path.exists(path):
-        export_onnx(model, path)
+        export_onnx(model, path, nhwc=nhwc, uint8_input=u8)
     return path, model

@@ -23,7 +23,7 @@ PARITY STATUS (see DESIGN.md "Oracle"):
 """
 
 from .scale import scaled_size, scale_nearest, ScaleError, valid_scale  # noqa: F401
-from .preprocess import preprocess_f32, norm_lut  # noqa: F401
+from .preprocess import preprocess_f32, preprocess_u8, norm_lut  # noqa: F401
 from .colorcode import (  # noqa: F401
     COLORS_PALETTE,
     color32_from_rgba_unmultiplied,

@@ -34,3 +34,11 @@ def preprocess_f32(bgr: np.ndarray) -> np.ndarray:
     x = x - MEAN_RGB  # lane -= mean
     x = x * (np.float32(1.0) / STD_RGB)  # lane *= 1/std
     return np.ascontiguousarray(np.transpose(x, (2, 0, 1)))
+
+
+def preprocess_u8(bgr: np.ndarray) -> np.ndarray:
+    """Uint8 models (predict_onnx.rs:117-122 with ColorSeq::BGR, :296-301): the bytes go to ``session.run`` as they are,
+    B,G,R order, only permuted to the model's layout.  Returned as ``[3][H][W]`` f32 (the values the first Cast node
+    of such a model produces), channel 0 = B."""
+    assert bgr.dtype == np.uint8 and bgr.ndim == 3 and bgr.shape[2] == 3
+    return np.ascontiguousarray(np.transpose(bgr.astype(np.float32), (2, 0, 1)))

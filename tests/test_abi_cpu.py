@@ -91,3 +91,19 @@ def test_onnx_input_format_errors(lib, tmp_path):
             torch.onnx.export(M(), (torch.zeros(*shape),), str(f), opset_version=12, dynamo=False, input_names=["input"], output_names=["out"])
         rc, text = describe(lib, str(f))
         assert rc == L.E_MODEL_INPUT_FORMAT and msg in text, text
+
+
+def test_describe_other_input_conventions(lib):
+    """The loader accepts the NHWC / Uint8 input conventions of infer_img_pre_proc (predict_onnx.rs:223-265) and reports
+    the colour order Model::control would pick (:296-301); no GPU needed."""
+    import ctypes as C
+
+    from infur_b200 import synth
+
+    for kind, want in (("fcn_tiny_u8_nhwc", "dtype=Uint8 layout=NHWC color=BGR"), ("fcn_tiny_f32_nhwc", "dtype=Float layout=NHWC color=RGB")):
+        path, _ = synth.ensure_fixture(kind)
+        need = C.c_size_t()
+        lib.infur_b200_onnx_describe(path.encode(), None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        assert lib.infur_b200_onnx_describe(path.encode(), buf, need.value, C.byref(need)) == 0
+        assert want in buf.value.decode()

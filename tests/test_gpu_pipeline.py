@@ -188,3 +188,20 @@ def test_post_fast_path_is_bit_identical(handle, tiny, w, h):
     assert (fast["decoded_rgba"] == full["decoded_rgba"]).all()
     assert (fast["blended_rgba"] == full["blended_rgba"]).all()
     assert len(np.unique(fast["class_map"])) >= 3          # a map with real class boundaries, not a constant
+
+
+@pytest.mark.parametrize("kind,uint8", [("fcn_tiny_u8_nhwc", True), ("fcn_tiny_f32_nhwc", False)])
+def test_other_input_conventions(handle, kind, uint8):
+    """infer_img_pre_proc's other cases (predict_onnx.rs:223-265, 296-306): an NHWC-input model and a Uint8-input model.
+    Float -> RGB + torchvision normalisation; Uint8 -> the raw bytes in B,G,R order.  Same parity bar as the NCHW Float model."""
+    path, model = synth.ensure_fixture(kind)
+    m = P.Model(handle)
+    m.control(path)
+    info = m.get_info()
+    assert info.input0_dtype == ("Uint8" if uint8 else "Float") and info.output_names == ["out", "aux"]
+    frame = synth.synth_frame(320, 240, 5)
+    handle.scale_control(1.0)
+    r = handle.advance(frame, 3)
+    ref = fcn.pipeline(model, frame, 1.0, emulate_fp16=True, uint8_input=uint8)
+    check_against_oracle(r["class_map"], r["decoded_rgba"], ref, 0.995)
+    assert len(np.unique(r["class_map"])) >= 3
