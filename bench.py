@@ -40,7 +40,7 @@ if ROOT not in sys.path:
 W, H = 1920, 1080
 FLOPS_NO_AUX = {(1920, 1080): 2189.025e9}   # 2 x MACs of the 55 convs of the `out` head
 # measured with ncu (profiles/r1_launches_summary.txt): DRAM bytes of all conv launches of one 8-frame step / 51 launches
-CONV_DRAM_BYTES_PER_LAUNCH = 35.24e9 / 51
+CONV_DRAM_BYTES_PER_LAUNCH = 34.76e9 / 51
 
 
 def peaks():
