@@ -205,3 +205,33 @@ def test_other_input_conventions(handle, kind, uint8):
     ref = fcn.pipeline(model, frame, 1.0, emulate_fp16=True, uint8_input=uint8)
     check_against_oracle(r["class_map"], r["decoded_rgba"], ref, 0.995)
     assert len(np.unique(r["class_map"])) >= 3
+
+
+def test_full_size_properties_1080p_batch8(fcn50):
+    """BASELINE.json's measured configuration (8 x 1080p through FCN-ResNet50), checked through size-independent
+    properties, since the CPU oracle needs ~2 s per 1080p frame: (1) a frame's result does not depend on the batch or
+    on the entry point (ring vs synchronous advance, batch 8 vs batch 1: different autotuned kernel variants, same bits);
+    (2) every decoded pixel is exactly the colour-table entry of its (class, alpha); (3) the display buffer is the frame,
+    the blend is `over` of the two; (4) the path is deterministic across repeated submissions; and one frame against the
+    oracle itself."""
+    path, model = fcn50
+    W, H, B = 1920, 1080, 8
+    frames = np.stack([synth.synth_frame(W, H, i) for i in range(B)])
+    with P.Handle(max_batch=B, ring_depth=2, blend=True) as h:
+        h.model_load(path)
+        t1, v1 = h.ring_acquire(B, W, H); v1[...] = frames; h.ring_submit(t1)
+        t2, v2 = h.ring_acquire(B, W, H); v2[...] = frames; h.ring_submit(t2)
+        r1 = h.ring_wait(t1)
+        cm, dec, bl = r1["class_map"].copy(), r1["decoded_rgba"].copy(), r1["blended_rgba"].copy()
+        r2 = h.ring_wait(t2)
+        assert (r2["class_map"] == cm).all() and (r2["decoded_rgba"] == dec).all()            # (4)
+        lut = oracle.color_lut()
+        assert (dec == lut[cm % 20, dec[..., 3]]).all()                                         # (2)
+        for i in (0, 5):
+            one = h.advance(frames[i], i + 1, want=("frame_rgba", "class_map", "decoded_rgba", "blended_rgba"))
+            assert (one["class_map"] == cm[i]).all() and (one["decoded_rgba"] == dec[i]).all()  # (1)
+            assert (one["frame_rgba"] == oracle.frame_rgba(frames[i])).all()                    # (3)
+            assert (bl[i] == oracle.blend_over(dec[i], one["frame_rgba"])).all() and (one["blended_rgba"] == bl[i]).all()
+        assert len(np.unique(cm)) >= 5
+    ref = fcn.pipeline(model, frames[0], 1.0, emulate_fp16=True)
+    check_against_oracle(cm[0], dec[0], ref, 0.995)
