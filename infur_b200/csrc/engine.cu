@@ -349,18 +349,18 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
   Cand best = {po.block_n, po.variant};
   float best_ms = 1e30f;
   Status st;
-  // two interleaved rounds, minimum per candidate: a single short measurement is at the mercy of clock ramps
-  for (int round = 0; round < 2 && st.ok(); ++round) {
+  // three interleaved rounds, minimum per candidate: a single short measurement is at the mercy of clock ramps
+  for (int round = 0; round < 3 && st.ok(); ++round) {
     for (const Cand& c : cands) {
       if (c.bn > d.block_n || d.cout_pad % c.bn != 0 || (c.var == kVarPair && !allow_pair) || (c.var == kVarHalo && !allow_halo)) continue;
       PlanOp trial;
       if (!(st = setup_conv_tc(d, io, trial, c.bn, c.var)).ok()) break;
       cudaError_t e = conv_tc_launch(c.bn, trial.maps, trial.geom, H->num_sms, H->stream);   // warm-up
       cudaEventRecord(e0, H->stream);
-      for (int r = 0; r < 2 && e == cudaSuccess; ++r) e = conv_tc_launch(c.bn, trial.maps, trial.geom, H->num_sms, H->stream);
+      for (int r = 0; r < 3 && e == cudaSuccess; ++r) e = conv_tc_launch(c.bn, trial.maps, trial.geom, H->num_sms, H->stream);
       cudaEventRecord(e1, H->stream);
       if (e == cudaSuccess) e = cudaEventSynchronize(e1);
-      H->launches += 3;
+      H->launches += 4;
       if (e != cudaSuccess) { st = Status::error(INFUR_E_RUNTIME, std::string("autotune: ") + cudaGetErrorString(e)); break; }
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
