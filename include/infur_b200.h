@@ -48,7 +48,8 @@ enum {
                                    * ExactReadError from the decoder process' exit status, exactly as the reference does */
 };
 
-enum { INFUR_RESIZE_NEAREST = 0 /* fr::ResizeAlg::Nearest, processing.rs:189 (the reference's only mode) */ };
+enum { INFUR_RESIZE_NEAREST = 0 /* fr::ResizeAlg::Nearest, processing.rs:189 (the reference's only mode; the default) */,
+       INFUR_RESIZE_BILINEAR = 1 /* opt-in extension (README.md:74 TODO): half-pixel bilinear, un-fused f32, round-half-up to u8 */ };
 enum { INFUR_CONV_TCGEN05 = 0, INFUR_CONV_VALIDATE = 1 /* slow CUDA-core kernel, validation only; never selected implicitly */,
        INFUR_CONV_TCGEN05_PAIR = 2 /* conv_test only: force the CTA-pair (cta_group::2) variant of the tcgen05 kernel */,
        INFUR_CONV_TCGEN05_HALO = 3 /* conv_test only: force the halo-patch variant (3x3 / stride 1 convolutions) */ };
@@ -58,7 +59,7 @@ typedef struct infur_b200_config {
   int32_t device;        /* CUDA ordinal */
   int32_t max_batch;     /* frames per ring slot (default 8) */
   int32_t ring_depth;    /* pinned ring slots (default 3) */
-  int32_t resize_mode;   /* INFUR_RESIZE_NEAREST */
+  int32_t resize_mode;   /* INFUR_RESIZE_NEAREST (parity mode) or INFUR_RESIZE_BILINEAR */
   int32_t compute_aux;   /* also evaluate the `aux` head (the reference's caller discards it, app.rs:116) */
   int32_t blend;         /* also produce blended_rgba (new feature; gui.rs:324-329 "todo: blend somehow?") */
   int32_t conv_impl;     /* INFUR_CONV_TCGEN05 */

@@ -27,6 +27,8 @@ E_UNSUPPORTED = 11
 E_TICKET = 12
 E_STREAM_END = 13
 
+RESIZE_NEAREST = 0
+RESIZE_BILINEAR = 1
 CONV_TCGEN05 = 0
 CONV_VALIDATE = 1
 CONV_TCGEN05_PAIR = 2   # conv_test only

@@ -15,6 +15,7 @@ namespace infur {
 Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool skip_weights, std::unique_ptr<DeviceModel>& out);
 Status get_plan(infur_b200_handle* H, int n, int w, int h, Plan** out);
 Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const OutPtrs& o, cudaStream_t s, float* op_ms, cudaEvent_t* evs);
+void fill_pre_args(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, PreArgs& pa);
 Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* d, const uint16_t* x, const uint16_t* wgt, const float* bias,
                       const uint16_t* residual, uint16_t* y, float* y_f32, float* elapsed_ms);
 }  // namespace infur
@@ -56,7 +57,7 @@ int32_t infur_b200_create(const infur_b200_config* cfg, infur_b200_handle** out)
     if (cfg->struct_size != sizeof(infur_b200_config)) return fail(nullptr, INFUR_E_INVALID_ARG, "create: config struct_size mismatch");
     c = *cfg;
   }
-  if (c.resize_mode != INFUR_RESIZE_NEAREST) return fail(nullptr, INFUR_E_UNSUPPORTED, "create: only INFUR_RESIZE_NEAREST (the reference's mode) is implemented");
+  if (c.resize_mode != INFUR_RESIZE_NEAREST && c.resize_mode != INFUR_RESIZE_BILINEAR) return fail(nullptr, INFUR_E_INVALID_ARG, "create: unknown resize_mode");
   if (c.conv_impl != INFUR_CONV_TCGEN05 && c.conv_impl != INFUR_CONV_VALIDATE) return fail(nullptr, INFUR_E_INVALID_ARG, "create: unknown conv_impl");
   if (c.use_cuda_graph != 0) return fail(nullptr, INFUR_E_UNSUPPORTED, "create: use_cuda_graph is reserved and must be 0");
   if (c.max_batch < 1 || c.max_batch > 64 || c.ring_depth < 1 || c.ring_depth > 16) return fail(nullptr, INFUR_E_INVALID_ARG, "create: max_batch must be 1..64, ring_depth 1..16");
@@ -473,26 +474,21 @@ int32_t infur_b200_scale_advance(infur_b200_handle* h, const uint8_t* bgr, uint3
   if (!bgr) return fail(h, INFUR_E_INVALID_ARG, "scale_advance: bgr is NULL");
   if (h->factor == 1.0f) { memcpy(out_bgr, bgr, need); return INFUR_OK; }   // deep copy (processing.rs:238-241)
   if (ow > (1u << 20) || oh > (1u << 20)) return fail(h, INFUR_E_UNSUPPORTED, "scale_advance: output larger than 2^20 per side");
-  std::vector<int32_t> xm, ym;
-  build_nearest_map((int)w, (int)ow, xm); build_nearest_map((int)hgt, (int)oh, ym);
-  uint8_t *d_in = nullptr, *d_out = nullptr; int32_t *d_x = nullptr, *d_y = nullptr;
-  int32_t rc = INFUR_OK;
-  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(d_x); cudaFree(d_y); };
-  if (cudaMalloc(&d_in, (size_t)w * hgt * 3) != cudaSuccess || cudaMalloc(&d_out, need) != cudaSuccess || cudaMalloc(&d_x, ow * 4) != cudaSuccess ||
-      cudaMalloc(&d_y, oh * 4) != cudaSuccess) { cleanup(); return fail(h, INFUR_E_RUNTIME, "scale_advance: cudaMalloc failed"); }
-  cudaMemcpyAsync(d_in, bgr, (size_t)w * hgt * 3, cudaMemcpyHostToDevice, h->stream);
-  cudaMemcpyAsync(d_x, xm.data(), ow * 4, cudaMemcpyHostToDevice, h->stream);
-  cudaMemcpyAsync(d_y, ym.data(), oh * 4, cudaMemcpyHostToDevice, h->stream);
-  PreArgs pa; memset(&pa, 0, sizeof(pa));
-  pa.src = d_in; pa.n = 1; pa.h = (int)hgt; pa.w = (int)w; pa.oh = (int)oh; pa.ow = (int)ow; pa.xmap = d_x; pa.ymap = d_y; pa.lut_h = h->d_lut_h;
-  pa.scaled_bgr = d_out;
+  // the plan of this (size, factor) owns the resampling tables (nearest maps or bilinear taps) and the staging buffers
+  Plan* pp = nullptr;
+  Status st = get_plan(h, 1, (int)w, (int)hgt, &pp);
+  if (!st.ok()) return fail(h, st);
+  Plan& p = *pp;
+  API_CU(h, cudaMemcpyAsync(p.d_in, bgr, (size_t)w * hgt * 3, cudaMemcpyHostToDevice, h->stream));
+  PreArgs pa;
+  fill_pre_args(h, p, p.d_in, pa);
+  pa.stem_in = nullptr;   // Scale alone: no normalised copy for the network
   cudaError_t e = launch_pre(pa, h->stream);
   h->launches++;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out_bgr, d_out, need, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_bgr, p.scaled, need, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  if (e != cudaSuccess) rc = fail(h, INFUR_E_RUNTIME, std::string("scale_advance: ") + cudaGetErrorString(e));
-  cleanup();
-  return rc;
+  if (e != cudaSuccess) return fail(h, INFUR_E_RUNTIME, std::string("scale_advance: ") + cudaGetErrorString(e));
+  return INFUR_OK;
 }
 
 int32_t infur_b200_model_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* logits_f32, size_t logits_cap,

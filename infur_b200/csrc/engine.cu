@@ -428,9 +428,21 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
   const size_t in_bytes = (size_t)n * w * h * 3, out_px = (size_t)n * p.ow * p.oh;
   if (!(st = dev_alloc(p, &p.d_in, in_bytes)).ok()) return st;
   if (!unit) {
-    std::vector<int32_t> xm, ym;
-    build_nearest_map(w, p.ow, xm); build_nearest_map(h, p.oh, ym);
-    if (!(st = dev_upload(p, &p.xmap, xm)).ok() || !(st = dev_upload(p, &p.ymap, ym)).ok()) return st;
+    if (H->cfg.resize_mode == INFUR_RESIZE_BILINEAR) {
+      std::vector<int32_t> i0, i1; std::vector<float> l0, l1;
+      build_bilinear_table(w, p.ow, i0, i1, l0, l1);
+      if (!(st = dev_upload(p, &p.sbx0, i0)).ok() || !(st = dev_upload(p, &p.sbx1, i1)).ok() || !(st = dev_upload(p, &p.sblx0, l0)).ok() ||
+          !(st = dev_upload(p, &p.sblx1, l1)).ok())
+        return st;
+      build_bilinear_table(h, p.oh, i0, i1, l0, l1);
+      if (!(st = dev_upload(p, &p.sby0, i0)).ok() || !(st = dev_upload(p, &p.sby1, i1)).ok() || !(st = dev_upload(p, &p.sbly0, l0)).ok() ||
+          !(st = dev_upload(p, &p.sbly1, l1)).ok())
+        return st;
+    } else {
+      std::vector<int32_t> xm, ym;
+      build_nearest_map(w, p.ow, xm); build_nearest_map(h, p.oh, ym);
+      if (!(st = dev_upload(p, &p.xmap, xm)).ok() || !(st = dev_upload(p, &p.ymap, ym)).ok()) return st;
+    }
     if (!(st = dev_alloc(p, &p.scaled, out_px * 3)).ok()) return st;
   }
   if (!(st = dev_alloc(p, &p.d_frame_rgba, out_px)).ok()) return st;
@@ -587,20 +599,27 @@ Status get_plan(infur_b200_handle* H, int n, int w, int h, Plan** out) {
 // ------------------------------------------------------------------------------------------------
 // Forward: Scale -> Model -> ColorCode on device buffers.
 
+// Scale (+ normalise) arguments of a plan: nearest maps or bilinear taps, the model's input convention.
+void fill_pre_args(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, PreArgs& pa) {
+  memset(&pa, 0, sizeof(pa));
+  const bool unit = p.factor == 1.0f;
+  pa.src = d_bgr; pa.n = p.n; pa.h = p.h; pa.w = p.w; pa.oh = p.oh; pa.ow = p.ow;
+  pa.xmap = p.xmap; pa.ymap = p.ymap;
+  pa.bx0 = p.sbx0; pa.bx1 = p.sbx1; pa.blx0 = p.sblx0; pa.blx1 = p.sblx1; pa.by0 = p.sby0; pa.by1 = p.sby1; pa.bly0 = p.sbly0; pa.bly1 = p.sbly1;
+  // Float models: RGB + torchvision normalisation; Uint8 models: the raw bytes in B,G,R order (predict_onnx.rs:103-137,296-306)
+  const bool u8_model = p.has_model && !H->model->lm.io.float_input;
+  pa.lut_h = u8_model ? H->d_lut_u8 : H->d_lut_h; pa.bgr_order = u8_model ? 1 : 0;
+  pa.stem_in = p.has_model ? p.stem_in : nullptr;
+  pa.scaled_bgr = unit ? nullptr : p.scaled;
+}
+
 Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const OutPtrs& o, cudaStream_t s, float* op_ms = nullptr,
                    cudaEvent_t* evs = nullptr) {
   const size_t out_px = (size_t)p.n * p.ow * p.oh;
   if (out_px == 0) return Status();
   const bool unit = p.factor == 1.0f;
   PreArgs pa;
-  memset(&pa, 0, sizeof(pa));
-  pa.src = d_bgr; pa.n = p.n; pa.h = p.h; pa.w = p.w; pa.oh = p.oh; pa.ow = p.ow;
-  pa.xmap = p.xmap; pa.ymap = p.ymap;
-  // Float models: RGB + torchvision normalisation; Uint8 models: the raw bytes in B,G,R order (predict_onnx.rs:103-137,296-306)
-  const bool u8_model = p.has_model && !H->model->lm.io.float_input;
-  pa.lut_h = u8_model ? H->d_lut_u8 : H->d_lut_h; pa.bgr_order = u8_model ? 1 : 0;
-  pa.stem_in = p.has_model ? p.stem_in : nullptr;
-  pa.scaled_bgr = unit ? nullptr : p.scaled;
+  fill_pre_args(H, p, d_bgr, pa);
   const uint8_t* frame = unit ? d_bgr : p.scaled;
   int ei = 0;
   if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));

@@ -79,6 +79,8 @@ struct Plan {
   std::vector<void*> owned;      // device allocations
   // device buffers
   int32_t *xmap = nullptr, *ymap = nullptr;
+  int32_t *sbx0 = nullptr, *sbx1 = nullptr, *sby0 = nullptr, *sby1 = nullptr;   // bilinear Scale taps
+  float *sblx0 = nullptr, *sblx1 = nullptr, *sbly0 = nullptr, *sbly1 = nullptr;
   int32_t *y0 = nullptr, *y1 = nullptr, *x0 = nullptr, *x1 = nullptr;
   float *ly0 = nullptr, *ly1 = nullptr, *lx0 = nullptr, *lx1 = nullptr;
   __half* stem_in = nullptr;

@@ -22,10 +22,29 @@ __global__ void __launch_bounds__(256) pre_generic_kernel(PreArgs a, int stem_pi
   const int y = blockIdx.y;
   const int img = blockIdx.z;
   if (x >= a.ow) return;
-  const int sx = a.xmap ? a.xmap[x] : x;
-  const int sy = a.ymap ? a.ymap[y] : y;
-  const uint8_t* p = a.src + (((size_t)img * a.h + sy) * a.w + sx) * 3;
-  const uint8_t b = p[0], g = p[1], r = p[2];
+  uint8_t b, g, r;
+  if (a.bx0) {
+    // opt-in bilinear Scale: ly0*(lx0*a + lx1*b) + ly1*(lx0*c + lx1*d), un-fused f32 in this order, u8 = floor(v + 0.5)
+    const int x0 = a.bx0[x], x1 = a.bx1[x], y0 = a.by0[y], y1 = a.by1[y];
+    const float lx0 = a.blx0[x], lx1 = a.blx1[x], ly0 = a.bly0[y], ly1 = a.bly1[y];
+    const uint8_t* base = a.src + (size_t)img * a.h * a.w * 3;
+    const uint8_t* p00 = base + ((size_t)y0 * a.w + x0) * 3; const uint8_t* p01 = base + ((size_t)y0 * a.w + x1) * 3;
+    const uint8_t* p10 = base + ((size_t)y1 * a.w + x0) * 3; const uint8_t* p11 = base + ((size_t)y1 * a.w + x1) * 3;
+    uint8_t o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float top = __fadd_rn(__fmul_rn(lx0, (float)p00[c]), __fmul_rn(lx1, (float)p01[c]));
+      const float bot = __fadd_rn(__fmul_rn(lx0, (float)p10[c]), __fmul_rn(lx1, (float)p11[c]));
+      const float v = floorf(__fadd_rn(__fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot)), 0.5f));
+      o[c] = (uint8_t)fminf(fmaxf(v, 0.f), 255.f);
+    }
+    b = o[0]; g = o[1]; r = o[2];
+  } else {
+    const int sx = a.xmap ? a.xmap[x] : x;
+    const int sy = a.ymap ? a.ymap[y] : y;
+    const uint8_t* p = a.src + (((size_t)img * a.h + sy) * a.w + sx) * 3;
+    b = p[0]; g = p[1]; r = p[2];
+  }
   if (a.scaled_bgr) {
     uint8_t* q = a.scaled_bgr + (((size_t)img * a.oh + y) * a.ow + x) * 3;
     q[0] = b; q[1] = g; q[2] = r;
@@ -425,7 +444,7 @@ __global__ void __launch_bounds__(128) direct_conv_kernel(DirectConvArgs a) {
 
 cudaError_t launch_pre(const PreArgs& a, cudaStream_t s) {
   const int pitch = stem_pitch_px(a.ow), rows = stem_rows(a.oh);
-  const bool unit = a.xmap == nullptr && a.ymap == nullptr && a.scaled_bgr == nullptr && a.stem_in != nullptr && (a.w % 4) == 0 &&
+  const bool unit = a.xmap == nullptr && a.ymap == nullptr && a.bx0 == nullptr && a.scaled_bgr == nullptr && a.stem_in != nullptr && (a.w % 4) == 0 &&
                     a.oh == a.h && a.ow == a.w;
   if (unit) {
     dim3 grid((a.w / 4 + 255) / 256, a.h, a.n);

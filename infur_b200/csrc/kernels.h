@@ -22,6 +22,9 @@ struct PreArgs {
   int oh, ow;            // size after Scale
   const int32_t* xmap;   // [ow] nearest source column (nullptr = identity)
   const int32_t* ymap;   // [oh]
+  // bilinear mode (all eight non-null): taps and weights per output column / row
+  const int32_t* bx0; const int32_t* bx1; const float* blx0; const float* blx1;
+  const int32_t* by0; const int32_t* by1; const float* bly0; const float* bly1;
   const __half* lut_h;   // [3][256] fp16, one table per network input channel
   int bgr_order;         // 0: network channels = (R, G, B) of the pixel (Float models); 1: (B, G, R) as stored (Uint8 models)
   __half* stem_in;       // [n][stem_rows(oh)][stem_pitch_px(ow)][4] fp16, or nullptr

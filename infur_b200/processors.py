@@ -109,12 +109,13 @@ class Handle:
     """Owner of one ``infur_b200_handle`` (one GPU, one owner thread)."""
 
     def __init__(self, device: int = 0, max_batch: int = 8, ring_depth: int = 3, compute_aux: bool = False, blend: bool = False,
-                 conv_impl: int = L.CONV_TCGEN05):
+                 conv_impl: int = L.CONV_TCGEN05, resize_mode: int = L.RESIZE_NEAREST):
         self.lib = L.load()
         cfg = L.Config()
         self.lib.infur_b200_default_config(C.byref(cfg))
         cfg.device, cfg.max_batch, cfg.ring_depth = device, max_batch, ring_depth
         cfg.compute_aux, cfg.blend, cfg.conv_impl = int(compute_aux), int(blend), conv_impl
+        cfg.resize_mode = resize_mode
         self.cfg = cfg
         self._h = C.c_void_p()
         rc = self.lib.infur_b200_create(C.byref(cfg), C.byref(self._h))

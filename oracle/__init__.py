@@ -22,7 +22,7 @@ PARITY STATUS (see DESIGN.md "Oracle"):
     function cites the reference call site it stands in for.
 """
 
-from .scale import scaled_size, scale_nearest, ScaleError, valid_scale  # noqa: F401
+from .scale import scaled_size, scale_nearest, scale_bilinear, ScaleError, valid_scale  # noqa: F401
 from .preprocess import preprocess_f32, preprocess_u8, norm_lut  # noqa: F401
 from .colorcode import (  # noqa: F401
     COLORS_PALETTE,

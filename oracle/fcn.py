@@ -21,7 +21,7 @@ from torch import nn
 
 from .colorcode import color_code_image, frame_rgba
 from .preprocess import preprocess_f32, preprocess_u8
-from .scale import scale_nearest
+from .scale import scale_bilinear, scale_nearest
 from .upsample import upsample_bilinear
 
 
@@ -93,10 +93,10 @@ def forward_lowres_fp16emu(model, x_nchw: np.ndarray, head: str = "out") -> np.n
     return y.numpy()
 
 
-def pipeline(model, bgr: np.ndarray, factor=1.0, emulate_fp16: bool = False, uint8_input: bool = False) -> dict:
+def pipeline(model, bgr: np.ndarray, factor=1.0, emulate_fp16: bool = False, uint8_input: bool = False, bilinear: bool = False) -> dict:
     """Whole path as sequenced by ``ProcessingApp::advance`` (infur/src/app.rs:107-153):
     Scale -> Model (``out`` head only, :116) -> ColorCode, plus the display buffer (:132-144)."""
-    scaled = scale_nearest(bgr, factor)
+    scaled = (scale_bilinear if bilinear else scale_nearest)(bgr, factor)   # bilinear: opt-in extension, not a reference mode
     x = (preprocess_u8(scaled) if uint8_input else preprocess_f32(scaled))[None]   # Uint8 models: raw bytes, B,G,R (predict_onnx.rs:296-301)
     fwd = forward_lowres_fp16emu if emulate_fp16 else forward_lowres
     low = fwd(model, x)[0]

@@ -78,3 +78,31 @@ def scale_nearest(img: np.ndarray, factor) -> np.ndarray:
     ys = nearest_indices(h, nh)
     xs = nearest_indices(w, nw)
     return np.ascontiguousarray(img[ys][:, xs])
+
+
+def scale_bilinear(img: np.ndarray, factor) -> np.ndarray:
+    """Opt-in extension, NOT a reference mode (the reference's only mode is Nearest, processing.rs:189; "bilinear" is an
+    open TODO in its README:74 and the mode BASELINE.json's north_star names).  Defined here: same size rule and error
+    cases as ``scale_nearest``; half-pixel-centre bilinear taps (``oracle.upsample.bilinear_tables``: ``src = s*(dst+0.5)-0.5``
+    clamped, f32), value ``ly0*(lx0*a + lx1*b) + ly1*(lx0*c + lx1*d)`` in un-fused f32 in exactly this order, then
+    ``u8 = floor(v + 0.5)`` clamped to 0..255.  No antialiasing prefilter (like cv2 INTER_LINEAR)."""
+    from .upsample import bilinear_tables
+
+    f = valid_scale(factor)
+    assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3
+    h, w = img.shape[:2]
+    if f == np.float32(1.0):
+        return img.copy()
+    if w == 0 or h == 0:
+        raise ScaleError("ZeroSizeIn", "scaling from 0-sized input")
+    nw, nh = scaled_size(w, h, f)
+    if nw == 0 or nh == 0:
+        raise ScaleError("ZeroSizeOut", "scaling to 0-sized output")
+    y0, y1, ly0, ly1 = bilinear_tables(h, nh)
+    x0, x1, lx0, lx1 = bilinear_tables(w, nw)
+    x = img.astype(np.float32)
+    lx0 = lx0[None, :, None]; lx1 = lx1[None, :, None]
+    top = (lx0 * x[y0][:, x0]).astype(np.float32) + (lx1 * x[y0][:, x1]).astype(np.float32)
+    bot = (lx0 * x[y1][:, x0]).astype(np.float32) + (lx1 * x[y1][:, x1]).astype(np.float32)
+    v = (ly0[:, None, None] * top).astype(np.float32) + (ly1[:, None, None] * bot).astype(np.float32)
+    return np.clip(np.floor(v + np.float32(0.5)), 0, 255).astype(np.uint8)

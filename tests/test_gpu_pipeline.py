@@ -235,3 +235,16 @@ def test_full_size_properties_1080p_batch8(fcn50):
         assert len(np.unique(cm)) >= 5
     ref = fcn.pipeline(model, frames[0], 1.0, emulate_fp16=True)
     check_against_oracle(cm[0], dec[0], ref, 0.995)
+
+
+def test_bilinear_scale_pipeline(tiny):
+    """The fused path with the opt-in bilinear Scale against the oracle pipeline using the same Scale definition."""
+    path, model = tiny
+    frame = synth.synth_frame(640, 480, 6)
+    with P.Handle(max_batch=1, resize_mode=L.RESIZE_BILINEAR) as h:
+        h.model_load(path)
+        h.scale_control(0.5)
+        r = h.advance(frame, 2, want=("scaled_bgr", "class_map", "decoded_rgba"))
+    ref = fcn.pipeline(model, frame, 0.5, emulate_fp16=True, bilinear=True)
+    assert (r["scaled_bgr"] == ref["scaled_bgr"]).all()
+    check_against_oracle(r["class_map"], r["decoded_rgba"], ref, 0.995)

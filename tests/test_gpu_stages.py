@@ -131,3 +131,18 @@ def test_golden_stages(handle):
     assert (handle.preprocess(g["scaled_half"]) == g["pre_half"]).all()
     r = handle.upsample_color(g["lowres"], 48, 64, want_logits=True)
     assert (r["logits"] == g["upsampled"]).all() and (r["class_map"] == g["class_map"]).all() and (r["decoded_rgba"] == g["decoded"]).all()
+
+
+@pytest.mark.parametrize("w,h,f", [(640, 480, 0.5), (127, 93, 0.37), (320, 240, 2.0), (200, 136, 0.73)])
+def test_bilinear_scale_extension_exact(w, h, f):
+    """INFUR_RESIZE_BILINEAR (opt-in; the reference only has Nearest): bit-exact against its oracle definition, alone and
+    as the first stage of the fused path."""
+    from infur_b200 import _lib as L
+
+    frame = synth.synth_frame(w, h, 2)
+    with P.Handle(max_batch=1, resize_mode=L.RESIZE_BILINEAR) as hd:
+        hd.scale_control(f)
+        ref = oracle.scale_bilinear(frame, f)
+        assert (hd.scale_advance(frame) == ref).all()
+        r = hd.advance(frame, 1, want=("scaled_bgr", "frame_rgba"))
+        assert (r["scaled_bgr"] == ref).all() and (r["frame_rgba"] == oracle.frame_rgba(ref)).all()

@@ -153,3 +153,22 @@ def test_golden_vectors():
     assert (up == g["upsampled"]).all()
     k, rgba = oracle.color_code_image(up)
     assert (k == g["class_map"]).all() and (rgba == g["decoded"]).all()
+
+
+def test_bilinear_scale_extension_tracks_cv2():
+    """The opt-in bilinear Scale (not a reference mode) is the plain half-pixel bilinear: within 1 grey level of
+    cv2.INTER_LINEAR (which rounds differently: fixed-point weights) for up- and down-scaling, same sizes/errors as nearest."""
+    import cv2
+
+    from infur_b200 import synth
+
+    img = synth.synth_frame(127, 93, 1)
+    for f in (0.5, 0.37, 2.0, 1.5):
+        out = oracle.scale_bilinear(img, f)
+        nw, nh = oracle.scaled_size(127, 93, f)
+        assert out.shape == (nh, nw, 3)
+        ref = cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR)
+        assert np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= 1
+    assert (oracle.scale_bilinear(img, 1.0) == img).all()
+    with pytest.raises(oracle.ScaleError):
+        oracle.scale_bilinear(np.zeros((10, 0, 3), np.uint8), 0.5)
