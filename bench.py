@@ -242,12 +242,17 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         sampler.start()
     l0 = h.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profiled = os.environ.get("INFUR_BENCH_PROFILE") == "1"   # ncu --profile-from-start off: only the timed region is captured
+    if profiled:
+        torch.cuda.profiler.start()
     e0.record(stream)
     for i in range(args.steps):
         step_device(i)
     e1.record(stream)
     stream.synchronize()
     torch.cuda.synchronize()
+    if profiled:
+        torch.cuda.profiler.stop()
     launches = h.launch_count() - l0
     barrier()
     ms = e0.elapsed_time(e1)
