@@ -248,3 +248,18 @@ def test_bilinear_scale_pipeline(tiny):
     ref = fcn.pipeline(model, frame, 0.5, emulate_fp16=True, bilinear=True)
     assert (r["scaled_bgr"] == ref["scaled_bgr"]).all()
     check_against_oracle(r["class_map"], r["decoded_rgba"], ref, 0.995)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 5), (16, 16), (33, 17), (9, 130)])
+def test_tiny_and_ragged_frames(handle, tiny, w, h):
+    """Frames far smaller than one 128-pixel tile, odd sizes, extreme aspect ratios: every TMA box overhangs the tensors."""
+    path, model = tiny
+    handle.model_load(path)
+    handle.scale_control(1.0)
+    frame = synth.synth_frame(w, h, 4)
+    r = handle.advance(frame, 1, want=("frame_rgba", "class_map", "decoded_rgba", "logits_f32"))
+    ref = fcn.pipeline(model, frame, 1.0, emulate_fp16=True)
+    assert r["class_map"].shape == (h, w) and (r["frame_rgba"] == ref["frame_rgba"]).all()
+    assert np.abs(r["logits_f32"] - ref["logits"]).max() < 0.05 * max(1.0, np.abs(ref["logits"]).max())
+    lut = oracle.color_lut()
+    assert (r["decoded_rgba"] == lut[r["class_map"] % 20, r["decoded_rgba"][..., 3]]).all()
