@@ -585,19 +585,32 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
 // row reads back what TMA wrote -- verified on hardware with the descriptor's base-offset field left 0 (setting it to
 // (start >> 7) & 7 gives wrong results).  Weights stream through their own ring, one (tap, chunk) tile per stage.
 constexpr int kHaloPatchPx = 16;                    // patch pitch in pixels: 8 + 2d <= 16, and a multiple of the 8-row swizzle atom
-constexpr int kHaloPatchBytesMax = kHaloPatchPx * 24 * 128;   // d = 4: 24 rows -> 48 KB
 constexpr int kHaloMaxBStages = 12;
+constexpr int kHaloMaxPatches = 4;
+
+// smem plan of the halo kernel for dilation d and N tile bn: up to 3 patch buffers (the patch of the NEXT tiles must be
+// in flight while this one is consumed: a 64 -> 64 layer spends only ~0.6 us of MMAs per patch), then the weight ring,
+// then the epilogue chunk buffers (4, or 2 when that leaves fewer than 4 weight stages).
+struct HaloPlan { int patch_bytes, patches, b_stages, epi_bufs, smem_bytes; };
+__host__ __device__ constexpr HaloPlan halo_plan(int d, int bn) {
+  HaloPlan p{};
+  p.patch_bytes = kHaloPatchPx * (16 + 2 * d) * 128;
+  p.patches = 3;
+  const int b_bytes = bn * kBlockK * 2;
+  p.epi_bufs = 4;
+  int rest = kSmemLimit - 1024 - kBarBytes - p.patches * p.patch_bytes - p.epi_bufs * kEpiBufBytes;
+  if (rest / b_bytes < 4) { p.epi_bufs = 2; rest += 2 * kEpiBufBytes; }
+  if (rest / b_bytes < 3) { p.patches = 2; rest += p.patch_bytes; }
+  p.b_stages = rest / b_bytes > kHaloMaxBStages ? kHaloMaxBStages : rest / b_bytes;
+  p.smem_bytes = p.patches * p.patch_bytes + p.b_stages * b_bytes + p.epi_bufs * kEpiBufBytes + 1024 + kBarBytes;
+  return p;
+}
 
 template <int BLOCK_N>
 struct HaloCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kAcc = BLOCK_N >= 256 ? 2 : 4;
   static constexpr int kTmemCols = kAcc * BLOCK_N;
-  __host__ __device__ static constexpr int b_stages() {
-    int s = (kSmemLimit - 1024 - kBarBytes - 2 * kHaloPatchBytesMax - 4 * kEpiBufBytes) / kBBytes;
-    return s > kHaloMaxBStages ? kHaloMaxBStages : s;
-  }
-  __host__ __device__ static constexpr int smem_bytes() { return 2 * kHaloPatchBytesMax + b_stages() * kBBytes + 4 * kEpiBufBytes + 1024 + kBarBytes; }
 };
 
 template <int BLOCK_N>
@@ -605,35 +618,36 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   using C = HaloCfg<BLOCK_N>;
   constexpr int ACC = C::kAcc;
-  constexpr int BS = C::b_stages();
+  const int d = g.halo_dil;
+  const HaloPlan hp = halo_plan(d, BLOCK_N);
+  const int BS = hp.b_stages, NP = hp.patches;
+  const uint32_t patch_bytes = (uint32_t)hp.patch_bytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_base = smem_base + 2 * kHaloPatchBytesMax;
+  const uint32_t b_base = smem_base + NP * patch_bytes;             // patch sizes are multiples of 2 KB: 1024-aligned
   const uint32_t epi_base = b_base + BS * C::kBBytes;
-  const uint32_t bar_base = epi_base + 4 * kEpiBufBytes;
-  // barriers: b_full[12], b_empty[12], a_full[2], a_empty[2], tmem_full[4], tmem_empty[4], epilogue (res, ready, free) x 4
+  const uint32_t bar_base = epi_base + hp.epi_bufs * kEpiBufBytes;
+  // barriers: b_full[12], b_empty[12], a_full[4], a_empty[4], tmem_full[4], tmem_empty[4], epilogue (res, ready, free) x 4
   auto bfull_bar = [&](int s) { return bar_base + 8u * s; };
   auto bempty_bar = [&](int s) { return bar_base + 8u * (kHaloMaxBStages + s); };
   auto afull_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + s); };
-  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + 2 + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + 4 + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + 4 + kMaxAcc + s); };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + kHaloMaxPatches + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + 2 * kHaloMaxPatches + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kHaloMaxBStages + 2 * kHaloMaxPatches + kMaxAcc + s); };
   EpiBars eb;
-  eb.res = bar_base + 8u * (2 * kHaloMaxBStages + 4 + 2 * kMaxAcc);
+  eb.res = bar_base + 8u * (2 * kHaloMaxBStages + 2 * kHaloMaxPatches + 2 * kMaxAcc);
   eb.ready = eb.res + 8u * kMaxEpiBufs;
   eb.free_ = eb.ready + 8u * kMaxEpiBufs;
   const uint32_t tmem_ptr_addr = eb.free_ + 8u * kMaxEpiBufs;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int d = g.halo_dil;
-  const uint32_t patch_bytes = (uint32_t)(kHaloPatchPx * (16 + 2 * d) * 128);
   const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
 
   if (warp == 0 && ptx::elect_one()) { ptx::prefetch_tmap(&maps.a[0]); ptx::prefetch_tmap(&maps.b); ptx::prefetch_tmap(&maps.c); }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < BS; ++s) { ptx::mbar_init(bfull_bar(s), 1); ptx::mbar_init(bempty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(afull_bar(s), 1); ptx::mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < NP; ++s) { ptx::mbar_init(afull_bar(s), 1); ptx::mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < ACC; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), kEpiWarps); }
     for (int s = 0; s < kMaxEpiBufs; ++s) {
       ptx::mbar_init(eb.res + 8u * s, 1);
@@ -661,10 +675,10 @@ conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
       for (int tile = sched.tile(0); tile >= 0; tile = sched.tile(++it)) {
         const TileCoord tc = decode_tile(g, tile);
         for (int cc = 0; cc < g.cchunks; ++cc, ++au) {
-          const int ab = au & 1;
-          ptx::mbar_wait(aempty_bar(ab), ((uint32_t)(au >> 1) & 1u) ^ 1u);
+          const int ab = au % NP;
+          ptx::mbar_wait(aempty_bar(ab), ((uint32_t)(au / NP) & 1u) ^ 1u);
           ptx::mbar_expect_tx(afull_bar(ab), patch_bytes);
-          ptx::tma_load_4d(smem_base + ab * kHaloPatchBytesMax, &maps.a[0], afull_bar(ab), cc * kBlockK, tc.ox0 - d, tc.oy0 - d, tc.img);
+          ptx::tma_load_4d(smem_base + ab * patch_bytes, &maps.a[0], afull_bar(ab), cc * kBlockK, tc.ox0 - d, tc.oy0 - d, tc.img);
           for (int tap = 0; tap < 9; ++tap) {
             ptx::mbar_wait(bempty_bar(bs), bphase ^ 1u);
             ptx::mbar_expect_tx(bfull_bar(bs), (uint32_t)C::kBBytes);
@@ -688,9 +702,9 @@ conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
         for (int cc = 0; cc < g.cchunks; ++cc, ++au) {
-          const int ab = au & 1;
-          ptx::mbar_wait(afull_bar(ab), (uint32_t)(au >> 1) & 1u);
-          const uint32_t patch = smem_base + ab * kHaloPatchBytesMax;
+          const int ab = au % NP;
+          ptx::mbar_wait(afull_bar(ab), (uint32_t)(au / NP) & 1u);
+          const uint32_t patch = smem_base + ab * patch_bytes;
           for (int tap = 0; tap < 9; ++tap) {
             ptx::mbar_wait(bfull_bar(bs), bphase);
             ptx::tc_fence_after();
@@ -710,9 +724,13 @@ conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
       }
     }
   } else if (warp == kDmaWarp) {
-    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false, Sched1, 4>(maps, g, sched, eb, epi_base);
+    if (ptx::elect_one()) {
+      if (hp.epi_bufs == 4) epilogue_dma<BLOCK_N, false, Sched1, 4>(maps, g, sched, eb, epi_base);
+      else epilogue_dma<BLOCK_N, false, Sched1, 2>(maps, g, sched, eb, epi_base);
+    }
   } else if (warp >= kEpiWarp0) {
-    epilogue_tma<BLOCK_N, ACC, false, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
+    if (hp.epi_bufs == 2) epilogue_tma<BLOCK_N, ACC, false, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
+    else epilogue_tma<BLOCK_N, ACC, false, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
   }
 
   ptx::tc_fence_before();
@@ -873,9 +891,9 @@ cudaError_t conv_tc_init() {
   if ((e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::smem_bytes())) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<128>::smem_bytes())) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<256>::smem_bytes())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   return cudaSuccess;
 }
@@ -893,9 +911,9 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     if (grid <= 0) return cudaSuccess;
     if (g.store_mode != 1 || g.bw_log2 != 3 || g.main_taps != 9 || g.num_taps != 9) return cudaErrorInvalidValue;
     switch (block_n) {
-      case 64: conv_halo_kernel<64><<<grid, kThreads, HaloCfg<64>::smem_bytes(), stream>>>(maps, g); break;
-      case 128: conv_halo_kernel<128><<<grid, kThreads, HaloCfg<128>::smem_bytes(), stream>>>(maps, g); break;
-      case 256: conv_halo_kernel<256><<<grid, kThreads, HaloCfg<256>::smem_bytes(), stream>>>(maps, g); break;
+      case 64: conv_halo_kernel<64><<<grid, kThreads, halo_plan(g.halo_dil, 64).smem_bytes, stream>>>(maps, g); break;
+      case 128: conv_halo_kernel<128><<<grid, kThreads, halo_plan(g.halo_dil, 128).smem_bytes, stream>>>(maps, g); break;
+      case 256: conv_halo_kernel<256><<<grid, kThreads, halo_plan(g.halo_dil, 256).smem_bytes, stream>>>(maps, g); break;
       default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
