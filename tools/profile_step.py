@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--steps", type=int, default=0)
     ap.add_argument("--kind", default="fcn50")
+    ap.add_argument("--scale", type=float, default=1.0, help="Scale factor (configs[4]: 3840x2160 at 0.5 vs 1.0)")
     ap.add_argument("--cuda-profiler", action="store_true", help="bracket the back-to-back steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     a = ap.parse_args()
     import torch
@@ -38,10 +39,12 @@ def main():
     frames = np.stack([synth.synth_frame(W, H, i) for i in range(min(B, 2))])
     frames = np.ascontiguousarray(np.resize(frames, (B, H, W, 3)))
     d = torch.from_numpy(frames).cuda()
-    d_class = torch.empty((B, H, W), dtype=torch.uint8, device="cuda")
-    d_rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device="cuda")
+    OW, OH = (W, H) if a.scale == 1.0 else (int(np.float32(W) * np.float32(a.scale)), int(np.float32(H) * np.float32(a.scale)))
+    d_class = torch.empty((B, OH, OW), dtype=torch.uint8, device="cuda")
+    d_rgba = torch.empty((B, OH, OW, 4), dtype=torch.uint8, device="cuda")
     with P.Handle(max_batch=B) as h:
         h.model_load(path)
+        h.scale_control(a.scale)
         for _ in range(2):
             h.advance_device(d.data_ptr(), B, W, H, d_class.data_ptr(), d_rgba.data_ptr(), sync=True)
         lines = [ln for ln in h.plan_text(B, W, H).splitlines() if ln.startswith(("conv ", "maxpool "))]
