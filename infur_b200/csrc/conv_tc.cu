@@ -1,20 +1,27 @@
-// tcgen05 implicit-GEMM convolution kernel (see conv_tc.h for the math and the data layout).
+// tcgen05 implicit-GEMM convolution kernels (see conv_tc.h for the math and the data layout).
 //
-// Persistent, warp-specialised, one CTA per SM:
-//   warp 0    TMA producer   - one elected lane issues the A (4-D activation box) and B (2-D weight box)
-//                              loads of each 64-channel K block into a ring of smem stages
-//   warp 1    MMA issuer     - one elected lane issues 4 x tcgen05.mma (M128 x N x K16) per K block into one
-//                              of two TMEM accumulator stages; tcgen05.commit releases the smem stage
+// Four persistent, warp-specialised kernels (one CTA per SM, 384 threads) that share one epilogue:
+//   conv_tc_kernel<N>     one CTA per 128-pixel x N tile; K blocks = (64-channel chunk, filter tap), tap-wise TMA loads
+//   conv_tc_pair_kernel   CTA pair (cta_group::2): 256 x 256 tile, each CTA loads its A half and half of the weights
+//   conv_halo_kernel<N>   3x3 / stride 1: one halo patch per chunk, nine taps = nine shifted UMMA descriptors
+//   stem_tc_kernel        7x7 / stride 2 on RGB: raw input rows read as Toeplitz operands, weights resident in smem
+// Warp roles in all of them:
+//   warp 0    TMA producer   - one elected lane issues the operand loads into a ring of smem stages
+//   warp 1    MMA issuer     - one elected lane issues 4 x tcgen05.mma (M128 x N x K16) per K block into one of the
+//                              2 (N = 256) or 4 (N <= 128) TMEM accumulator stages; tcgen05.commit releases the smem
+//                              stage and signals the epilogue
 //   warp 2    TMEM allocator
 //   warp 3    epilogue DMA   - one elected lane issues the TMA stores of finished output chunks and the TMA
 //                              prefetch of residual chunks (all bulk-group accounting in one thread)
-//   warps 4-11 epilogue      - tcgen05.ld the finished accumulator (thread = output pixel), + bias
-//                              (+ residual) (ReLU) -> fp16, overlapping the next tile's MMAs through the
-//                              second accumulator stage.  fp16 outputs are staged per 64-channel chunk in
-//                              128B-swizzled smem and written with TMA stores (which also clip tiles that
-//                              overhang the image); the residual chunk is TMA-prefetched into the same
-//                              buffer up to 4 chunks ahead, so the HBM traffic of the epilogue is fully
-//                              asynchronous.  The f32 logit head (21 channels) uses direct stores.
+//   warps 4-11 epilogue      - tcgen05.ld the finished accumulator (thread = output pixel, 32 channels), + bias
+//                              (+ residual) -> fp16 -> ReLU, overlapping the next tiles' MMAs through the other
+//                              accumulator stages.  Outputs are staged per 64-channel chunk in 128B-swizzled smem
+//                              and written with TMA stores (which also clip tiles that overhang the image); the
+//                              residual chunk is TMA-prefetched into the same buffer up to 4 chunks ahead, so the
+//                              HBM traffic of the epilogue is fully asynchronous.  The f32 logit head (21 channels)
+//                              uses direct stores.
+// Every variant accumulates the K blocks of an output element in the same (chunk-major) order: results are
+// bit-identical whichever variant the plan-time autotuner picks.
 #include "conv_tc.h"
 #include "ptx.cuh"
 
