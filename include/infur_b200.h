@@ -209,6 +209,13 @@ int32_t infur_b200_scale_advance(infur_b200_handle* h, const uint8_t* bgr, uint3
 int32_t infur_b200_model_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* logits_f32, size_t logits_cap,
                                  float* aux_logits_f32, size_t aux_cap, uint32_t* num_classes, int32_t* has_model);
 
+/* Diagnostics: the `out` head's logits BEFORE the final Resize, [K][lh][lw] f32 (lh = hgt / 8, lw = w / 8 for FCN), of
+ * one image fed as is (no Scale).  This is the tensor the fused post-kernel up-samples; the parity tests compare it with
+ * the oracle directly (bit-exactly for quantised models).  Sizes are written even when the buffer is too small
+ * (INFUR_E_BUFFER_TOO_SMALL); without a model *k = 0 and the call returns OK. */
+int32_t infur_b200_model_lowres(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* lowres, size_t cap_floats,
+                                uint32_t* k, uint32_t* lw, uint32_t* lh);
+
 /* Pre-processing of ImageSession::forward alone (predict_onnx.rs:103-137): [h][w][3] u8 BGR ->
  * [3][h][w] f32 RGB-normalised. */
 int32_t infur_b200_preprocess(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* out_nchw,
@@ -240,6 +247,12 @@ typedef struct infur_b200_conv_desc {
   uint32_t n, h, w, cin, cout, kh, kw, stride, pad, dil;
   int32_t relu;
   int32_t impl; /* INFUR_CONV_TCGEN05 / INFUR_CONV_VALIDATE */
+  /* Quantised layer (qmul != NULL; tcgen05 implementations only): x, wgt, residual hold integers (q - zero point) in
+   * fp16, bias the int32 bias as f32, and the epilogue requantises like QLinearConv [+ QLinearAdd]:
+   *   r = clamp(rne((acc + bias) * qmul[c]), q_lo, q_hi);  with residual: r = clamp(rne(r * q_ra + res * q_rb), q_lo2, q_hi2);
+   * y holds r (fp16), y_f32 holds r * q_deq. */
+  const float* qmul; /* [cout] or NULL */
+  float q_lo, q_hi, q_ra, q_rb, q_lo2, q_hi2, q_deq;
 } infur_b200_conv_desc;
 int32_t infur_b200_conv_test(infur_b200_handle* h, const infur_b200_conv_desc* d, const uint16_t* x,
                              const uint16_t* wgt, const float* bias, const uint16_t* residual, uint16_t* y,

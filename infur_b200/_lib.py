@@ -70,7 +70,8 @@ class Slot(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [(k, C.c_uint32) for k in ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "pad", "dil")] + [
-        ("relu", C.c_int32), ("impl", C.c_int32)]
+        ("relu", C.c_int32), ("impl", C.c_int32), ("qmul", C.c_void_p)] + [
+        (k, C.c_float) for k in ("q_lo", "q_hi", "q_ra", "q_rb", "q_lo2", "q_hi2", "q_deq")]
 
 
 # every symbol include/infur_b200.h declares: name -> (restype, argtypes)
@@ -103,6 +104,8 @@ SYMBOLS = {
     "infur_b200_scale_advance": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "infur_b200_model_advance": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                              C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
+    "infur_b200_model_lowres": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "infur_b200_preprocess": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "infur_b200_color_code": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "infur_b200_upsample_color": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,

@@ -510,6 +510,39 @@ int32_t infur_b200_model_advance(infur_b200_handle* h, const uint8_t* bgr, uint3
   return rc;
 }
 
+int32_t infur_b200_model_lowres(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* lowres, size_t cap_floats,
+                                uint32_t* k, uint32_t* lw, uint32_t* lh) {
+  if (!h) return INFUR_E_INVALID_ARG;
+  if (k) *k = 0;
+  if (lw) *lw = 0;
+  if (lh) *lh = 0;
+  if (!h->model) return INFUR_OK;
+  const float factor = h->factor;
+  const bool dirty = h->dirty;
+  h->factor = 1.0f;
+  infur_b200_out o;
+  memset(&o, 0, sizeof(o));
+  o.struct_size = sizeof(o);
+  std::vector<uint8_t> cls((size_t)w * hgt);   // one requested output makes advance run the step (no buffer = size query)
+  o.class_map = cls.data(); o.class_map_cap = cls.size();
+  int32_t rc = infur_b200_advance_batch(h, bgr, 1, w, hgt, nullptr, &o);
+  Plan* pp = nullptr;
+  if (rc == INFUR_OK) { Status st = get_plan(h, 1, (int)w, (int)hgt, &pp); if (!st.ok()) rc = fail(h, st); }
+  h->factor = factor; h->dirty = dirty;
+  if (rc != INFUR_OK) return rc;
+  const Plan& p = *pp;
+  if (k) *k = (uint32_t)p.k;
+  if (lw) *lw = (uint32_t)p.lw;
+  if (lh) *lh = (uint32_t)p.lh;
+  const size_t px = (size_t)p.lh * p.lw;
+  if (!lowres || cap_floats < px * p.k) return fail(h, INFUR_E_BUFFER_TOO_SMALL, "model_lowres: buffer too small");
+  std::vector<float> tmp(px * p.ldk);
+  API_CU(h, cudaMemcpy(tmp.data(), p.lowres, tmp.size() * 4, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < px; ++i)
+    for (int c = 0; c < p.k; ++c) lowres[(size_t)c * px + i] = tmp[i * p.ldk + c];
+  return INFUR_OK;
+}
+
 int32_t infur_b200_preprocess(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, float* out_nchw, size_t out_cap_bytes) {
   if (!h) return INFUR_E_INVALID_ARG;
   cudaSetDevice(h->cfg.device);

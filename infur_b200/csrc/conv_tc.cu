@@ -122,6 +122,17 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
           v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
         }
         const size_t off = pix * (size_t)g.out_ld + (size_t)(n0 + c0);
+        if (g.quant) {   // QLinearConv requantisation (ConvTcGeom::quant)
+          const float4* m4 = reinterpret_cast<const float4*>(g.qmul + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 m = __ldg(m4 + j);
+            v[4 * j + 0] = fminf(fmaxf(rintf(__fmul_rn(v[4 * j + 0], m.x)), g.q_lo), g.q_hi);
+            v[4 * j + 1] = fminf(fmaxf(rintf(__fmul_rn(v[4 * j + 1], m.y)), g.q_lo), g.q_hi);
+            v[4 * j + 2] = fminf(fmaxf(rintf(__fmul_rn(v[4 * j + 2], m.z)), g.q_lo), g.q_hi);
+            v[4 * j + 3] = fminf(fmaxf(rintf(__fmul_rn(v[4 * j + 3], m.w)), g.q_lo), g.q_hi);
+          }
+        }
         if (g.residual != nullptr) {
           const uint4* r4 = reinterpret_cast<const uint4*>(g.residual + off);
 #pragma unroll
@@ -131,8 +142,13 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float2 f = __half22float2(h[q]);
-              v[8 * j + 2 * q] += f.x;
-              v[8 * j + 2 * q + 1] += f.y;
+              if (g.quant) {   // QLinearAdd
+                v[8 * j + 2 * q] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[8 * j + 2 * q], g.q_ra), __fmul_rn(f.x, g.q_rb))), g.q_lo2), g.q_hi2);
+                v[8 * j + 2 * q + 1] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[8 * j + 2 * q + 1], g.q_ra), __fmul_rn(f.y, g.q_rb))), g.q_lo2), g.q_hi2);
+              } else {
+                v[8 * j + 2 * q] += f.x;
+                v[8 * j + 2 * q + 1] += f.y;
+              }
             }
           }
         }
@@ -141,6 +157,10 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (g.out_f32 != nullptr) {
+          if (g.quant && g.q_deq != 0.f) {   // DequantizeLinear of the logits
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], g.q_deq);
+          }
           float4* o4 = reinterpret_cast<float4*>(g.out_f32 + off);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -192,11 +212,16 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
       const int b = q % EB;
       const uint32_t use = (uint32_t)(q / EB);
       const uint32_t rowp = epi_base + b * kEpiBufBytes + (uint32_t)row * 128u;
-      float4 bias[8];
+      float4 bias[8], qm[8];
       {
         const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0 + c * 64 + half * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) bias[j] = __ldg(b4 + j);
+      }
+      if (g.quant) {
+        const float4* m4 = reinterpret_cast<const float4*>(g.qmul + n0 + c * 64 + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qm[j] = __ldg(m4 + j);
       }
       uint32_t acc[32];
       ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), acc);
@@ -231,7 +256,23 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
         // the scalar f32 operations they replace
         ptx::add_f32x2(v[0], v[1], bl.x, bl.y); ptx::add_f32x2(v[2], v[3], bl.z, bl.w);
         ptx::add_f32x2(v[4], v[5], bh.x, bh.y); ptx::add_f32x2(v[6], v[7], bh.z, bh.w);
-        if (HAS_RES) {
+        if (g.quant) {
+          // quantised layer: v is the exact integer accumulator + bias; requantise like QLinearConv, then (HAS_RES) add the
+          // residual like QLinearAdd.  Separate f32 multiplies and adds (no FMA contraction), round half to even.
+          const float4 ml = qm[2 * j], mh = qm[2 * j + 1];
+          const float mm[8] = {ml.x, ml.y, ml.z, ml.w, mh.x, mh.y, mh.z, mh.w};
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = fminf(fmaxf(rintf(__fmul_rn(v[t], mm[t])), g.q_lo), g.q_hi);
+          if (HAS_RES) {
+            const uint32_t rw[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&rw[t]));
+              v[2 * t] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[2 * t], g.q_ra), __fmul_rn(r.x, g.q_rb))), g.q_lo2), g.q_hi2);
+              v[2 * t + 1] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[2 * t + 1], g.q_ra), __fmul_rn(r.y, g.q_rb))), g.q_lo2), g.q_hi2);
+            }
+          }
+        } else if (HAS_RES) {
           const uint32_t rw[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {

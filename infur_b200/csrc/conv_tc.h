@@ -39,6 +39,12 @@ struct ConvTcGeom {
   const __half* residual;     // NHWC like out, or nullptr
   __half* out;                // fp16 NHWC, or nullptr when out_f32 is used
   float* out_f32;             // f32 NHWC (logit head)
+  // Quantised layer (QLinearConv [+ QLinearAdd], onnx_reader.h ConvOp): operands are integers carried in fp16, the epilogue
+  // requantises  r = clamp(rne((acc + bias) * qmul[c]), q_lo, q_hi);  with a residual  r = clamp(rne(r * q_ra + res * q_rb),
+  // q_lo2, q_hi2);  an f32 head stores r * q_deq.
+  int32_t quant;
+  const float* qmul;          // [tiles_n * BLOCK_N]
+  float q_lo, q_hi, q_ra, q_rb, q_lo2, q_hi2, q_deq;
   int8_t tap_view[kMaxTaps + 3];
   uint8_t tap_cc[kMaxTaps + 3];  // 64-channel chunks of each tap (a fused shortcut tap may differ from the main taps)
   int16_t tap_dx[kMaxTaps + 1];

@@ -81,6 +81,7 @@ static bool pair_disabled_env() { const char* e = getenv("INFUR_B200_NO_CTA_PAIR
 
 static void classify_conv(const ConvOp& c, bool reads_input, bool is_head, DevConv& d) {
   d.cin = c.cin; d.cout = c.cout; d.kh = c.kh; d.kw = c.kw; d.stride = c.stride; d.pad = c.pad; d.dil = c.dil; d.relu = c.relu;
+  d.quant = c.quant; d.q_lo = c.q_lo; d.q_hi = c.q_hi; d.q_ra = c.q_ra; d.q_rb = c.q_rb; d.q_lo2 = c.q_lo2; d.q_hi2 = c.q_hi2; d.q_deq = c.deq_scale;
   d.stem = false; d.tc_ok = false;
   static const int cands[4] = {256, 128, 64, 32};
   d.block_n = 32;
@@ -142,7 +143,12 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
     if (d.stem) { d.wv_off = off; off = align_up(off + (size_t)c.cout * c.kh * c.kw * c.cin * 2, 256); }
     else d.wv_off = d.w_off;
     d.b_off = off; off = align_up(off + (size_t)d.cout_pad * 4, 256);
+    if (d.quant) {
+      if (cfg.conv_impl != INFUR_CONV_TCGEN05) return Status::error(INFUR_E_UNSUPPORTED, "quantised models run on the tcgen05 path only (cfg.conv_impl)");
+      d.q_off = off; off = align_up(off + (size_t)d.cout_pad * 4, 256);
+    }
   }
+  if (m.quant) { dm->lut_q_off = off; off = align_up(off + 768 * 2, 256); }
   dm->arena_bytes = off;
   CU_TRY(cudaMalloc(&dm->arena, off ? off : 256));
   if (skip_weights) {
@@ -172,6 +178,24 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
       }
       float* b = reinterpret_cast<float*>(host.data() + d.b_off);
       for (int co = 0; co < c.cout; ++co) b[co] = c.bias[co];
+      if (d.quant) {
+        float* q = reinterpret_cast<float*>(host.data() + d.q_off);
+        for (int co = 0; co < c.cout; ++co) q[co] = c.qmul[co];
+      }
+    }
+    if (m.quant) {
+      // QuantizeLinear on the network input folded into the pre-kernel table: q = sat(rne(x / scale) + zp), stored as q - zp.
+      // x is the value ImageSession::forward would feed (predict_onnx.rs:117-137): normalised f32, or the raw byte.
+      float lut_f[768];
+      if (m.io.float_input) build_norm_lut(lut_f);
+      else for (int i = 0; i < 768; ++i) lut_f[i] = (float)(i & 255);
+      __half* lq = reinterpret_cast<__half*>(host.data() + dm->lut_q_off);
+      for (int i = 0; i < 768; ++i) {
+        volatile float t = lut_f[i] / m.in_scale;
+        float r = nearbyintf(t) + (float)m.in_zp;
+        r = fminf(fmaxf(r, (float)m.in_qmin), (float)m.in_qmax);
+        lq[i] = __float2half_rn(r - (float)m.in_zp);
+      }
     }
     CU_TRY(cudaMemcpy(dm->arena, host.data(), off, cudaMemcpyHostToDevice));
   }
@@ -195,6 +219,7 @@ struct ConvIO {
   __half* y = nullptr;
   float* y_f32 = nullptr;
   int out_ld = 0;
+  const float* qmul = nullptr;   // quantised layer (DevConv::quant)
 };
 
 enum { kVarPlain = 0, kVarPair = 1, kVarHalo = 2 };
@@ -235,6 +260,10 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   if (halo) { if (!halo_ok(d) || io.y_f32 || io.residual) return Status::error(INFUR_E_UNSUPPORTED, "halo variant: needs a 3x3 / stride 1 / pad = dilation convolution without residual"); g.stages = 0; }
   g.num_work = ((io.n * g.tiles_x * g.tiles_y + 1) / 2) * g.tiles_n;
   g.bias = io.bias; g.residual = io.residual; g.out = io.y; g.out_f32 = io.y_f32;
+  if (d.quant) {
+    g.quant = 1; g.qmul = io.qmul;
+    g.q_lo = d.q_lo; g.q_hi = d.q_hi; g.q_ra = d.q_ra; g.q_rb = d.q_rb; g.q_lo2 = d.q_lo2; g.q_hi2 = d.q_hi2; g.q_deq = d.q_deq;
+  }
   Status st;
   const uint32_t box[4] = {64, (uint32_t)(d.stem ? 128 : bw), (uint32_t)(d.stem ? 1 : bh), 1};
   if (d.stem) {
@@ -538,6 +567,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       io.x = reinterpret_cast<const __half*>(ti.ptr); io.n = n; io.h = ti.h; io.w = ti.w; io.oh = to.h; io.ow = to.w;
       io.wgt = reinterpret_cast<const __half*>(M->arena + d.w_off);
       io.bias = reinterpret_cast<const float*>(M->arena + d.b_off);
+      if (d.quant) io.qmul = reinterpret_cast<const float*>(M->arena + d.q_off);
       io.residual = op.conv.residual >= 0 ? reinterpret_cast<const __half*>(p.tensors[op.conv.residual].ptr) : nullptr;
       if (op.conv.in2 >= 0) {
         const TensorInfo& t2 = p.tensors[op.conv.in2];
@@ -609,6 +639,7 @@ void fill_pre_args(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, PreArgs&
   // Float models: RGB + torchvision normalisation; Uint8 models: the raw bytes in B,G,R order (predict_onnx.rs:103-137,296-306)
   const bool u8_model = p.has_model && !H->model->lm.io.float_input;
   pa.lut_h = u8_model ? H->d_lut_u8 : H->d_lut_h; pa.bgr_order = u8_model ? 1 : 0;
+  if (p.has_model && H->model->lm.quant) pa.lut_h = reinterpret_cast<const __half*>(H->model->arena + H->model->lut_q_off);
   pa.stem_in = p.has_model ? p.stem_in : nullptr;
   pa.scaled_bgr = unit ? nullptr : p.scaled;
 }
@@ -676,6 +707,10 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   ConvOp c;
   c.cin = (int)cd->cin; c.cout = (int)cd->cout; c.kh = (int)cd->kh; c.kw = (int)cd->kw; c.stride = (int)cd->stride; c.pad = (int)cd->pad;
   c.dil = (int)cd->dil; c.relu = cd->relu != 0;
+  if (cd->qmul) {
+    c.quant = true; c.q_lo = cd->q_lo; c.q_hi = cd->q_hi; c.q_ra = cd->q_ra; c.q_rb = cd->q_rb; c.q_lo2 = cd->q_lo2; c.q_hi2 = cd->q_hi2;
+    c.deq_scale = cd->q_deq;
+  }
   if (cd->n == 0 || cd->h == 0 || cd->w == 0 || c.cin <= 0 || c.cout <= 0 || c.kh <= 0 || c.kw <= 0 || c.stride <= 0 || c.dil <= 0 || c.pad < 0)
     return Status::error(INFUR_E_INVALID_ARG, "conv_test: bad descriptor");
   const int n = (int)cd->n, h = (int)cd->h, w = (int)cd->w;
@@ -688,6 +723,7 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   const bool pair = cd->impl == INFUR_CONV_TCGEN05_PAIR;
   const bool halo = cd->impl == INFUR_CONV_TCGEN05_HALO;
   const bool tc = cd->impl == INFUR_CONV_TCGEN05 || pair || halo;
+  if (c.quant && !tc) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: quantised layers run on the tcgen05 implementations only");
   if (tc && !d.tc_ok) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: shape not supported by the tcgen05 kernel: " + d.why_not);
   Plan tmp;
   Status st;
@@ -704,10 +740,15 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
     for (size_t j = 0; j < wcount; ++j) wp[j] = wh[j];
   }
   __half *d_w = nullptr, *d_wv = nullptr, *d_x = nullptr, *d_res = nullptr, *d_y = nullptr;
-  float *d_b = nullptr, *d_yf = nullptr;
+  float *d_b = nullptr, *d_yf = nullptr, *d_q = nullptr;
   std::vector<float> bp((size_t)d.cout_pad, 0.f);
   for (int co = 0; co < c.cout; ++co) bp[co] = bias[co];
   if (!(st = dev_upload(tmp, &d_w, wp)).ok() || !(st = dev_upload(tmp, &d_b, bp)).ok()) return st;
+  if (c.quant) {
+    std::vector<float> qp((size_t)d.cout_pad, 0.f);
+    for (int co = 0; co < c.cout; ++co) qp[co] = cd->qmul[co];
+    if (!(st = dev_upload(tmp, &d_q, qp)).ok()) return st;
+  }
   {
     std::vector<__half> wv(wh, wh + wcount);
     if (!(st = dev_upload(tmp, &d_wv, wv)).ok()) return st;
@@ -738,7 +779,7 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   else { if (!(st = dev_alloc(tmp, &d_y, ocount)).ok()) return st; CU_TRY(cudaMemset(d_y, 0, ocount * 2)); }
   ConvIO io;
   io.x = d_x; io.n = n; io.h = h; io.w = w; io.oh = oh; io.ow = ow; io.wgt = d_w; io.bias = d_b; io.residual = d_res; io.y = d_y; io.y_f32 = d_yf;
-  io.out_ld = out_ld;
+  io.out_ld = out_ld; io.qmul = d_q;
   PlanOp po;
   if (pair && (d.block_n != 256 || d.stem || f32out)) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the CTA-pair variant needs cout % 256 == 0 and an fp16 output");
   if (halo && !halo_ok(d)) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the halo variant needs a 3x3 / stride 1 / pad = dilation convolution");

@@ -36,6 +36,10 @@ struct DevConv {
   size_t w_off = 0;        // fp16 [cout_pad][kdim] for the tcgen05 kernel (byte offset into the arena)
   size_t wv_off = 0;       // fp16 [cout][kh][kw][cin] for the validation kernel (== w_off unless stem)
   size_t b_off = 0;        // f32 [cout_pad]
+  // quantised layer: requantisation multipliers f32 [cout_pad] at q_off, scalars as in ConvOp
+  bool quant = false;
+  size_t q_off = 0;
+  float q_lo = 0.f, q_hi = 0.f, q_ra = 0.f, q_rb = 0.f, q_lo2 = 0.f, q_hi2 = 0.f, q_deq = 0.f;
 };
 
 struct DeviceModel {
@@ -45,6 +49,7 @@ struct DeviceModel {
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   int out_head = -1, aux_head = -1;
+  size_t lut_q_off = 0;          // quantised models: fp16 [3][256] pre-kernel table of QuantizeLinear(input) - zero point
   ~DeviceModel();
 };
 

@@ -71,6 +71,7 @@ void parse_tensor(Cursor c, OnnxTensor& t) {
         if (w == 2) { size_t n = (size_t)(s.end - s.p) / 4; size_t o = t.float_data.size(); t.float_data.resize(o + n); memcpy(t.float_data.data() + o, s.p, n * 4); }
         else { float x; uint32_t u = (uint32_t)v; memcpy(&x, &u, 4); t.float_data.push_back(x); }
         break;
+      case 5: { std::vector<int64_t> tmp; packed_varints(w, v, s, tmp); for (auto x : tmp) t.int32_data.push_back((int32_t)x); break; }
       case 7: packed_varints(w, v, s, t.int64_data); break;
       case 8: t.name = str(s); break;
       case 9: t.raw = s.p; t.raw_size = (size_t)(s.end - s.p); break;
@@ -167,6 +168,24 @@ std::vector<float> tensor_f32(const OnnxTensor& t, const std::string& what) {
   if (t.raw && t.raw_size == n * 4) memcpy(v.data(), t.raw, n * 4);
   else if (t.float_data.size() == n) v = t.float_data;
   else throw ModelError(INFUR_E_MODEL_LOAD, what + ": initializer '" + t.name + "' has inconsistent data size");
+  return v;
+}
+
+// Integer initializer (UINT8 / INT8 / INT32; raw_data or int32_data) widened to int32.
+std::vector<int32_t> tensor_i32(const OnnxTensor& t, const std::string& what) {
+  const size_t n = t.numel();
+  std::vector<int32_t> v(n);
+  const size_t esz = t.dtype == 6 ? 4 : (t.dtype == 2 || t.dtype == 3) ? 1 : 0;
+  if (!esz) throw ModelError(INFUR_E_MODEL_LOAD, what + ": initializer '" + t.name + "' must be UINT8, INT8 or INT32");
+  if (t.raw && t.raw_size == n * esz) {
+    for (size_t i = 0; i < n; ++i) {
+      if (t.dtype == 2) v[i] = t.raw[i];
+      else if (t.dtype == 3) v[i] = (int8_t)t.raw[i];
+      else memcpy(&v[i], t.raw + 4 * i, 4);
+    }
+  } else if (t.int32_data.size() == n) {
+    v = t.int32_data;
+  } else throw ModelError(INFUR_E_MODEL_LOAD, what + ": initializer '" + t.name + "' has inconsistent data size");
   return v;
 }
 
@@ -278,20 +297,26 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       input_chain.insert(n.out[0]);
       continue;
     }
-    if (n.op == "Conv" || n.op == "Relu" || n.op == "Add" || n.op == "MaxPool" || n.op == "Resize") { compute.push_back(&n); continue; }
+    if (n.op == "Conv" || n.op == "Relu" || n.op == "Add" || n.op == "MaxPool" || n.op == "Resize" || n.op == "QLinearConv" ||
+        n.op == "QLinearAdd" || n.op == "QuantizeLinear" || n.op == "DequantizeLinear") { compute.push_back(&n); continue; }
     if (shape_ops.count(n.op)) {
       // only allowed when it does not touch an activation except through Shape
       for (auto& o : n.out) shape_values.insert(o);
       continue;
     }
-    throw ModelError(INFUR_E_MODEL_LOAD, "unsupported operator '" + n.op + "' (node '" + n.name + "'); supported: Conv, Relu, Add, MaxPool, Resize"
-                     + (n.op.find("Linear") != std::string::npos || n.op[0] == 'Q' ? " -- quantised (QLinear/QDQ) models are not supported" : ""));
+    throw ModelError(INFUR_E_MODEL_LOAD, "unsupported operator '" + n.op + "' (node '" + n.name + "'); supported: Conv, Relu, Add, MaxPool, Resize and the "
+                     "QOperator forms QuantizeLinear, QLinearConv, QLinearAdd, DequantizeLinear");
   }
   std::map<std::string, int> consumers;
   std::map<std::string, const OnnxNode*> single_consumer;
   for (auto* n : compute) {
-    size_t n_data = (n->op == "Conv" || n->op == "Resize") ? 1 : n->in.size();
-    for (size_t i = 0; i < n_data && i < n->in.size(); ++i) {
+    // activation inputs only (weights, scales, zero points and sizes are not tensors of the lowered graph)
+    std::vector<size_t> data;
+    if (n->op == "QLinearAdd") data = {0, 3};
+    else if (n->op == "Add") data = {0, 1};
+    else data = {0};
+    for (size_t i : data) {
+      if (i >= n->in.size()) continue;
       std::string r = resolve(n->in[i]);
       consumers[r]++;
       single_consumer[r] = n;
@@ -332,10 +357,162 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
     return false;
   };
 
+  // ---- quantised (QOperator) graphs: per-tensor (scale, zero point) of every quantised activation
+  struct QInfo { float scale; int zp, qmin, qmax; };
+  std::map<int, QInfo> qinfo;          // tensor id -> quantisation; absent = float tensor
+  std::map<std::string, QInfo> pending_q;  // output quantisation of a pending QLinearConv
+  std::set<int> dequantized;           // tensor ids whose stored form is the de-quantised f32 value (head inputs of Resize)
+  auto q_init = [&](const OnnxNode& n, size_t idx, const char* what) -> const OnnxTensor& {
+    if (idx >= n.in.size() || n.in[idx].empty()) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': missing " + what);
+    auto it = g.inits.find(resolve(n.in[idx]));
+    if (it == g.inits.end()) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': " + what + " is not an initializer");
+    return it->second;
+  };
+  auto q_scale = [&](const OnnxNode& n, size_t idx, const char* what) {
+    std::vector<float> v = tensor_f32(q_init(n, idx, what), n.op + " '" + n.name + "'");
+    if (v.size() != 1 || !(v[0] > 0.f)) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': " + what + " must be one positive FLOAT");
+    return v[0];
+  };
+  auto q_zp = [&](const OnnxNode& n, size_t idx, const char* what, float scale) {
+    QInfo q{scale, 0, 0, 255};
+    if (idx >= n.in.size() || n.in[idx].empty()) return q;   // optional: uint8 zero
+    const OnnxTensor& t = q_init(n, idx, what);
+    std::vector<int32_t> v = tensor_i32(t, n.op + " '" + n.name + "'");
+    if (v.size() != 1 || (t.dtype != 2 && t.dtype != 3)) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': " + what + " must be one UINT8 / INT8 value");
+    q.zp = v[0];
+    if (t.dtype == 3) { q.qmin = -128; q.qmax = 127; }
+    return q;
+  };
+  auto same_q = [](const QInfo& a, const QInfo& b) { return a.scale == b.scale && a.zp == b.zp && a.qmin == b.qmin; };
+  auto need_q = [&](int tensor, const QInfo& want, const OnnxNode& n, const char* which) {
+    auto it = qinfo.find(tensor);
+    if (it == qinfo.end()) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': input " + which + " is not a quantised tensor");
+    if (!same_q(it->second, want))
+      throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': scale / zero point of input " + which + " differ from its producer's (re-quantising edges are not supported)");
+  };
+  auto need_float = [&](int tensor, const OnnxNode& n) {
+    if (qinfo.count(tensor)) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "' reads a quantised tensor (mixed float / quantised graphs are not supported)");
+  };
+  auto conv_geometry = [&](const OnnxNode& n, const OnnxTensor& wt, ConvOp& c) {
+    if (wt.dims.size() != 4) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': weight must be 4-D");
+    c.cout = (int)wt.dims[0]; c.cin = (int)wt.dims[1]; c.kh = (int)wt.dims[2]; c.kw = (int)wt.dims[3];
+    if (attr_i(n, "group", 1) != 1) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': group != 1 is not supported");
+    auto strides = attr_ints(n, "strides", {1, 1}), dil = attr_ints(n, "dilations", {1, 1}), pads = attr_ints(n, "pads", {0, 0, 0, 0});
+    auto ks = attr_ints(n, "kernel_shape", {c.kh, c.kw});
+    if (ks.size() != 2 || ks[0] != c.kh || ks[1] != c.kw) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': kernel_shape does not match the weight");
+    if (auto* ap = n.attr("auto_pad")) if (!ap->s.empty() && ap->s != "NOTSET") throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': auto_pad is not supported");
+    if (strides.size() != 2 || strides[0] != strides[1] || dil.size() != 2 || dil[0] != dil[1] || pads.size() != 4 || !all_eq(pads, pads[0]) || c.kh != c.kw)
+      throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': only square kernels with symmetric stride/dilation/padding are supported");
+    c.stride = (int)strides[0]; c.dil = (int)dil[0]; c.pad = (int)pads[0];
+  };
+
   for (auto* np : compute) {
     const OnnxNode& n = *np;
     if (fused.count(np)) continue;
-    if (n.op == "Conv") {
+    if (n.op == "QuantizeLinear") {
+      // only on the network input: the pre-kernel's lookup table produces the quantised values directly
+      if (n.in.empty() || !input_chain.count(resolve(n.in[0])))
+        throw ModelError(INFUR_E_MODEL_LOAD, "QuantizeLinear '" + n.name + "': only supported on the network input");
+      const float sc = q_scale(n, 1, "y_scale");
+      QInfo q = q_zp(n, 2, "y_zero_point", sc);
+      m.quant = true; m.in_scale = sc; m.in_zp = q.zp; m.in_qmin = q.qmin; m.in_qmax = q.qmax;
+      tid[n.out[0]] = m.input_tensor;
+      qinfo[m.input_tensor] = q;
+    } else if (n.op == "QLinearConv") {
+      // x, x_scale, x_zero_point, w, w_scale, w_zero_point, y_scale, y_zero_point, [B]
+      if (n.in.size() < 8) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearConv '" + n.name + "' needs 8 or 9 inputs");
+      const OnnxTensor& wt = q_init(n, 3, "weight");
+      LoweredOp op; op.kind = OpKind::Conv; op.name = n.name.empty() ? n.out[0] : n.name;
+      ConvOp& c = op.conv;
+      conv_geometry(n, wt, c);
+      c.quant = true;
+      const float xs = q_scale(n, 1, "x_scale");
+      const QInfo xq = q_zp(n, 2, "x_zero_point", xs);
+      const float ys = q_scale(n, 6, "y_scale");
+      const QInfo yq = q_zp(n, 7, "y_zero_point", ys);
+      std::vector<float> ws = tensor_f32(q_init(n, 4, "w_scale"), "QLinearConv '" + n.name + "'");
+      std::vector<int32_t> wz = tensor_i32(q_init(n, 5, "w_zero_point"), "QLinearConv '" + n.name + "'");
+      if ((ws.size() != 1 && (int)ws.size() != c.cout) || (wz.size() != 1 && (int)wz.size() != c.cout))
+        throw ModelError(INFUR_E_MODEL_LOAD, "QLinearConv '" + n.name + "': w_scale / w_zero_point must be scalars or per-output-channel");
+      std::vector<int32_t> wq = tensor_i32(wt, "QLinearConv '" + n.name + "'");
+      if (wt.dtype == 6) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearConv '" + n.name + "': weight must be UINT8 or INT8");
+      c.weight.resize(wq.size());
+      for (int o = 0; o < c.cout; ++o) {
+        const int z = wz[wz.size() == 1 ? 0 : o];
+        for (int i = 0; i < c.cin; ++i)
+          for (int y = 0; y < c.kh; ++y)
+            for (int x = 0; x < c.kw; ++x)
+              c.weight[(((size_t)o * c.kh + y) * c.kw + x) * c.cin + i] = (float)(wq[(((size_t)o * c.cin + i) * c.kh + y) * c.kw + x] - z);
+      }
+      c.bias.assign(c.cout, 0.f);
+      if (n.in.size() >= 9 && !n.in[8].empty()) {
+        const OnnxTensor& bt = q_init(n, 8, "bias");
+        if (bt.dtype != 6) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearConv '" + n.name + "': bias must be INT32");
+        std::vector<int32_t> b = tensor_i32(bt, "QLinearConv '" + n.name + "'");
+        if ((int)b.size() != c.cout) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearConv '" + n.name + "': bias length mismatch");
+        for (int o = 0; o < c.cout; ++o) {
+          if (b[o] >= (1 << 24) || b[o] <= -(1 << 24))
+            throw ModelError(INFUR_E_MODEL_LOAD, "QLinearConv '" + n.name + "': |bias| >= 2^24 cannot be carried exactly by the f32 accumulator");
+          c.bias[o] = (float)b[o];
+        }
+      }
+      c.qmul.resize(c.cout);
+      for (int o = 0; o < c.cout; ++o) {
+        // ONNX Runtime's QLinearConv: output_scale[c] = (x_scale * w_scale[c]) / y_scale, evaluated in f32
+        volatile float t = xs * ws[ws.size() == 1 ? 0 : o];
+        volatile float q = t / ys;
+        c.qmul[o] = q;
+      }
+      c.q_lo = (float)(yq.qmin - yq.zp); c.q_hi = (float)(yq.qmax - yq.zp);
+      op.in = need(n.in[0], n);
+      need_q(op.in, xq, n, "x");
+      if (m.tensor_channels[op.in] != c.cin) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearConv '" + n.name + "': input has " + std::to_string(m.tensor_channels[op.in]) + " channels, weight expects " + std::to_string(c.cin));
+      const std::string out_name = n.out[0];
+      if (consumers[out_name] == 1 && single_consumer[out_name]->op == "QLinearAdd") { pending[out_name] = std::move(op); pending_q[out_name] = yq; continue; }
+      std::string final_name;
+      op.conv.relu = take_relu(out_name, final_name);
+      emit(std::move(op), final_name);
+      qinfo[tid[final_name]] = yq;
+    } else if (n.op == "QLinearAdd") {
+      // A, A_scale, A_zero_point, B, B_scale, B_zero_point, C_scale, C_zero_point   (com.microsoft)
+      if (n.in.size() < 7) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearAdd '" + n.name + "' needs 7 or 8 inputs");
+      const std::string a = resolve(n.in[0]), b = resolve(n.in[3]);
+      const bool a_main = pending.count(a) != 0;
+      if (!a_main && !pending.count(b)) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearAdd '" + n.name + "': neither input is a convolution output (stand-alone QLinearAdd is not supported)");
+      const std::string main_name = a_main ? a : b, other = a_main ? b : a;
+      const size_t mi = a_main ? 0 : 3, oi = a_main ? 3 : 0;
+      const float ms = q_scale(n, mi + 1, "scale"), os_ = q_scale(n, oi + 1, "scale"), cs = q_scale(n, 6, "C_scale");
+      const QInfo mq = q_zp(n, mi + 2, "zero point", ms), oq = q_zp(n, oi + 2, "zero point", os_), cq = q_zp(n, 7, "C_zero_point", cs);
+      if (pending.count(other)) {  // the projection shortcut of a bottleneck: runs on its own first
+        LoweredOp o = std::move(pending[other]); pending.erase(other);
+        emit(std::move(o), other);
+        qinfo[tid[other]] = pending_q[other];
+      }
+      LoweredOp op = std::move(pending[main_name]); pending.erase(main_name);
+      if (!same_q(pending_q[main_name], mq)) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearAdd '" + n.name + "': scale / zero point of the convolution input differ from the QLinearConv's output");
+      op.conv.residual = need(other, n);
+      need_q(op.conv.residual, oq, n, "(residual)");
+      if (m.tensor_channels[op.conv.residual] != op.conv.cout) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearAdd '" + n.name + "': channel mismatch");
+      // ONNX Runtime's QLinearAdd: C = sat(rne(A_scale / C_scale * (A - A_zp) + B_scale / C_scale * (B - B_zp)) + C_zp), f32
+      { volatile float ra = ms / cs, rb = os_ / cs; op.conv.q_ra = ra; op.conv.q_rb = rb; }
+      op.conv.q_lo2 = (float)(cq.qmin - cq.zp); op.conv.q_hi2 = (float)(cq.qmax - cq.zp);
+      std::string final_name;
+      op.conv.relu = take_relu(n.out[0], final_name);
+      emit(std::move(op), final_name);
+      qinfo[tid[final_name]] = cq;
+    } else if (n.op == "DequantizeLinear") {
+      // only as the step between a head convolution and its Resize: the convolution stores the de-quantised f32 logits
+      const int t = need(n.in[0], n);
+      const float sc = q_scale(n, 1, "x_scale");
+      need_q(t, q_zp(n, 2, "x_zero_point", sc), n, "x");
+      int prod = -1;
+      for (size_t j = 0; j < m.ops.size(); ++j) if (m.ops[j].out == t) prod = (int)j;
+      if (prod < 0 || m.ops[prod].kind != OpKind::Conv || m.ops[prod].conv.residual >= 0 || consumers[resolve(n.in[0])] != 1)
+        throw ModelError(INFUR_E_MODEL_LOAD, "DequantizeLinear '" + n.name + "': only supported on a convolution output that nothing else reads (the logits before Resize)");
+      m.ops[prod].conv.deq_scale = sc;
+      tid[n.out[0]] = t;
+      dequantized.insert(t);
+    } else if (n.op == "Conv") {
       if (n.in.size() < 2) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "' has no weight input");
       auto wit = g.inits.find(resolve(n.in[1]));
       if (wit == g.inits.end()) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': weight is not an initializer (quantised / dynamic weights are not supported)");
@@ -366,6 +543,7 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
         if ((int)c.bias.size() != c.cout) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': bias length mismatch");
       } else c.bias.assign(c.cout, 0.f);
       op.in = need(n.in[0], n);
+      need_float(op.in, n);
       if (m.tensor_channels[op.in] != c.cin) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': input has " + std::to_string(m.tensor_channels[op.in]) + " channels, weight expects " + std::to_string(c.cin));
       const std::string out_name = n.out[0];
       if (consumers[out_name] == 1 && single_consumer[out_name]->op == "Add") { pending[out_name] = std::move(op); continue; }
@@ -385,6 +563,7 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       }
       LoweredOp op = std::move(pending[main_name]); pending.erase(main_name);
       op.conv.residual = need(other, n);
+      need_float(op.conv.residual, n);
       if (m.tensor_channels[op.conv.residual] != op.conv.cout) throw ModelError(INFUR_E_MODEL_LOAD, "Add '" + n.name + "': channel mismatch");
       std::string final_name;
       op.conv.relu = take_relu(n.out[0], final_name);
@@ -398,7 +577,9 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       LoweredOp op; op.kind = OpKind::MaxPool; op.name = n.name.empty() ? n.out[0] : n.name;
       op.pool_k = (int)ks[0]; op.pool_s = (int)st[0]; op.pool_p = (int)pads[0];
       op.in = need(n.in[0], n);
+      const int pool_in = op.in;
       emit(std::move(op), n.out[0]);
+      if (qinfo.count(pool_in)) qinfo[tid[n.out[0]]] = qinfo[pool_in];   // max commutes with the affine quantisation map
     } else if (n.op == "Resize") {
       std::string mode = n.attr("mode") ? n.attr("mode")->s : "nearest";
       std::string ctm = n.attr("coordinate_transformation_mode") ? n.attr("coordinate_transformation_mode")->s : "half_pixel";
@@ -412,10 +593,18 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       for (auto& vi : g.outputs) if (vi.name == n.out[0]) is_output = true;
       if (!is_output) throw ModelError(INFUR_E_MODEL_LOAD, "Resize '" + n.name + "': only supported as the last node of an output head");
       LoweredHead hd; hd.name = n.out[0]; hd.tensor = need(n.in[0], n); hd.num_classes = m.tensor_channels[hd.tensor];
+      if (qinfo.count(hd.tensor) && !dequantized.count(hd.tensor))
+        throw ModelError(INFUR_E_MODEL_LOAD, "Resize '" + n.name + "' reads a quantised tensor; expected DequantizeLinear before it");
       m.heads.push_back(hd);
     }
   }
   if (!pending.empty()) throw ModelError(INFUR_E_MODEL_LOAD, "internal: convolution output left without its Add");
+  for (auto& op : m.ops)
+    if (op.kind == OpKind::Conv && op.conv.quant != m.quant)
+      throw ModelError(INFUR_E_MODEL_LOAD, "convolution '" + op.name + "': float and quantised convolutions cannot be mixed in one model");
+  if (m.quant)
+    for (auto& h : m.heads)
+      if (!dequantized.count(h.tensor)) throw ModelError(INFUR_E_MODEL_LOAD, "head '" + h.name + "' of a quantised model is not fed by DequantizeLinear");
   if (m.heads.empty()) throw ModelError(INFUR_E_MODEL_LOAD, "model has no `Resize` output head (not an FCN-style segmentation model)");
   // heads in graph-output order
   std::vector<LoweredHead> ordered;
@@ -429,6 +618,7 @@ int fuse_projection_shortcuts(LoweredModel& m) {
     LoweredOp& op = m.ops[i];
     if (op.kind != OpKind::Conv) continue;
     ConvOp& c = op.conv;
+    if (c.quant) continue;   // each QLinearConv re-quantises its own output: the two sums cannot share an accumulator
     if (c.residual < 0 || c.in2 >= 0 || c.kh != 1 || c.kw != 1 || c.stride != 1 || c.pad != 0 || c.cin % 64 != 0) continue;
     // producer of the residual: a bare 1x1 convolution whose output nobody else reads
     int pj = -1, uses = 0;
@@ -458,7 +648,9 @@ std::string describe(const LoweredModel& m) {
   std::ostringstream os;
   os << "inputs:";
   for (auto& s : m.io.input_names) os << " " << s;
-  os << " dtype=" << m.io.input0_dtype << " layout=" << (m.io.nchw ? "NCHW" : "NHWC") << " color=" << (m.io.rgb ? "RGB" : "BGR") << "\n";
+  os << " dtype=" << m.io.input0_dtype << " layout=" << (m.io.nchw ? "NCHW" : "NHWC") << " color=" << (m.io.rgb ? "RGB" : "BGR");
+  if (m.quant) os << " quantised(zp=" << m.in_zp << ")";
+  os << "\n";
   os << "outputs:";
   for (auto& s : m.io.output_names) os << " " << s;
   os << "\n";
@@ -467,7 +659,13 @@ std::string describe(const LoweredModel& m) {
     if (o.kind == OpKind::Conv) {
       const ConvOp& c = o.conv;
       os << i << " conv t" << o.in << "->t" << o.out << " " << c.cin << "->" << c.cout << " k" << c.kh << " s" << c.stride << " p" << c.pad << " d" << c.dil
-         << (c.residual >= 0 ? " +t" + std::to_string(c.residual) : std::string()) << (c.relu ? " relu" : "") << "\n";
+         << (c.residual >= 0 ? " +t" + std::to_string(c.residual) : std::string()) << (c.relu ? " relu" : "");
+      if (c.quant) {
+        os << " q[" << c.q_lo << "," << c.q_hi << "]";
+        if (c.residual >= 0) os << " add[" << c.q_lo2 << "," << c.q_hi2 << "]";
+        if (c.deq_scale != 0.f) os << " deq";
+      }
+      os << "\n";
     } else {
       os << i << " maxpool t" << o.in << "->t" << o.out << " k" << o.pool_k << " s" << o.pool_s << " p" << o.pool_p << "\n";
     }

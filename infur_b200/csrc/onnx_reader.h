@@ -19,6 +19,7 @@ struct OnnxTensor {
   size_t raw_size = 0;
   std::vector<float> float_data;
   std::vector<int64_t> int64_data;
+  std::vector<int32_t> int32_data;   // also carries INT8 / UINT8 / INT32 values when raw_data is not used
   size_t numel() const { size_t n = 1; for (auto d : dims) n *= (size_t)d; return n; }
 };
 
@@ -77,6 +78,17 @@ struct ConvOp {
   // over tensor `in2` accumulated into the same output: out = act(conv(in) + conv2(in2) + bias), bias = b + b2.
   int in2 = -1, cin2 = 0, stride2 = 1;
   std::vector<float> weight2;        // [cout][cin2]
+  // Quantised convolution (QLinearConv, optionally followed by a QLinearAdd).  Activations are carried as the integers
+  // q - zero_point (|.| <= 255, exact in fp16), `weight` holds w_q - w_zero_point and `bias` the int32 bias, so the fp16
+  // tensor-core product with f32 accumulation IS the integer accumulator while it stays below 2^24.  The epilogue
+  // requantises like ONNX Runtime's QLinearConv / QLinearAdd:
+  //   r = clamp(rne((acc + bias) * qmul[c]), q_lo, q_hi)                 qmul[c] = (x_scale * w_scale[c]) / y_scale
+  //   r = clamp(rne(r * q_ra + res * q_rb), q_lo2, q_hi2)                (only with `residual`; q_ra = a_scale / c_scale ...)
+  // and a head convolution followed by DequantizeLinear stores r * deq_scale as f32 logits.
+  bool quant = false;
+  std::vector<float> qmul;           // [cout]
+  float q_lo = 0.f, q_hi = 0.f, q_ra = 0.f, q_rb = 0.f, q_lo2 = 0.f, q_hi2 = 0.f;
+  float deq_scale = 0.f;
 };
 
 struct LoweredOp {
@@ -110,6 +122,10 @@ struct LoweredModel {
   std::vector<LoweredOp> ops;        // topological order
   std::vector<LoweredHead> heads;    // in graph-output order
   std::vector<int> tensor_channels;  // per tensor id
+  // QOperator-format (quantised) model: QuantizeLinear on the network input, q = sat(rne(x / in_scale) + in_zp)
+  bool quant = false;
+  float in_scale = 1.f;
+  int in_zp = 0, in_qmin = 0, in_qmax = 255;
 };
 
 struct ModelError : public std::exception {

@@ -262,6 +262,19 @@ class Handle:
                                                       C.byref(k), C.byref(has)))
         return [lg, aux] if want_aux else [lg]
 
+    def model_lowres(self, img: np.ndarray) -> Optional[np.ndarray]:
+        """Diagnostics: the ``out`` head's logits before the final Resize, ``[K][h/8][w/8]`` f32 (None without a model)."""
+        img = _check_bgr(img)
+        hgt, w = img.shape[:2]
+        k, lw, lh = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        rc = self.lib.infur_b200_model_lowres(self._h, img.ctypes.data, w, hgt, None, 0, C.byref(k), C.byref(lw), C.byref(lh))
+        if k.value == 0:
+            self._check(rc)
+            return None
+        out = np.empty((k.value, lh.value, lw.value), dtype=np.float32)
+        self._check(self.lib.infur_b200_model_lowres(self._h, img.ctypes.data, w, hgt, out.ctypes.data, out.size, C.byref(k), C.byref(lw), C.byref(lh)))
+        return out
+
     def color_code(self, hm: np.ndarray):
         hm = np.ascontiguousarray(hm, dtype=np.float32)
         k, h, w = hm.shape
@@ -289,8 +302,10 @@ class Handle:
         return lut
 
     # -- diagnostics
-    def conv_test(self, x, w, bias, residual=None, stride=1, pad=0, dil=1, relu=False, impl=L.CONV_TCGEN05, f32_out=False, timed=False):
-        """x: [N][H][W][Cin] fp16, w: [Cout][kh][kw][Cin] fp16, bias f32 [Cout], residual like the output."""
+    def conv_test(self, x, w, bias, residual=None, stride=1, pad=0, dil=1, relu=False, impl=L.CONV_TCGEN05, f32_out=False, timed=False,
+                  quant=None):
+        """x: [N][H][W][Cin] fp16, w: [Cout][kh][kw][Cin] fp16, bias f32 [Cout], residual like the output.
+        ``quant``: dict(qmul=[Cout] f32, q_lo, q_hi[, q_ra, q_rb, q_lo2, q_hi2][, q_deq]) runs the layer as a quantised one."""
         x = np.ascontiguousarray(x, dtype=np.float16)
         w = np.ascontiguousarray(w, dtype=np.float16)
         bias = np.ascontiguousarray(bias, dtype=np.float32)
@@ -299,6 +314,12 @@ class Handle:
         oh = (h + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         ow = (wd + 2 * pad - dil * (kw - 1) - 1) // stride + 1
         d = L.ConvDesc(n, h, wd, cin, cout, kh, kw, stride, pad, dil, int(relu), impl)
+        if quant is not None:
+            qmul = np.ascontiguousarray(quant["qmul"], dtype=np.float32)
+            assert qmul.shape == (cout,)
+            d.qmul = qmul.ctypes.data
+            for k in ("q_lo", "q_hi", "q_ra", "q_rb", "q_lo2", "q_hi2", "q_deq"):
+                setattr(d, k, float(quant.get(k, 0.0)))
         y = np.zeros((n, oh, ow, cout), dtype=np.float32 if f32_out else np.float16)
         res = np.ascontiguousarray(residual, dtype=np.float16) if residual is not None else None
         ms = C.c_float()

@@ -1,0 +1,122 @@
+"""GPU: quantised (QOperator-format) models.  Integer work: the bar is bit-exact.
+
+The product keeps quantised activations as the integers q - zero_point in fp16, the weights as w_q - w_zero_point, and
+requantises in the convolution epilogue (csrc/conv_tc.cu); while |accumulator| < 2^24 the fp16 x fp16 -> f32 tensor-core
+sum IS the int32 accumulator, so every QLinearConv / QLinearAdd output must equal the oracle's (oracle/qlinear.py) exactly,
+through every kernel variant.  Whole model: the low-resolution logits (after DequantizeLinear) are compared bit for bit;
+behind them the path is the float one (bilinear Resize in f32 -> ColorCode), held to the same bar as test_gpu_pipeline.py.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from infur_b200 import _lib as L
+from infur_b200 import processors as P
+from infur_b200 import quantize, synth
+from oracle import onnx_min, qlinear
+
+pytestmark = pytest.mark.gpu
+
+# n, h, w, cin, cout, k, stride, pad, dil, residual, impl, f32 head
+QCASES = [
+    (1, 8, 16, 64, 64, 1, 1, 0, 1, False, L.CONV_TCGEN05, False),
+    (2, 30, 40, 64, 256, 1, 1, 0, 1, True, L.CONV_TCGEN05, False),
+    (1, 30, 40, 256, 512, 1, 1, 0, 1, True, L.CONV_TCGEN05_PAIR, False),
+    (1, 30, 40, 512, 256, 1, 1, 0, 1, False, L.CONV_TCGEN05_PAIR, False),
+    (1, 30, 40, 64, 64, 3, 1, 1, 1, False, L.CONV_TCGEN05, False),
+    (1, 30, 40, 64, 128, 3, 1, 1, 1, False, L.CONV_TCGEN05_HALO, False),
+    (1, 33, 47, 128, 128, 3, 1, 2, 2, False, L.CONV_TCGEN05_HALO, False),
+    (1, 60, 80, 128, 128, 3, 2, 1, 1, False, L.CONV_TCGEN05, False),
+    (1, 60, 80, 256, 512, 1, 2, 0, 1, False, L.CONV_TCGEN05, False),
+    (2, 61, 75, 3, 64, 7, 2, 3, 1, False, L.CONV_TCGEN05, False),
+    (1, 30, 40, 512, 21, 1, 1, 0, 1, False, L.CONV_TCGEN05, True),
+    (1, 30, 40, 2048, 512, 3, 1, 1, 1, False, L.CONV_TCGEN05, False),
+]
+
+
+@pytest.mark.parametrize("case", QCASES, ids=lambda c: "n%d_%dx%d_c%d-%d_k%d_s%d_p%d_d%d%s_impl%d%s" % (c[:9] + ("_add" if c[9] else "", c[10], "_deq" if c[11] else "")))
+def test_qlinear_conv_bit_exact(handle, case):
+    n, h, w, cin, cout, k, stride, pad, dil, res, impl, f32 = case
+    rng = np.random.default_rng(abs(hash(case)) % 2**31)
+    x_zp, y_zp, r_zp, c_zp = 117, 128 if (res or f32) else 0, 0, 0
+    xq = rng.integers(0, 256, size=(n, cin, h, w), dtype=np.uint8)
+    wq = rng.integers(-127, 128, size=(cout, cin, k, k), dtype=np.int8)
+    bq = rng.integers(-20000, 20000, size=cout, dtype=np.int32)
+    x_scale, y_scale = np.float32(0.021), np.float32(0.043)
+    w_scale = (rng.random(cout).astype(np.float32) + np.float32(0.5)) * np.float32(y_scale / x_scale / (40.0 * np.sqrt(cin * k * k)))
+    stats = []
+    yq = qlinear.qlinear_conv(xq, x_scale, np.uint8(x_zp), wq, w_scale, np.zeros(cout, np.int8), y_scale, np.uint8(y_zp), bq, stride, pad, dil, stats)
+    assert stats[0] < 2**24                      # the exactness condition of the fp16-operand representation
+    quant = {"qmul": (x_scale * w_scale) / y_scale, "q_lo": -y_zp, "q_hi": 255 - y_zp}
+    expect = yq.astype(np.int32) - y_zp
+    rq = None
+    if res:
+        rq = rng.integers(0, 256, size=yq.shape, dtype=np.uint8)
+        r_scale, c_scale = np.float32(0.017), np.float32(0.031)
+        cq = qlinear.qlinear_add(yq, y_scale, np.uint8(y_zp), rq, r_scale, np.uint8(r_zp), c_scale, np.uint8(c_zp))
+        quant.update(q_ra=y_scale / c_scale, q_rb=r_scale / c_scale, q_lo2=-c_zp, q_hi2=255 - c_zp)
+        expect = cq.astype(np.int32) - c_zp
+    if f32:
+        quant["q_deq"] = y_scale
+        expect = qlinear.dequantize_linear(yq, y_scale, np.uint8(y_zp))
+    xc = (xq.astype(np.int32) - x_zp).transpose(0, 2, 3, 1)              # NHWC, centred: what the engine stores
+    wc = wq.astype(np.int32).transpose(0, 2, 3, 1)
+    rc = (rq.astype(np.int32) - r_zp).transpose(0, 2, 3, 1) if res else None
+    y = handle.conv_test(xc, wc, bq.astype(np.float32), rc, stride, pad, dil, relu=False, impl=impl, f32_out=f32, quant=quant)
+    got = y.astype(np.float32).transpose(0, 3, 1, 2)
+    assert got.shape == expect.shape
+    bad = got != expect.astype(np.float32)
+    assert not bad.any(), f"{bad.sum()} of {bad.size} outputs differ; first at {np.argwhere(bad)[0]}: got {got[bad][0]} want {expect[bad][0]}"
+    assert len(np.unique(expect)) > 32           # the case exercises the whole range, not a saturated constant
+
+
+@pytest.fixture(scope="module")
+def tiny_int8():
+    return quantize.ensure_fixture("fcn_tiny_int8")
+
+
+def test_quantised_model_info(handle, tiny_int8):
+    handle.model_load(tiny_int8)
+    info = handle.model_info()
+    assert info.input_names == ["input"] and info.output_names == ["out"] and info.input0_dtype == "Float"
+
+
+@pytest.mark.parametrize("w,h", [(128, 96), (320, 240), (200, 136)])
+def test_quantised_model_lowres_bit_exact(handle, tiny_int8, w, h):
+    handle.model_load(tiny_int8)
+    g = onnx_min.load(tiny_int8)
+    frame = synth.synth_frame(w, h, 3)
+    env = qlinear.run(g, oracle.preprocess_f32(frame)[None])
+    assert env["__max_abs_acc__"] < 2**24
+    want = env[qlinear.lowres_name(g)][0]
+    got = handle.model_lowres(frame)
+    assert got.shape == want.shape
+    assert (got == want).all(), f"{(got != want).sum()} of {got.size} low-resolution logits differ (max {np.abs(got - want).max()})"
+
+
+def test_quantised_pipeline_vs_oracle(handle, tiny_int8):
+    from test_gpu_pipeline import check_against_oracle
+    g = onnx_min.load(tiny_int8)
+    pipe = P.GpuPipeline(handle)
+    pipe.control(("Model", tiny_int8))
+    pipe.control(("Scale", 0.5))
+    frame = synth.synth_frame(640, 480, 5)
+    out = pipe.advance(P.Frame(3, frame))
+    scaled = oracle.scale_nearest(frame, 0.5)
+    env = qlinear.run(g, oracle.preprocess_f32(scaled)[None])
+    logits = env["out"][0]
+    klass, rgba = oracle.color_code_image(logits)
+    ref = {"class_map": klass.astype(np.uint8), "logits": logits, "decoded_rgba": rgba}
+    assert out.id == 3 and out.size == [320, 240]
+    assert (out.buffer == oracle.frame_rgba(scaled)).all()
+    match = check_against_oracle(out.class_map, out.decoded_buffer, ref, 0.999)
+    assert match > 0.999
+    pipe.control(("Scale", 1.0))
+
+
+def test_quantised_batch_matches_single(handle, tiny_int8):
+    handle.model_load(tiny_int8)
+    frames = np.stack([synth.synth_frame(320, 240, i) for i in range(8)])
+    res = handle.advance_batch(frames, ids=list(range(1, 9)))
+    one = handle.advance(frames[5], id=6)
+    assert (res[5]["class_map"] == one["class_map"]).all() and (res[5]["decoded_rgba"] == one["decoded_rgba"]).all()

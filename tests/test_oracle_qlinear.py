@@ -1,0 +1,125 @@
+"""Quantised-model oracle (oracle/qlinear.py) against the examples of the ONNX operator specification, the fixture
+writer -> reader round trip, and the product's C++ lowering of QOperator graphs (CPU only: onnx_describe needs no GPU)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from infur_b200 import _lib as L
+from infur_b200 import onnx_write as W
+from infur_b200 import quantize
+from oracle import onnx_min, qlinear
+
+
+def test_quantize_linear_spec_example():
+    # ONNX QuantizeLinear example: scale 2, zero point 128
+    x = np.array([0, 2, 3, 1000, -254, -1000], dtype=np.float32)
+    y = qlinear.quantize_linear(x, np.float32(2), np.uint8(128))
+    assert y.tolist() == [128, 129, 130, 255, 1, 0]      # 3 / 2 = 1.5 rounds to even (2)
+
+
+def test_dequantize_linear_spec_example():
+    x = np.array([0, 3, 128, 255], dtype=np.uint8)
+    y = qlinear.dequantize_linear(x, np.float32(2), np.uint8(128))
+    assert y.tolist() == [-256.0, -250.0, 0.0, 254.0]
+
+
+def test_qlinear_conv_spec_example_row():
+    # first row of the ONNX QLinearConv example (1x1 kernel w = 0, w_zp = 255: y = -(x - 132) * 255 * s + 123 with
+    # s = x_scale * w_scale / y_scale = 1 / 255)
+    x = np.array([[[[255, 174, 162, 25, 203, 168, 58]]]], dtype=np.uint8)
+    w = np.array([[[[0]]]], dtype=np.uint8)
+    y = qlinear.qlinear_conv(x, np.float32(0.00369204697), np.uint8(132), w, np.array([0.00172794575], np.float32), np.array([255], np.uint8),
+                             np.float32(0.00162681262), np.uint8(123))
+    assert y[0, 0, 0].tolist() == [0, 81, 93, 230, 52, 87, 197]
+
+
+def test_qlinear_conv_padding_bias_and_saturation():
+    # 3x3, pad 1: the padded border contributes (x_zp - x_zp) = 0; bias is int32 in units of x_scale * w_scale
+    x = np.full((1, 1, 3, 3), 12, dtype=np.uint8)
+    w = np.ones((1, 1, 3, 3), dtype=np.int8)
+    y = qlinear.qlinear_conv(x, np.float32(1), np.uint8(10), w, np.array([1], np.float32), np.array([0], np.int8), np.float32(1), np.uint8(0),
+                             bias=np.array([5], np.int32), pad=1)
+    assert y[0, 0].tolist() == [[13, 17, 13], [17, 23, 17], [13, 17, 13]]     # 2 * taps inside + 5
+    y = qlinear.qlinear_conv(x, np.float32(1), np.uint8(10), w, np.array([1], np.float32), np.array([0], np.int8), np.float32(0.05), np.uint8(0), pad=1)
+    assert y.max() == 255 and y.dtype == np.uint8                               # saturates
+    y = qlinear.qlinear_conv(x, np.float32(1), np.uint8(10), -w, np.array([1], np.float32), np.array([0], np.int8), np.float32(1), np.uint8(3), pad=1)
+    assert y[0, 0].tolist() == [[0, 0, 0], [0, 0, 0], [0, 0, 0]]                # negative sums clamp at 0 (the folded ReLU)
+
+
+def test_qlinear_add_hand_computed():
+    a = np.array([[[[10, 200, 130]]]], dtype=np.uint8)
+    b = np.array([[[[0, 255, 7]]]], dtype=np.uint8)
+    # (a - 128) * 0.5 / 0.25 + (b - 0) * 0.125 / 0.25 = 2 (a - 128) + b / 2, + zero point 3
+    y = qlinear.qlinear_add(a, np.float32(0.5), np.uint8(128), b, np.float32(0.125), np.uint8(0), np.float32(0.25), np.uint8(3))
+    # -236 saturates to 0; 144 + 127.5 saturates to 255; 4 + 3.5 = 7.5 rounds half to even = 8, + 3 = 11
+    assert y[0, 0, 0].tolist() == [0, 255, 11]
+
+
+def _describe(path_or_bytes, tmp_path):
+    lib = L.load()
+    if isinstance(path_or_bytes, (bytes, bytearray)):
+        p = os.path.join(tmp_path, "m.onnx")
+        with open(p, "wb") as f:
+            f.write(path_or_bytes)
+    else:
+        p = path_or_bytes
+    buf = C.create_string_buffer(1 << 16)
+    need = C.c_size_t()
+    rc = lib.infur_b200_onnx_describe(p.encode(), buf, len(buf), C.byref(need))
+    return rc, buf.value.decode()
+
+
+def test_fixture_round_trip_and_lowering(tmp_path):
+    path = quantize.ensure_fixture("fcn_tiny_int8")
+    g = onnx_min.load(path)
+    ops = [n.op for n in g.nodes]
+    assert ops.count("QLinearConv") == 19 and ops.count("QLinearAdd") == 4 and ops[0] == "QuantizeLinear"
+    assert g.inputs == [("input", 1, ["batch", 3, "height", "width"])]
+    assert [n.domain for n in g.nodes if n.op == "QLinearAdd"] == ["com.microsoft"] * 4
+    rc, text = _describe(path, str(tmp_path))
+    assert rc == 0, text
+    assert "quantised(zp=" in text and text.count(" conv ") == 19 and text.count(" add[") == 4 and text.count(" deq") == 1
+    assert "head out" in text and "classes=21" in text
+
+
+def _tiny_graph(mid_quantize=False, bad_scale=False, float_conv=False):
+    """input -> QuantizeLinear -> QLinearConv(3->64 7x7 s2) -> DequantizeLinear -> Resize."""
+    inits = {
+        "xs": np.array(0.02, np.float32), "xz": np.array(100, np.uint8),
+        "w": np.ones((64, 3, 7, 7), np.int8), "ws": np.full(64, 0.01, np.float32), "wz": np.zeros(64, np.int8),
+        "ys": np.array(0.1, np.float32), "yz": np.array(0, np.uint8), "b": np.zeros(64, np.int32),
+        "xs2": np.array(0.03, np.float32),
+        "c0": np.array([0], np.int64), "c2": np.array([2], np.int64), "c4": np.array([4], np.int64),
+    }
+    nodes = [W.node("QuantizeLinear", ["input", "xs", "xz"], ["x"])]
+    src = "x"
+    if mid_quantize:
+        nodes += [W.node("DequantizeLinear", ["x", "xs", "xz"], ["xf"]), W.node("QuantizeLinear", ["xf", "xs", "xz"], ["x2"])]
+        src = "x2"
+    nodes.append(W.node("QLinearConv", [src, "xs2" if bad_scale else "xs", "xz", "w", "ws", "wz", "ys", "yz", "b"], ["y"], kernel_shape=[7, 7],
+                        strides=[2, 2], pads=[3, 3, 3, 3]))
+    nodes += [
+        W.node("DequantizeLinear", ["y", "ys", "yz"], ["yf"]),
+        W.node("Shape", ["input"], ["ish"]), W.node("Slice", ["ish", "c2", "c4", "c0"], ["hw"]),
+        W.node("Shape", ["yf"], ["lsh"]), W.node("Slice", ["lsh", "c0", "c2", "c0"], ["nc"]),
+        W.node("Concat", ["nc", "hw"], ["sizes"], axis=0),
+        W.node("Resize", ["yf", "", "", "sizes"], ["out"], mode="linear", coordinate_transformation_mode="half_pixel"),
+    ]
+    return W.model(nodes, inits, [W.value_info("input", W.FLOAT, ["n", 3, "h", "w"])], [W.value_info("out", W.FLOAT, ["n", 64, "h", "w"])],
+                   opsets=(("", 12), ("com.microsoft", 1)))
+
+
+def test_lowering_accepts_minimal_quantised_graph(tmp_path):
+    rc, text = _describe(_tiny_graph(), str(tmp_path))
+    assert rc == 0 and "q[0,255] deq" in text, text
+    env = qlinear.run(onnx_min.load(_tiny_graph()), np.zeros((1, 3, 16, 16), np.float32))
+    assert env["out"].shape == (1, 64, 16, 16)
+
+
+def test_lowering_rejects_requantising_edges(tmp_path):
+    rc, text = _describe(_tiny_graph(bad_scale=True), str(tmp_path))
+    assert rc == L.E_MODEL_LOAD and "differ from its producer" in text, text
+    rc, text = _describe(_tiny_graph(mid_quantize=True), str(tmp_path))
+    assert rc == L.E_MODEL_LOAD, text

@@ -18,6 +18,7 @@ CASES = {
     "l1_conv3": (270, 480, 64, 256, 1, 1, 0, 1, True, True),
     "l1_down": (270, 480, 64, 256, 1, 1, 0, 1, False, False),
     "l2_conv3": (135, 240, 128, 512, 1, 1, 0, 1, True, True),
+    "l1_conv1a": (270, 480, 64, 64, 1, 1, 0, 1, True, False),
     "l1_conv2": (270, 480, 64, 64, 3, 1, 1, 1, True, False),
     "l2_conv2": (135, 240, 128, 128, 3, 1, 1, 1, True, False),
     "l3_conv1": (135, 240, 1024, 256, 1, 1, 0, 1, True, False),
