@@ -88,7 +88,7 @@ struct Sched2 {   // one CTA pair per (two consecutive M tiles, one N tile); an 
 };
 
 // Direct-store epilogue (f32 logit head): thread = output pixel, 32 channels at a time.
-template <int BLOCK_N, int ACC>
+template <int BLOCK_N, int ACC, bool QUANT>
 __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int quad, int lane,
                                                 int row) {
   const int bw_log2 = g.bw_log2;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
           v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
         }
         const size_t off = pix * (size_t)g.out_ld + (size_t)(n0 + c0);
-        if (g.quant) {   // QLinearConv requantisation (ConvTcGeom::quant)
+        if (QUANT) {   // QLinearConv requantisation (ConvTcGeom::quant)
           const float4* m4 = reinterpret_cast<const float4*>(g.qmul + n0 + c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -142,7 +142,7 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float2 f = __half22float2(h[q]);
-              if (g.quant) {   // QLinearAdd
+              if (QUANT) {   // QLinearAdd
                 v[8 * j + 2 * q] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[8 * j + 2 * q], g.q_ra), __fmul_rn(f.x, g.q_rb))), g.q_lo2), g.q_hi2);
                 v[8 * j + 2 * q + 1] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[8 * j + 2 * q + 1], g.q_ra), __fmul_rn(f.y, g.q_rb))), g.q_lo2), g.q_hi2);
               } else {
@@ -157,7 +157,7 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (g.out_f32 != nullptr) {
-          if (g.quant && g.q_deq != 0.f) {   // DequantizeLinear of the logits
+          if (QUANT && g.q_deq != 0.f) {   // DequantizeLinear of the logits
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], g.q_deq);
           }
@@ -191,7 +191,7 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 // announces its part through the chunk_ready mbarrier and moves on.
 struct EpiBars { uint32_t res, ready, free_; };
 
-template <int BLOCK_N, int ACC, bool HAS_RES, class Sched, bool PAIR = false, int EB = 4>
+template <int BLOCK_N, int ACC, bool HAS_RES, bool QUANT, class Sched, bool PAIR = false, int EB = 4>
 __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sched, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                              const EpiBars eb, uint32_t epi_base, int ew, int lane) {
   constexpr int CH = BLOCK_N / 64;            // chunks per tile
@@ -218,7 +218,7 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
 #pragma unroll
         for (int j = 0; j < 8; ++j) bias[j] = __ldg(b4 + j);
       }
-      if (g.quant) {
+      if (QUANT) {
         const float4* m4 = reinterpret_cast<const float4*>(g.qmul + n0 + c * 64 + half * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) qm[j] = __ldg(m4 + j);
@@ -256,7 +256,7 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
         // the scalar f32 operations they replace
         ptx::add_f32x2(v[0], v[1], bl.x, bl.y); ptx::add_f32x2(v[2], v[3], bl.z, bl.w);
         ptx::add_f32x2(v[4], v[5], bh.x, bh.y); ptx::add_f32x2(v[6], v[7], bh.z, bh.w);
-        if (g.quant) {
+        if (QUANT) {
           // quantised layer: v is the exact integer accumulator + bias; requantise like QLinearConv, then (HAS_RES) add the
           // residual like QLinearAdd.  Separate f32 multiplies and adds (no FMA contraction), round half to even.
           const float4 ml = qm[2 * j], mh = qm[2 * j + 1];
@@ -338,7 +338,7 @@ __device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvT
   ptx::tma_store_wait<0>();
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool QUANT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   using C = Cfg<BLOCK_N>;
@@ -465,13 +465,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     // ===================== epilogue =====================
     const int ew = warp - kEpiWarp0;         // ew % 4 == warp % 4: the TMEM lane quadrant this warp may read
     if (g.store_mode == 0) {
-      if (ew < 4) epilogue_direct<BLOCK_N, C::kAcc>(g, tmem_base, tfull_bar(0), tempty_bar(0), ew, lane, ew * 32 + lane);
+      if (ew < 4) epilogue_direct<BLOCK_N, C::kAcc, QUANT>(g, tmem_base, tfull_bar(0), tempty_bar(0), ew, lane, ew * 32 + lane);
     } else if constexpr (BLOCK_N >= 64) {
       const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
       if (g.store_mode == 1) {
-        if (g.epi_bufs == 4) epilogue_tma<BLOCK_N, C::kAcc, false, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-        else epilogue_tma<BLOCK_N, C::kAcc, false, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-      } else epilogue_tma<BLOCK_N, C::kAcc, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+        if (g.epi_bufs == 4) epilogue_tma<BLOCK_N, C::kAcc, false, QUANT, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+        else epilogue_tma<BLOCK_N, C::kAcc, false, QUANT, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      } else epilogue_tma<BLOCK_N, C::kAcc, true, QUANT, Sched1>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
     }
   }
 
@@ -501,6 +501,7 @@ __host__ __device__ constexpr int pair_stages(int epi_bufs) {
 }
 __host__ __device__ constexpr int pair_smem_bytes(int epi_bufs) { return pair_stages(epi_bufs) * kPairStageBytes + epi_bufs * kEpiBufBytes + 1024 + kBarBytes; }
 
+template <bool QUANT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   constexpr int BLOCK_N = 256;
@@ -610,8 +611,8 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
     }
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;
-    if (g.store_mode == 1) epilogue_tma<BLOCK_N, ACC, false, Sched2, true, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-    else epilogue_tma<BLOCK_N, ACC, true, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    if (g.store_mode == 1) epilogue_tma<BLOCK_N, ACC, false, QUANT, Sched2, true, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    else epilogue_tma<BLOCK_N, ACC, true, QUANT, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
   }
 
   ptx::tc_fence_before();
@@ -661,7 +662,7 @@ struct HaloCfg {
   static constexpr int kTmemCols = kAcc * BLOCK_N;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool QUANT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   using C = HaloCfg<BLOCK_N>;
@@ -777,8 +778,8 @@ conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
       else epilogue_dma<BLOCK_N, false, Sched1, 2>(maps, g, sched, eb, epi_base);
     }
   } else if (warp >= kEpiWarp0) {
-    if (hp.epi_bufs == 2) epilogue_tma<BLOCK_N, ACC, false, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
-    else epilogue_tma<BLOCK_N, ACC, false, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
+    if (hp.epi_bufs == 2) epilogue_tma<BLOCK_N, ACC, false, QUANT, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
+    else epilogue_tma<BLOCK_N, ACC, false, QUANT, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
   }
 
   ptx::tc_fence_before();
@@ -804,6 +805,7 @@ constexpr int kStemTxBytes = 7 * kStemRowBytes;
 constexpr int kStemStages = 8;
 constexpr int kStemSmemBytes = kStemStages * kStemStageBytes + 4 * kEpiBufBytes + kStemWBytes + 1024 + kBarBytes;
 
+template <bool QUANT>
 __global__ void __launch_bounds__(kThreads, 1)
 stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   constexpr int BLOCK_N = 64;
@@ -898,7 +900,7 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   } else if (warp == kDmaWarp) {
     if (ptx::elect_one()) epilogue_dma<BLOCK_N, false, Sched1, 4>(maps, g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, eb, epi_base);
   } else if (warp >= kEpiWarp0) {
-    epilogue_tma<BLOCK_N, ACC, false, Sched1, false, 4>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
+    epilogue_tma<BLOCK_N, ACC, false, QUANT, Sched1, false, 4>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
                                  warp - kEpiWarp0, lane);
   }
 
@@ -915,7 +917,8 @@ cudaError_t launch_one(const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms,
   const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
   if (grid <= 0) return cudaSuccess;
   if (g.stages != Cfg<BLOCK_N>::stages(g.epi_bufs) || (g.store_mode != 0 && BLOCK_N < 64)) return cudaErrorInvalidValue;
-  conv_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream>>>(maps, g);
+  if (g.quant) conv_tc_kernel<BLOCK_N, true><<<grid, kThreads, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream>>>(maps, g);
+  else conv_tc_kernel<BLOCK_N, false><<<grid, kThreads, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream>>>(maps, g);
   return cudaGetLastError();
 }
 
@@ -933,17 +936,18 @@ int conv_tc_stages(int block_n, int epi_bufs) {
 }
 
 cudaError_t conv_tc_init() {
-  cudaError_t e;
-  if ((e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
-  return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  auto opt_in = [&](auto kernel, int bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
+  opt_in(conv_tc_kernel<32, false>, kSmemLimit); opt_in(conv_tc_kernel<32, true>, kSmemLimit);
+  opt_in(conv_tc_kernel<64, false>, kSmemLimit); opt_in(conv_tc_kernel<64, true>, kSmemLimit);
+  opt_in(conv_tc_kernel<128, false>, kSmemLimit); opt_in(conv_tc_kernel<128, true>, kSmemLimit);
+  opt_in(conv_tc_kernel<256, false>, kSmemLimit); opt_in(conv_tc_kernel<256, true>, kSmemLimit);
+  opt_in(stem_tc_kernel<false>, kStemSmemBytes); opt_in(stem_tc_kernel<true>, kStemSmemBytes);
+  opt_in(conv_halo_kernel<64, false>, kSmemLimit); opt_in(conv_halo_kernel<64, true>, kSmemLimit);
+  opt_in(conv_halo_kernel<128, false>, kSmemLimit); opt_in(conv_halo_kernel<128, true>, kSmemLimit);
+  opt_in(conv_halo_kernel<256, false>, kSmemLimit); opt_in(conv_halo_kernel<256, true>, kSmemLimit);
+  opt_in(conv_tc_pair_kernel<false>, kSmemLimit); opt_in(conv_tc_pair_kernel<true>, kSmemLimit);
+  return e;
 }
 
 cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream) {
@@ -951,7 +955,8 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
     if (block_n != 64 || g.store_mode != 1 || g.bw_log2 != 7) return cudaErrorInvalidValue;
-    stem_tc_kernel<<<grid, kThreads, kStemSmemBytes, stream>>>(maps, g);
+    if (g.quant) stem_tc_kernel<true><<<grid, kThreads, kStemSmemBytes, stream>>>(maps, g);
+    else stem_tc_kernel<false><<<grid, kThreads, kStemSmemBytes, stream>>>(maps, g);
     return cudaGetLastError();
   }
   if (g.halo) {
@@ -959,9 +964,18 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     if (grid <= 0) return cudaSuccess;
     if (g.store_mode != 1 || g.bw_log2 != 3 || g.main_taps != 9 || g.num_taps != 9) return cudaErrorInvalidValue;
     switch (block_n) {
-      case 64: conv_halo_kernel<64><<<grid, kThreads, halo_plan(g.halo_dil, 64).smem_bytes, stream>>>(maps, g); break;
-      case 128: conv_halo_kernel<128><<<grid, kThreads, halo_plan(g.halo_dil, 128).smem_bytes, stream>>>(maps, g); break;
-      case 256: conv_halo_kernel<256><<<grid, kThreads, halo_plan(g.halo_dil, 256).smem_bytes, stream>>>(maps, g); break;
+      case 64:
+        if (g.quant) conv_halo_kernel<64, true><<<grid, kThreads, halo_plan(g.halo_dil, 64).smem_bytes, stream>>>(maps, g);
+        else conv_halo_kernel<64, false><<<grid, kThreads, halo_plan(g.halo_dil, 64).smem_bytes, stream>>>(maps, g);
+        break;
+      case 128:
+        if (g.quant) conv_halo_kernel<128, true><<<grid, kThreads, halo_plan(g.halo_dil, 128).smem_bytes, stream>>>(maps, g);
+        else conv_halo_kernel<128, false><<<grid, kThreads, halo_plan(g.halo_dil, 128).smem_bytes, stream>>>(maps, g);
+        break;
+      case 256:
+        if (g.quant) conv_halo_kernel<256, true><<<grid, kThreads, halo_plan(g.halo_dil, 256).smem_bytes, stream>>>(maps, g);
+        else conv_halo_kernel<256, false><<<grid, kThreads, halo_plan(g.halo_dil, 256).smem_bytes, stream>>>(maps, g);
+        break;
       default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -970,7 +984,8 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     const int clusters = g.num_work < num_sms / 2 ? g.num_work : num_sms / 2;
     if (clusters <= 0) return cudaSuccess;
     if (block_n != 256 || g.store_mode == 0 || g.stages != pair_stages(g.epi_bufs)) return cudaErrorInvalidValue;
-    conv_tc_pair_kernel<<<2 * clusters, kThreads, pair_smem_bytes(g.epi_bufs), stream>>>(maps, g);
+    if (g.quant) conv_tc_pair_kernel<true><<<2 * clusters, kThreads, pair_smem_bytes(g.epi_bufs), stream>>>(maps, g);
+    else conv_tc_pair_kernel<false><<<2 * clusters, kThreads, pair_smem_bytes(g.epi_bufs), stream>>>(maps, g);
     return cudaGetLastError();
   }
   switch (block_n) {
