@@ -135,13 +135,37 @@ def cpu_pipeline_fps(frames: np.ndarray, model, threads: int, reps: int) -> tupl
     return 1.0 / med, med
 
 
+def cpu_int8_frame(graph, bgr: np.ndarray):
+    """One frame through the quantised restatement (oracle/qlinear.py): Scale 1.0 -> pre-process -> integer-exact QOperator
+    interpreter (torch-CPU f64 convolutions of integers) -> Resize -> ColorCode.  --model int8 only."""
+    import oracle
+    from oracle import qlinear
+
+    scaled = oracle.scale_nearest(bgr, 1.0)
+    env = qlinear.run(graph, oracle.preprocess_f32(scaled)[None])
+    oracle.color_code_image(env[graph.outputs[0][0]][0])
+    oracle.frame_rgba(scaled)
+
+
+def model_fixture(args):
+    """(path, label, dtype) of the benchmarked network: FCN-ResNet50 fp16 (BASELINE configs[1..4]) or, with --model int8, its
+    QOperator-quantised form (the kind of file configs[0] names)."""
+    from infur_b200 import quantize, synth
+
+    if args.model == "int8":
+        return quantize.ensure_fixture("fcn50_int8"), "FCN-ResNet50 int8 (QOperator: QLinearConv / QLinearAdd; seeded synthetic weights, statically quantised)", "int8"
+    path = synth.fixture_path("fcn50")
+    if not os.path.exists(path):
+        synth.ensure_fixture("fcn50")
+    return path, "FCN-ResNet50 (seeded synthetic weights in an opset-12 .onnx)", "f16"
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     from infur_b200 import synth
 
     cores = os.cpu_count() or 1
-    _, model = synth.ensure_fixture("fcn50")
     frames = np.stack([synth.synth_frame(W, H, i) for i in range(2)])
     import torch
     import torch.nn.functional as F
@@ -149,9 +173,17 @@ def run_reference(args, rank: int, world: int):
     import oracle
 
     torch.set_num_threads(cores)
-    model.eval()
+    int8 = args.model == "int8"
+    if int8:
+        from oracle import onnx_min
+        graph = onnx_min.load(model_fixture(args)[0])
+    else:
+        _, model = synth.ensure_fixture("fcn50")
+        model.eval()
 
     def one(i):
+        if int8:
+            return cpu_int8_frame(graph, frames[i % len(frames)])
         with torch.no_grad():
             bgr = frames[i % len(frames)]
             scaled = oracle.scale_nearest(bgr, 1.0)
@@ -175,12 +207,13 @@ def run_reference(args, rank: int, world: int):
     dt = time.perf_counter() - t0
     fps = done / dt
     args.steps_timed = done
-    sample = f"{done} single 1920x1080 frames (one frame per step; {args.steps} requested, bounded to {args.cpu_budget_s:.0f} s), torch-CPU fp32 FCN-ResNet50 both heads + numpy Scale/ColorCode"
+    what = "integer-exact QOperator interpreter (torch-CPU f64 convolutions)" if int8 else "torch-CPU fp32 FCN-ResNet50 both heads"
+    sample = f"{done} single 1920x1080 frames (one frame per step; {args.steps} requested, bounded to {args.cpu_budget_s:.0f} s), {what} + numpy Scale/ColorCode"
     print(json.dumps({
         "impl": "reference", "metric": "1080p frames/sec through FCN-ResNet50", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "steps_timed": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1080p synthetic stream, FCN-ResNet50 (seeded synthetic weights), scale 1.0; CPU restatement of the reference's "
+        "vs_baseline": None, "dtype": "int8" if int8 else "f32", "data": "synthetic",
+        "config": {"workload": "1080p synthetic stream, " + model_fixture(args)[1] + ", scale 1.0; CPU restatement of the reference's "
                                "onnxruntime path (the reference itself cannot be built here: no Rust/onnxruntime/model file)", "frames_per_step": 1},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -208,10 +241,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             dist.barrier()
 
     B = args.batch
-    path = synth.fixture_path("fcn50")
-    if rank == 0 and not os.path.exists(path):
-        synth.ensure_fixture("fcn50")
+    if rank == 0:
+        model_fixture(args)
     barrier()
+    path, model_label, dtype = model_fixture(args)
 
     h = P.Handle(device=local_rank, max_batch=B, ring_depth=args.ring_depth)
     # weights: rank 0 packs + uploads, every other rank receives the packed arena over NCCL (init only)
@@ -318,10 +351,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         roofline = {
             "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv+bias+ReLU(+residual)), all %d launches of one step" % n_conv,
             "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": CONV_DRAM_BYTES_PER_LAUNCH,
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of one step (8 frames) / launches, from "
-                            "profiles/r1_launches_step_b8_1080p.csv; algorithmic bytes per launch = 8 x 3546.9 MB (layer-wise, shortcuts fused) / launches",
-            "algorithmic_bytes_per_launch": B * 3546.9e6 / n_conv,
+            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": CONV_DRAM_BYTES_PER_LAUNCH if args.model == "f16" else None,
+            "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of one step (8 frames) / launches, from "
+                             "profiles/r1_launches_step_b8_1080p.csv; algorithmic bytes per launch = 8 x 3546.9 MB (layer-wise, shortcuts fused) / launches")
+                            if args.model == "f16" else "no ncu capture of the quantised plan yet; algorithmic bytes per launch from plan_text",
+            "algorithmic_bytes_per_launch": (B * 3546.9e6 if args.model == "f16" else
+                                             1e6 * sum(float(ln.split(" MB ")[1]) for ln in op_lines if ln.startswith("conv "))) / n_conv,
             "flops_per_launch_avg": flops / n_conv, "ms_per_launch_avg": conv_ms / n_conv, "ms_all_launches": conv_ms,
             "peak_source": pk["source"] + " (sustained cuBLAS bf16: the kernel is timed inside a long step)",
         }
@@ -334,7 +369,19 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                  hbm("maxpool_kernel (3x3/s2, NHWC fp16)", 66.3552 + 16.5888, pool_ms),
                  hbm("post_kernel (bilinear x8 upsample + argmax + colour)", 2.7216 + 8.2944 + 2.0736, post_ms)]
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.model == "int8":
+            import torch as _t
+            from oracle import onnx_min
+            cores = os.cpu_count() or 1
+            _t.set_num_threads(cores)
+            graph = onnx_min.load(path)
+            t0 = time.perf_counter()
+            cpu_int8_frame(graph, base[0])
+            sec = time.perf_counter() - t0
+            cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": f"1 single 1920x1080 frame ({sec:.1f} s); oracle port: integer-exact QOperator interpreter (torch-CPU f64 convolutions) "
+                             "+ numpy Scale/ColorCode"}
+        elif not args.no_cpu_baseline:
             _, model = synth.ensure_fixture("fcn50")
             cores = os.cpu_count() or 1
             fps_cpu, sec = cpu_pipeline_fps(base[:2], model, cores, reps=args.cpu_frames)
@@ -344,9 +391,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         out = {
             "metric": "1080p frames/sec through FCN-ResNet50", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "configs[2]: 1080p synthetic stream, batch=8 frames per step per GPU, FCN-ResNet50 (seeded synthetic weights "
-                                   "in an opset-12 .onnx), scale 1.0, out head only, class map + premultiplied RGBA out",
+            "dtype": dtype if dtype == "f16" else "int8 (integers carried exactly in f16 tensor-core operands, f32 accumulators < 2^24)", "data": "synthetic",
+            "config": {"workload": "configs[2]: 1080p synthetic stream, batch=8 frames per step per GPU, " + model_label +
+                                   ", scale 1.0, out head only, class map + premultiplied RGBA out",
                        "frames_per_step_per_gpu": B, "width": W, "height": H, "ring_depth": depth, "sharding": "frames by rank, no collective",
                        "l2": "inputs cycle through 4 x 8 distinct frames (199 MB) and each step streams > 30 GB of activations: larger than L2"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": world * B * W * H * 3, "d2h_bytes_per_step": world * B * W * H * 5,
@@ -368,6 +415,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="f16", choices=["f16", "int8"], help="f16: BASELINE configs[1..4] (default); int8: the QOperator-quantised network")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--ring-depth", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=3)

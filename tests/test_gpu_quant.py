@@ -120,3 +120,25 @@ def test_quantised_batch_matches_single(handle, tiny_int8):
     res = handle.advance_batch(frames, ids=list(range(1, 9)))
     one = handle.advance(frames[5], id=6)
     assert (res[5]["class_map"] == one["class_map"]).all() and (res[5]["decoded_rgba"] == one["decoded_rgba"]).all()
+
+
+def test_quantised_fcn50_config1(handle):
+    """configs[0] analogue on the kind of model the reference's tests load (int8 FCN-ResNet50, 320x240): the low-resolution
+    logits of all 53 quantised convolutions + 16 quantised adds are bit-exact, the class map follows."""
+    from test_gpu_pipeline import check_against_oracle
+    path = quantize.ensure_fixture("fcn50_int8")
+    g = onnx_min.load(path)
+    handle.model_load(path)
+    handle.scale_control(1.0)
+    frame = synth.synth_frame(320, 240, 7)
+    env = qlinear.run(g, oracle.preprocess_f32(frame)[None])
+    assert env["__max_abs_acc__"] < 2**24
+    got = handle.model_lowres(frame)
+    want = env[qlinear.lowres_name(g)][0]
+    assert (got == want).all(), f"{(got != want).sum()} of {got.size} low-resolution logits differ"
+    out = handle.advance(frame, id=1)
+    logits = env["out"][0]
+    klass, rgba = oracle.color_code_image(logits)
+    ref = {"class_map": klass.astype(np.uint8), "logits": logits, "decoded_rgba": rgba}
+    check_against_oracle(out["class_map"], out["decoded_rgba"], ref, 0.999)
+    assert len(np.unique(out["class_map"])) >= 8
