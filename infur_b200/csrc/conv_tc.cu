@@ -87,6 +87,16 @@ struct Sched2 {   // one CTA pair per (two consecutive M tiles, one N tile); an 
   __device__ __forceinline__ int count() const { return cluster < num_work ? (num_work - cluster + nclusters - 1) / nclusters : 0; }
 };
 
+// Round-half-even of a value already clamped to |v| <= 2^22, as two full-rate adds (the conversion instruction behind
+// rintf runs at a quarter of that rate and paced the epilogue of the HBM-bound quantised layers).  Clamping first is
+// equivalent: the clamp bounds are integers, so clamp(rne(v)) == rne(clamp(v)).
+constexpr float kRneMagic = 12582912.f;   // 1.5 * 2^23
+__device__ __forceinline__ float rne_small(float v) { return __fadd_rn(__fadd_rn(v, kRneMagic), -kRneMagic); }
+__device__ __forceinline__ float requant(float v, float m, float lo, float hi) { return rne_small(fminf(fmaxf(__fmul_rn(v, m), lo), hi)); }
+__device__ __forceinline__ float requant_add(float a, float ra, float b, float rb, float lo, float hi) {
+  return rne_small(fminf(fmaxf(__fadd_rn(__fmul_rn(a, ra), __fmul_rn(b, rb)), lo), hi));
+}
+
 // Direct-store epilogue (f32 logit head): thread = output pixel, 32 channels at a time.
 template <int BLOCK_N, int ACC, bool QUANT>
 __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int quad, int lane,
@@ -127,10 +137,10 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 m = __ldg(m4 + j);
-            v[4 * j + 0] = fminf(fmaxf(rintf(__fmul_rn(v[4 * j + 0], m.x)), g.q_lo), g.q_hi);
-            v[4 * j + 1] = fminf(fmaxf(rintf(__fmul_rn(v[4 * j + 1], m.y)), g.q_lo), g.q_hi);
-            v[4 * j + 2] = fminf(fmaxf(rintf(__fmul_rn(v[4 * j + 2], m.z)), g.q_lo), g.q_hi);
-            v[4 * j + 3] = fminf(fmaxf(rintf(__fmul_rn(v[4 * j + 3], m.w)), g.q_lo), g.q_hi);
+            v[4 * j + 0] = requant(v[4 * j + 0], m.x, g.q_lo, g.q_hi);
+            v[4 * j + 1] = requant(v[4 * j + 1], m.y, g.q_lo, g.q_hi);
+            v[4 * j + 2] = requant(v[4 * j + 2], m.z, g.q_lo, g.q_hi);
+            v[4 * j + 3] = requant(v[4 * j + 3], m.w, g.q_lo, g.q_hi);
           }
         }
         if (g.residual != nullptr) {
@@ -143,8 +153,8 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
             for (int q = 0; q < 4; ++q) {
               const float2 f = __half22float2(h[q]);
               if (QUANT) {   // QLinearAdd
-                v[8 * j + 2 * q] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[8 * j + 2 * q], g.q_ra), __fmul_rn(f.x, g.q_rb))), g.q_lo2), g.q_hi2);
-                v[8 * j + 2 * q + 1] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[8 * j + 2 * q + 1], g.q_ra), __fmul_rn(f.y, g.q_rb))), g.q_lo2), g.q_hi2);
+                v[8 * j + 2 * q] = requant_add(v[8 * j + 2 * q], g.q_ra, f.x, g.q_rb, g.q_lo2, g.q_hi2);
+                v[8 * j + 2 * q + 1] = requant_add(v[8 * j + 2 * q + 1], g.q_ra, f.y, g.q_rb, g.q_lo2, g.q_hi2);
               } else {
                 v[8 * j + 2 * q] += f.x;
                 v[8 * j + 2 * q + 1] += f.y;
@@ -262,14 +272,25 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
           const float4 ml = qm[2 * j], mh = qm[2 * j + 1];
           const float mm[8] = {ml.x, ml.y, ml.z, ml.w, mh.x, mh.y, mh.z, mh.w};
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = fminf(fmaxf(rintf(__fmul_rn(v[t], mm[t])), g.q_lo), g.q_hi);
+          for (int t = 0; t < 8; t += 2) {
+            ptx::mul_f32x2(v[t], v[t + 1], mm[t], mm[t + 1]);
+            v[t] = fminf(fmaxf(v[t], g.q_lo), g.q_hi); v[t + 1] = fminf(fmaxf(v[t + 1], g.q_lo), g.q_hi);
+            ptx::add_f32x2(v[t], v[t + 1], kRneMagic, kRneMagic);
+            ptx::add_f32x2(v[t], v[t + 1], -kRneMagic, -kRneMagic);
+          }
           if (HAS_RES) {
             const uint32_t rw[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&rw[t]));
-              v[2 * t] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[2 * t], g.q_ra), __fmul_rn(r.x, g.q_rb))), g.q_lo2), g.q_hi2);
-              v[2 * t + 1] = fminf(fmaxf(rintf(__fadd_rn(__fmul_rn(v[2 * t + 1], g.q_ra), __fmul_rn(r.y, g.q_rb))), g.q_lo2), g.q_hi2);
+              float a0 = v[2 * t], a1 = v[2 * t + 1], b0 = r.x, b1 = r.y;
+              ptx::mul_f32x2(a0, a1, g.q_ra, g.q_ra);
+              ptx::mul_f32x2(b0, b1, g.q_rb, g.q_rb);
+              ptx::add_f32x2(a0, a1, b0, b1);
+              a0 = fminf(fmaxf(a0, g.q_lo2), g.q_hi2); a1 = fminf(fmaxf(a1, g.q_lo2), g.q_hi2);
+              ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);
+              ptx::add_f32x2(a0, a1, -kRneMagic, -kRneMagic);
+              v[2 * t] = a0; v[2 * t + 1] = a1;
             }
           }
         } else if (HAS_RES) {

@@ -104,6 +104,12 @@ __device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float 
       : "+f"(a0), "+f"(a1)
       : "f"(b0), "f"(b1));
 }
+// (a0, a1) *= (b0, b1) as one FMUL2; each lane rounds like a scalar mul.rn.f32
+__device__ __forceinline__ void mul_f32x2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tmul.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
 // c + float(h) in one FHADD (the fp16 operand is converted exactly, one rounding)
 __device__ __forceinline__ float add_f32_f16(float c, unsigned short h) {
   float d;
