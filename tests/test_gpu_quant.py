@@ -142,3 +142,25 @@ def test_quantised_fcn50_config1(handle):
     ref = {"class_map": klass.astype(np.uint8), "logits": logits, "decoded_rgba": rgba}
     check_against_oracle(out["class_map"], out["decoded_rgba"], ref, 0.999)
     assert len(np.unique(out["class_map"])) >= 8
+
+
+def test_quantised_fcn50_1080p_full_size(handle):
+    """BASELINE's frame size: one 1080p frame through the quantised FCN-ResNet50, low-resolution logits bit-exact against the
+    integer oracle (about 20 s of CPU work), and frame 0 of a batch of 8 identical to the single-frame result."""
+    path = quantize.ensure_fixture("fcn50_int8")
+    g = onnx_min.load(path)
+    handle.model_load(path)
+    handle.scale_control(1.0)
+    frames = np.stack([synth.synth_frame(1920, 1080, i) for i in range(2)])
+    env = qlinear.run(g, oracle.preprocess_f32(frames[0])[None])
+    assert env["__max_abs_acc__"] < 2**24
+    got = handle.model_lowres(frames[0])
+    want = env[qlinear.lowres_name(g)][0]
+    assert got.shape == want.shape == (21, 135, 240)
+    assert (got == want).all(), f"{(got != want).sum()} of {got.size} low-resolution logits differ"
+    batch = np.ascontiguousarray(np.resize(frames, (8, 1080, 1920, 3)))
+    res = handle.advance_batch(batch, ids=list(range(1, 9)), want=("class_map", "decoded_rgba"))
+    one = handle.advance(frames[0], id=1, want=("class_map", "decoded_rgba"))
+    assert (res[0]["class_map"] == one["class_map"]).all() and (res[2]["decoded_rgba"] == one["decoded_rgba"]).all()
+    klass = env["out"][0].argmax(0)
+    assert (one["class_map"] == klass).mean() > 0.999
