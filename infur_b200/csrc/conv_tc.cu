@@ -23,6 +23,8 @@
 // Every variant accumulates the K blocks of an output element in the same (chunk-major) order: results are
 // bit-identical whichever variant the plan-time autotuner picks.
 #include "conv_tc.h"
+
+#include <cstdlib>
 #include "ptx.cuh"
 
 namespace infur {
@@ -406,6 +408,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  // everything above touched only this CTA's smem / TMEM: with a programmatic launch it overlaps the previous kernel's tail
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
@@ -570,6 +575,8 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
   ptx::tc_fence_before();
   ptx::cluster_sync();      // barrier inits and TMEM of both CTAs are in place before anything crosses the pair
   ptx::tc_fence_after();
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
@@ -733,6 +740,9 @@ conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  // everything above touched only this CTA's smem / TMEM: with a programmatic launch it overlaps the previous kernel's tail
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
@@ -874,6 +884,9 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  // everything above touched only this CTA's smem / TMEM: with a programmatic launch it overlaps the previous kernel's tail
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
@@ -933,14 +946,30 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   }
 }
 
+// Launch with programmatic stream serialization: the kernel may begin (prologue only, see grid_dep_wait) while the
+// previous kernel of the stream drains.  INFUR_B200_NO_PDL=1 turns it off.
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("INFUR_B200_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+template <class Kernel>
+cudaError_t launch_conv(Kernel kernel, int grid, int smem, cudaStream_t stream, const ConvTcMaps& maps, const ConvTcGeom& g) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, maps, g);
+}
+
 template <int BLOCK_N>
 cudaError_t launch_one(const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream) {
   const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
   if (grid <= 0) return cudaSuccess;
   if (g.stages != Cfg<BLOCK_N>::stages(g.epi_bufs) || (g.store_mode != 0 && BLOCK_N < 64)) return cudaErrorInvalidValue;
-  if (g.quant) conv_tc_kernel<BLOCK_N, true><<<grid, kThreads, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream>>>(maps, g);
-  else conv_tc_kernel<BLOCK_N, false><<<grid, kThreads, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream>>>(maps, g);
-  return cudaGetLastError();
+  if (g.quant) return launch_conv(conv_tc_kernel<BLOCK_N, true>, grid, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream, maps, g);
+  return launch_conv(conv_tc_kernel<BLOCK_N, false>, grid, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream, maps, g);
 }
 
 }  // namespace
@@ -976,9 +1005,8 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
     if (block_n != 64 || g.store_mode != 1 || g.bw_log2 != 7) return cudaErrorInvalidValue;
-    if (g.quant) stem_tc_kernel<true><<<grid, kThreads, kStemSmemBytes, stream>>>(maps, g);
-    else stem_tc_kernel<false><<<grid, kThreads, kStemSmemBytes, stream>>>(maps, g);
-    return cudaGetLastError();
+    if (g.quant) return launch_conv(stem_tc_kernel<true>, grid, kStemSmemBytes, stream, maps, g);
+    return launch_conv(stem_tc_kernel<false>, grid, kStemSmemBytes, stream, maps, g);
   }
   if (g.halo) {
     const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
@@ -986,17 +1014,14 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     if (g.store_mode != 1 || g.bw_log2 != 3 || g.main_taps != 9 || g.num_taps != 9) return cudaErrorInvalidValue;
     switch (block_n) {
       case 64:
-        if (g.quant) conv_halo_kernel<64, true><<<grid, kThreads, halo_plan(g.halo_dil, 64).smem_bytes, stream>>>(maps, g);
-        else conv_halo_kernel<64, false><<<grid, kThreads, halo_plan(g.halo_dil, 64).smem_bytes, stream>>>(maps, g);
-        break;
+        return g.quant ? launch_conv(conv_halo_kernel<64, true>, grid, halo_plan(g.halo_dil, 64).smem_bytes, stream, maps, g)
+                       : launch_conv(conv_halo_kernel<64, false>, grid, halo_plan(g.halo_dil, 64).smem_bytes, stream, maps, g);
       case 128:
-        if (g.quant) conv_halo_kernel<128, true><<<grid, kThreads, halo_plan(g.halo_dil, 128).smem_bytes, stream>>>(maps, g);
-        else conv_halo_kernel<128, false><<<grid, kThreads, halo_plan(g.halo_dil, 128).smem_bytes, stream>>>(maps, g);
-        break;
+        return g.quant ? launch_conv(conv_halo_kernel<128, true>, grid, halo_plan(g.halo_dil, 128).smem_bytes, stream, maps, g)
+                       : launch_conv(conv_halo_kernel<128, false>, grid, halo_plan(g.halo_dil, 128).smem_bytes, stream, maps, g);
       case 256:
-        if (g.quant) conv_halo_kernel<256, true><<<grid, kThreads, halo_plan(g.halo_dil, 256).smem_bytes, stream>>>(maps, g);
-        else conv_halo_kernel<256, false><<<grid, kThreads, halo_plan(g.halo_dil, 256).smem_bytes, stream>>>(maps, g);
-        break;
+        return g.quant ? launch_conv(conv_halo_kernel<256, true>, grid, halo_plan(g.halo_dil, 256).smem_bytes, stream, maps, g)
+                       : launch_conv(conv_halo_kernel<256, false>, grid, halo_plan(g.halo_dil, 256).smem_bytes, stream, maps, g);
       default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -1005,9 +1030,8 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     const int clusters = g.num_work < num_sms / 2 ? g.num_work : num_sms / 2;
     if (clusters <= 0) return cudaSuccess;
     if (block_n != 256 || g.store_mode == 0 || g.stages != pair_stages(g.epi_bufs)) return cudaErrorInvalidValue;
-    if (g.quant) conv_tc_pair_kernel<true><<<2 * clusters, kThreads, pair_smem_bytes(g.epi_bufs), stream>>>(maps, g);
-    else conv_tc_pair_kernel<false><<<2 * clusters, kThreads, pair_smem_bytes(g.epi_bufs), stream>>>(maps, g);
-    return cudaGetLastError();
+    if (g.quant) return launch_conv(conv_tc_pair_kernel<true>, 2 * clusters, pair_smem_bytes(g.epi_bufs), stream, maps, g);
+    return launch_conv(conv_tc_pair_kernel<false>, 2 * clusters, pair_smem_bytes(g.epi_bufs), stream, maps, g);
   }
   switch (block_n) {
     case 32: return launch_one<32>(maps, g, num_sms, stream);

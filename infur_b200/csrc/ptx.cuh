@@ -97,6 +97,12 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                : "memory");
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------
+// wait: blocks until the grids this one depends on have completed and flushed (no-op when the launch carried no
+// programmatic dependency); launch: lets the next grid in the stream start its prologue as SMs free up.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- packed / mixed-precision adds (sm_100) -------------------------------------------------
 // (a0, a1) += (b0, b1) as one FADD2; each lane rounds like a scalar add.rn.f32
 __device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
