@@ -242,7 +242,7 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(tempty0 + 8u * as, 0));
+          if (PAIR) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(tempty0 + 8u * as, 0));
           else ptx::mbar_arrive(tempty0 + 8u * as);
         }
       }

@@ -182,6 +182,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// Same without the release fence (which at cluster scope is MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR: microseconds under load).
+// For the accumulator hand-back only: what must be ordered before the arrive are this warp's tcgen05.ld reads, and those are
+// ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync; no generic-proxy memory is handed over.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 // TMA loads whose completion may be signalled on an mbarrier of the peer CTA (bar = shared::cluster address)
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
