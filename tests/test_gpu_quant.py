@@ -164,3 +164,21 @@ def test_quantised_fcn50_1080p_full_size(handle):
     assert (res[0]["class_map"] == one["class_map"]).all() and (res[2]["decoded_rgba"] == one["decoded_rgba"]).all()
     klass = env["out"][0].argmax(0)
     assert (one["class_map"] == klass).mean() > 0.999
+
+
+def test_golden_qlinear_on_gpu(handle):
+    """The committed golden vectors (tests/golden/qlinear.npz): QLinearConv (3x3, dilation 2) + QLinearAdd through the CUDA path."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "qlinear.npz"))
+    xs, ys, rs, cs = np.float32(0.023), np.float32(0.031), np.float32(0.019), np.float32(0.027)
+    quant = {"qmul": (xs * g["w_scale"]) / ys, "q_lo": -131, "q_hi": 255 - 131, "q_ra": ys / cs, "q_rb": rs / cs, "q_lo2": 0, "q_hi2": 255}
+    xc = (g["q_in"].astype(np.int32) - 121).transpose(0, 2, 3, 1)
+    wc = g["w"].astype(np.int32).transpose(0, 2, 3, 1)
+    rc = g["q_res"].astype(np.int32).transpose(0, 2, 3, 1)
+    for impl in (L.CONV_TCGEN05, L.CONV_TCGEN05_HALO):
+        if impl == L.CONV_TCGEN05_HALO:   # the halo variant has no residual input: check the convolution alone
+            y = handle.conv_test(xc, wc, g["bias"].astype(np.float32), None, 1, 2, 2, impl=impl, quant={k: quant[k] for k in ("qmul", "q_lo", "q_hi")})
+            assert (y.astype(np.int32).transpose(0, 3, 1, 2) + 131 == g["q_conv"]).all()
+        else:
+            y = handle.conv_test(xc, wc, g["bias"].astype(np.float32), rc, 1, 2, 2, impl=impl, quant=quant)
+            assert (y.astype(np.int32).transpose(0, 3, 1, 2) == g["q_add"]).all()

@@ -123,3 +123,16 @@ def test_lowering_rejects_requantising_edges(tmp_path):
     assert rc == L.E_MODEL_LOAD and "differ from its producer" in text, text
     rc, text = _describe(_tiny_graph(mid_quantize=True), str(tmp_path))
     assert rc == L.E_MODEL_LOAD, text
+
+
+def test_golden_qlinear_vectors():
+    """Committed fixtures (tests/golden/make_golden.py) pin the quantised restatement across refactors."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "qlinear.npz"))
+    q_in = qlinear.quantize_linear(g["x"], np.float32(0.023), np.uint8(121))
+    assert (q_in == g["q_in"]).all()
+    q_conv = qlinear.qlinear_conv(q_in, np.float32(0.023), np.uint8(121), g["w"], g["w_scale"], np.zeros(64, np.int8), np.float32(0.031), np.uint8(131),
+                                  g["bias"], 1, 2, 2)
+    assert (q_conv == g["q_conv"]).all() and 0 < q_conv.min() + 1 and len(np.unique(q_conv)) > 100
+    q_add = qlinear.qlinear_add(q_conv, np.float32(0.031), np.uint8(131), g["q_res"], np.float32(0.019), np.uint8(0), np.float32(0.027), np.uint8(0))
+    assert (q_add == g["q_add"]).all()
+    assert (qlinear.dequantize_linear(q_add, np.float32(0.027), np.uint8(0)) == g["deq"]).all()
