@@ -22,9 +22,14 @@
 //                              uses direct stores.
 // Every variant accumulates the K blocks of an output element in the same (chunk-major) order: results are
 // bit-identical whichever variant the plan-time autotuner picks.
+// Each kernel exists twice (template parameter QUANT): the fp16 form, and the form for quantised layers whose epilogue
+// requantises exact integer accumulators like QLinearConv / QLinearAdd (ConvTcGeom::quant, onnx_reader.h ConvOp).
+// All are launched with programmatic stream serialization: the prologue (barrier init, TMEM allocation, descriptor
+// prefetch) overlaps the previous kernel's tail, griddepcontrol.wait precedes the first global access.
 #include "conv_tc.h"
 
 #include <cstdlib>
+
 #include "ptx.cuh"
 
 namespace infur {
