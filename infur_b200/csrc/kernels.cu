@@ -142,6 +142,54 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __half* __restrict__
   reinterpret_cast<uint4*>(out)[idx] = o;
 }
 
+// The FCN stem pool (3x3 / stride 2 / pad 1), row-streaming: thread = (8 channels, output column) walks down a strip of
+// output rows; the horizontal maxima of input row 2*oy+1 serve output rows oy and oy+1 from registers, and the column
+// overlap between neighbouring threads hits L1, so every input element crosses the L2->SM port about once instead of
+// 2.25 times (the gather kernel above is bound by exactly that port).  Same __hmax2 reductions: identical results.
+constexpr int kPoolStrip = 16;
+__global__ void __launch_bounds__(256) maxpool3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int h, int w, int c8, int oh, int ow) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ow * c8) return;
+  const int cg = idx % c8, ox = idx / c8;
+  const int img = blockIdx.z;
+  const int oy0 = blockIdx.y * kPoolStrip, oy1 = min(oy0 + kPoolStrip, oh);
+  const uint4* src = reinterpret_cast<const uint4*>(in) + (size_t)img * h * w * c8 + cg;
+  uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)img * oh * ow * c8 + (size_t)ox * c8 + cg;
+  const __half2 ninf = __halves2half2(__ushort_as_half((unsigned short)0xFC00), __ushort_as_half((unsigned short)0xFC00));
+  const int ix = 2 * ox;
+  auto hrow = [&](int iy, __half2 (&r)[4]) {
+    const uint4* row = src + (size_t)iy * w * c8;
+    const uint4 v1 = __ldg(row + (size_t)ix * c8);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&v1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = h1[q];
+    if (ix > 0) {
+      const uint4 v0 = __ldg(row + (size_t)(ix - 1) * c8);
+      const __half2* h0 = reinterpret_cast<const __half2*>(&v0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[q] = __hmax2(r[q], h0[q]);
+    }
+    if (ix + 1 < w) {
+      const uint4 v2 = __ldg(row + (size_t)(ix + 1) * c8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[q] = __hmax2(r[q], h2[q]);
+    }
+  };
+  __half2 prev[4] = {ninf, ninf, ninf, ninf};
+  if (oy0 > 0) hrow(2 * oy0 - 1, prev);
+  for (int oy = oy0; oy < oy1; ++oy) {
+    __half2 a[4], b[4] = {ninf, ninf, ninf, ninf};
+    hrow(2 * oy, a);
+    if (2 * oy + 1 < h) hrow(2 * oy + 1, b);
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { ho[q] = __hmax2(__hmax2(prev[q], a[q]), b[q]); prev[q] = b[q]; }
+    dst[(size_t)oy * ow * c8] = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: the network's final Resize(linear, half_pixel) fused with ColorCode::advance
 // (infur/src/decode_predict.rs:53-79) and color_code (:32-36).  One CTA = one 32 x 32 output tile:
@@ -464,6 +512,12 @@ cudaError_t launch_preprocess_f32(const uint8_t* bgr, int h, int w, const float*
 
 cudaError_t launch_maxpool(const __half* in, __half* out, int n, int h, int w, int c, int oh, int ow, int k, int stride, int pad,
                            cudaStream_t s) {
+  if (k == 3 && stride == 2 && pad == 1 && oh == (h - 1) / 2 + 1 && ow == (w - 1) / 2 + 1 && n <= 65535) {
+    const int c8 = c / 8;
+    dim3 grid((unsigned)((ow * c8 + 255) / 256), (unsigned)((oh + kPoolStrip - 1) / kPoolStrip), (unsigned)n);
+    maxpool3s2_kernel<<<grid, 256, 0, s>>>(in, out, h, w, c8, oh, ow);
+    return cudaGetLastError();
+  }
   const size_t total = (size_t)n * oh * ow * (c / 8);
   maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, n, h, w, c / 8, oh, ow, k, stride, pad);
   return cudaGetLastError();
