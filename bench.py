@@ -366,7 +366,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                     "ms_per_launch": t_ms, "algorithmic_MB_per_frame": mb_per_frame}
         other = [hbm("pre_unit_vec4_kernel (Scale 1.0 + u8->fp16 normalise)", 6.2208 + 12.4416, pre_ms),
-                 hbm("maxpool_kernel (3x3/s2, NHWC fp16)", 66.3552 + 16.5888, pool_ms),
+                 hbm("maxpool3s2_kernel (3x3/s2, NHWC fp16)", 66.3552 + 16.5888, pool_ms),
                  hbm("post_kernel (bilinear x8 upsample + argmax + colour)", 2.7216 + 8.2944 + 2.0736, post_ms)]
         cpu = None
         if not args.no_cpu_baseline and args.model == "int8":
