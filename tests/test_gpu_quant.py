@@ -109,8 +109,11 @@ def test_quantised_pipeline_vs_oracle(handle, tiny_int8):
     ref = {"class_map": klass.astype(np.uint8), "logits": logits, "decoded_rgba": rgba}
     assert out.id == 3 and out.size == [320, 240]
     assert (out.buffer == oracle.frame_rgba(scaled)).all()
-    match = check_against_oracle(out.class_map, out.decoded_buffer, ref, 0.999)
-    assert match > 0.999
+    check_against_oracle(out.class_map, out.decoded_buffer, ref, 0.999)
+    # in fact nothing differs: the logits before Resize are the oracle's bit for bit, and the Resize + ColorCode kernel is
+    # bit-exact given equal logits (tests/test_gpu_stages.py) -- the whole path is integer / LUT / exactly-ordered f32 work
+    assert (out.class_map == ref["class_map"]).all(), f"{(out.class_map != ref['class_map']).sum()} class-map pixels differ"
+    assert (out.decoded_buffer == ref["decoded_rgba"]).all()
     pipe.control(("Scale", 1.0))
 
 
@@ -141,6 +144,7 @@ def test_quantised_fcn50_config1(handle):
     klass, rgba = oracle.color_code_image(logits)
     ref = {"class_map": klass.astype(np.uint8), "logits": logits, "decoded_rgba": rgba}
     check_against_oracle(out["class_map"], out["decoded_rgba"], ref, 0.999)
+    assert (out["class_map"] == ref["class_map"]).all() and (out["decoded_rgba"] == ref["decoded_rgba"]).all()   # end to end bit-identical
     assert len(np.unique(out["class_map"])) >= 8
 
 
@@ -162,8 +166,8 @@ def test_quantised_fcn50_1080p_full_size(handle):
     res = handle.advance_batch(batch, ids=list(range(1, 9)), want=("class_map", "decoded_rgba"))
     one = handle.advance(frames[0], id=1, want=("class_map", "decoded_rgba"))
     assert (res[0]["class_map"] == one["class_map"]).all() and (res[2]["decoded_rgba"] == one["decoded_rgba"]).all()
-    klass = env["out"][0].argmax(0)
-    assert (one["class_map"] == klass).mean() > 0.999
+    klass, rgba = oracle.color_code_image(env["out"][0])
+    assert (one["class_map"] == klass).all() and (one["decoded_rgba"] == rgba).all()   # 1080p: class map and mask bit-identical end to end
 
 
 def test_golden_qlinear_on_gpu(handle):
