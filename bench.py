@@ -367,7 +367,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "ms_per_launch": t_ms, "algorithmic_MB_per_frame": mb_per_frame}
         other = [hbm("pre_unit_vec4_kernel (Scale 1.0 + u8->fp16 normalise)", 6.2208 + 12.4416, pre_ms),
                  hbm("maxpool3s2_kernel (3x3/s2, NHWC fp16)", 66.3552 + 16.5888, pool_ms),
-                 hbm("post_kernel (bilinear x8 upsample + argmax + colour)", 2.7216 + 8.2944 + 2.0736, post_ms)]
+                 hbm("post_strip_kernel (bilinear x8 upsample + argmax + colour)", 2.7216 + 8.2944 + 2.0736, post_ms)]
+        other[2]["note"] = ("issue-bound, not HBM-bound: 21 un-fused f32 interpolations + strict-'>' scan per output pixel, 1.4e8 warp "
+                            "instructions per launch at 2.2 IPC per SM (profiles/r1_ncu4_prepost.txt); HBM fraction shown for completeness")
         cpu = None
         if not args.no_cpu_baseline and args.model == "int8":
             import torch as _t
