@@ -52,7 +52,8 @@ enum { INFUR_RESIZE_NEAREST = 0 /* fr::ResizeAlg::Nearest, processing.rs:189 (th
        INFUR_RESIZE_BILINEAR = 1 /* opt-in extension (README.md:74 TODO): half-pixel bilinear, un-fused f32, round-half-up to u8 */ };
 enum { INFUR_CONV_TCGEN05 = 0, INFUR_CONV_VALIDATE = 1 /* slow CUDA-core kernel, validation only; never selected implicitly */,
        INFUR_CONV_TCGEN05_PAIR = 2 /* conv_test only: force the CTA-pair (cta_group::2) variant of the tcgen05 kernel */,
-       INFUR_CONV_TCGEN05_HALO = 3 /* conv_test only: force the halo-patch variant (3x3 / stride 1 convolutions) */ };
+       INFUR_CONV_TCGEN05_HALO = 3, /* conv_test only: force the halo-patch variant (3x3 / stride 1 convolutions) */
+       INFUR_CONV_TCGEN05_I8 = 4 /* conv_test only: the layer as an int8 plan runs it (u8 tensors, tcgen05.mma.kind::i8) */ };
 
 typedef struct infur_b200_config {
   uint32_t struct_size;  /* sizeof(infur_b200_config) */
@@ -253,6 +254,9 @@ typedef struct infur_b200_conv_desc {
    * y holds r (fp16), y_f32 holds r * q_deq. */
   const float* qmul; /* [cout] or NULL */
   float q_lo, q_hi, q_ra, q_rb, q_lo2, q_hi2, q_deq;
+  /* INFUR_CONV_TCGEN05_I8: the layer as an int8 plan runs it (u8 activation tensors, native int8 MMA; x must be >= 0,
+   * i.e. input zero point 0): zero points of the residual and of the output tensor.  Host buffers keep the centred form. */
+  int32_t q_zres, q_zout;
 } infur_b200_conv_desc;
 int32_t infur_b200_conv_test(infur_b200_handle* h, const infur_b200_conv_desc* d, const uint16_t* x,
                              const uint16_t* wgt, const float* bias, const uint16_t* residual, uint16_t* y,

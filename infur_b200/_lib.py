@@ -33,6 +33,7 @@ CONV_TCGEN05 = 0
 CONV_VALIDATE = 1
 CONV_TCGEN05_PAIR = 2   # conv_test only
 CONV_TCGEN05_HALO = 3   # conv_test only
+CONV_TCGEN05_I8 = 4     # conv_test only: int8 plan form of a quantised layer
 LOAD_DEFAULT = 0
 LOAD_SKIP_WEIGHTS = 1
 
@@ -71,7 +72,7 @@ class Slot(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [(k, C.c_uint32) for k in ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "pad", "dil")] + [
         ("relu", C.c_int32), ("impl", C.c_int32), ("qmul", C.c_void_p)] + [
-        (k, C.c_float) for k in ("q_lo", "q_hi", "q_ra", "q_rb", "q_lo2", "q_hi2", "q_deq")]
+        (k, C.c_float) for k in ("q_lo", "q_hi", "q_ra", "q_rb", "q_lo2", "q_hi2", "q_deq")] + [("q_zres", C.c_int32), ("q_zout", C.c_int32)]
 
 
 # every symbol include/infur_b200.h declares: name -> (restype, argtypes)

@@ -22,8 +22,9 @@
 //                              uses direct stores.
 // Every variant accumulates the K blocks of an output element in the same (chunk-major) order: results are
 // bit-identical whichever variant the plan-time autotuner picks.
-// Each kernel exists twice (template parameter QUANT): the fp16 form, and the form for quantised layers whose epilogue
-// requantises exact integer accumulators like QLinearConv / QLinearAdd (ConvTcGeom::quant, onnx_reader.h ConvOp).
+// Each kernel is instantiated per MODE: 0 the fp16 form; 1 quantised layers carried in fp16 (the epilogue requantises exact
+// integer accumulators like QLinearConv / QLinearAdd, ConvTcGeom::quant, onnx_reader.h ConvOp); 2 the same with u8 outputs
+// (the stem of an int8 plan); 3 native int8: u8 activations x s8 weights through tcgen05.mma.kind::i8 into s32 accumulators.
 // All are launched with programmatic stream serialization: the prologue (barrier init, TMEM allocation, descriptor
 // prefetch) overlaps the previous kernel's tail, griddepcontrol.wait precedes the first global access.
 #include "conv_tc.h"
@@ -51,10 +52,13 @@ constexpr int kMaxAcc = 4;
 constexpr int kSmemLimit = 232448;                  // 227 KB per CTA
 constexpr int kBarBytes = 512;
 
-template <int BLOCK_N>
+// I8: u8 activations / s8 weights (1 byte per element): a K block of 64 channels is a 64-byte row, 64B swizzle
+template <int BLOCK_N, bool I8 = false>
 struct Cfg {
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEsz = I8 ? 1 : 2;
+  static constexpr int kA = kBlockM * kBlockK * kEsz;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * kEsz;
+  static constexpr int kStageBytes = kA + kBBytes;
   static constexpr int kAcc = BLOCK_N >= 256 ? 2 : 4;     // TMEM accumulator stages: as many 128 x BLOCK_N f32 tiles as fit in 512 columns (max 4)
   static constexpr int kTmemCols = kAcc * BLOCK_N;        // power of two, 128 .. 512
   // epilogue buffers: 0 (direct stores), 2 (TMA store), 4 (TMA store + TMA residual prefetch)
@@ -105,7 +109,7 @@ __device__ __forceinline__ float requant_add(float a, float ra, float b, float r
 }
 
 // Direct-store epilogue (f32 logit head): thread = output pixel, 32 channels at a time.
-template <int BLOCK_N, int ACC, bool QUANT>
+template <int BLOCK_N, int ACC, int MODE>
 __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int quad, int lane,
                                                 int row) {
   const int bw_log2 = g.bw_log2;
@@ -128,18 +132,30 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
       ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, acc);
       ptx::tmem_ld_wait();
       if (valid) {
-        const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
         float v[32];
+        if (MODE == 3) {   // s32 accumulators + int32 bias, converted like QLinearConv does: f32(acc + bias)
+          const int4* b4 = reinterpret_cast<const int4*>(g.bias_i32 + n0 + c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(b4 + j);
-          v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
-          v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
-          v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
-          v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+          for (int j = 0; j < 8; ++j) {
+            const int4 b = __ldg(b4 + j);
+            v[4 * j + 0] = __int2float_rn((int)acc[4 * j + 0] + b.x);
+            v[4 * j + 1] = __int2float_rn((int)acc[4 * j + 1] + b.y);
+            v[4 * j + 2] = __int2float_rn((int)acc[4 * j + 2] + b.z);
+            v[4 * j + 3] = __int2float_rn((int)acc[4 * j + 3] + b.w);
+          }
+        } else {
+          const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+            v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+            v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+          }
         }
         const size_t off = pix * (size_t)g.out_ld + (size_t)(n0 + c0);
-        if (QUANT) {   // QLinearConv requantisation (ConvTcGeom::quant)
+        if (MODE >= 1) {   // QLinearConv requantisation (ConvTcGeom::quant)
           const float4* m4 = reinterpret_cast<const float4*>(g.qmul + n0 + c0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -159,7 +175,7 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float2 f = __half22float2(h[q]);
-              if (QUANT) {   // QLinearAdd
+              if (MODE >= 1) {   // QLinearAdd
                 v[8 * j + 2 * q] = requant_add(v[8 * j + 2 * q], g.q_ra, f.x, g.q_rb, g.q_lo2, g.q_hi2);
                 v[8 * j + 2 * q + 1] = requant_add(v[8 * j + 2 * q + 1], g.q_ra, f.y, g.q_rb, g.q_lo2, g.q_hi2);
               } else {
@@ -174,7 +190,7 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (g.out_f32 != nullptr) {
-          if (QUANT && g.q_deq != 0.f) {   // DequantizeLinear of the logits
+          if (MODE >= 1 && g.q_deq != 0.f) {   // DequantizeLinear of the logits
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(v[j], g.q_deq);
           }
@@ -208,7 +224,7 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
 // announces its part through the chunk_ready mbarrier and moves on.
 struct EpiBars { uint32_t res, ready, free_; };
 
-template <int BLOCK_N, int ACC, bool HAS_RES, bool QUANT, class Sched, bool PAIR = false, int EB = 4>
+template <int BLOCK_N, int ACC, bool HAS_RES, int MODE, class Sched, bool PAIR = false, int EB = 4>
 __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sched, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                              const EpiBars eb, uint32_t epi_base, int ew, int lane) {
   constexpr int CH = BLOCK_N / 64;            // chunks per tile
@@ -228,6 +244,62 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
     for (int c = 0; c < CH; ++c, ++q) {
       const int b = q % EB;
       const uint32_t use = (uint32_t)(q / EB);
+      if (MODE >= 2) {
+        // ---- u8 outputs (int8 plan): the chunk is 128 rows x 64 bytes, unswizzled; a thread owns 32 bytes of its row
+        const uint32_t rowq = epi_base + b * kEpiBufBytes + (uint32_t)row * 64u + (uint32_t)half * 32u;
+        const int cofs = n0 + c * 64 + half * 32;
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), acc);
+        ptx::tmem_ld_wait();
+        if (c == CH - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(tempty0 + 8u * as, 0));
+            else ptx::mbar_arrive(tempty0 + 8u * as);
+          }
+        }
+        uint32_t rw[8];
+        if (HAS_RES) {
+          ptx::mbar_wait(eb.res + 8u * b, use & 1u);
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(rowq));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "r"(rowq + 16u));
+        } else if (use >= 1) {
+          ptx::mbar_wait(eb.free_ + 8u * b, (use - 1u) & 1u);
+        }
+        uint32_t ow[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {            // 4 channels -> one 32-bit word of u8
+          const float4 m = __ldg(reinterpret_cast<const float4*>(g.qmul + cofs) + j);
+          float t[4];
+          if (MODE == 3) {
+            const int4 bi = __ldg(reinterpret_cast<const int4*>(g.bias_i32 + cofs) + j);
+            t[0] = __int2float_rn((int)acc[4 * j + 0] + bi.x); t[1] = __int2float_rn((int)acc[4 * j + 1] + bi.y);
+            t[2] = __int2float_rn((int)acc[4 * j + 2] + bi.z); t[3] = __int2float_rn((int)acc[4 * j + 3] + bi.w);
+          } else {
+            const float4 bf = __ldg(reinterpret_cast<const float4*>(g.bias + cofs) + j);
+            t[0] = __uint_as_float(acc[4 * j + 0]) + bf.x; t[1] = __uint_as_float(acc[4 * j + 1]) + bf.y;
+            t[2] = __uint_as_float(acc[4 * j + 2]) + bf.z; t[3] = __uint_as_float(acc[4 * j + 3]) + bf.w;
+          }
+          const float mm[4] = {m.x, m.y, m.z, m.w};
+          uint32_t word = 0;
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            float r = requant(t[x], mm[x], g.q_lo, g.q_hi);
+            if (HAS_RES) r = requant_add(r, g.q_ra, __uint2float_rn((rw[j] >> (8 * x)) & 0xffu) - g.q_zres, g.q_rb, g.q_lo2, g.q_hi2);
+            if (g.relu) r = fmaxf(r, 0.f);
+            // r + zero point is an integer in [0, 255]: with 1.5 * 2^23 added it sits in the low mantissa bits
+            word |= (__float_as_uint(__fadd_rn(r, g.q_zmagic)) & 0xffu) << (8 * x);
+          }
+          ow[j] = word;
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowq), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowq + 16u), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(eb.ready + 8u * b);
+        continue;
+      }
       const uint32_t rowp = epi_base + b * kEpiBufBytes + (uint32_t)row * 128u;
       float4 bias[8], qm[8];
       {
@@ -235,7 +307,7 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
 #pragma unroll
         for (int j = 0; j < 8; ++j) bias[j] = __ldg(b4 + j);
       }
-      if (QUANT) {
+      if (MODE >= 1) {
         const float4* m4 = reinterpret_cast<const float4*>(g.qmul + n0 + c * 64 + half * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) qm[j] = __ldg(m4 + j);
@@ -273,7 +345,7 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
         // the scalar f32 operations they replace
         ptx::add_f32x2(v[0], v[1], bl.x, bl.y); ptx::add_f32x2(v[2], v[3], bl.z, bl.w);
         ptx::add_f32x2(v[4], v[5], bh.x, bh.y); ptx::add_f32x2(v[6], v[7], bh.z, bh.w);
-        if (QUANT) {
+        if (MODE >= 1) {
           // quantised layer: v is the exact integer accumulator + bias; requantise like QLinearConv, then (HAS_RES) add the
           // residual like QLinearAdd.  Separate f32 multiplies and adds (no FMA contraction), round half to even.
           const float4 ml = qm[2 * j], mh = qm[2 * j + 1];
@@ -329,14 +401,14 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
 // The single thread that owns every bulk copy of the epilogue: stores chunk q when all eight warps have
 // written it, then (one store later, so it never waits on the store it just issued) recycles the previous
 // buffer: HAS_RES -> prefetch the residual of chunk q-1+EB into it, else -> mark it free.
-template <int BLOCK_N, bool HAS_RES, class Sched, int EB = 4>
+template <int BLOCK_N, bool HAS_RES, class Sched, int EB = 4, int CHUNK_BYTES = kEpiBufBytes>
 __device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvTcGeom& g, const Sched sched, const EpiBars eb, uint32_t epi_base) {
   constexpr int CH = BLOCK_N / 64;
   const int total = sched.count() * CH;
   auto issue_res = [&](int qq) {
     const TileCoord tc = decode_tile(g, sched.tile(qq / CH));
     const int b = qq % EB;
-    ptx::mbar_expect_tx(eb.res + 8u * b, (uint32_t)kEpiBufBytes);
+    ptx::mbar_expect_tx(eb.res + 8u * b, (uint32_t)CHUNK_BYTES);
     ptx::tma_load_4d(epi_base + b * kEpiBufBytes, &maps.r, eb.res + 8u * b, tc.nt * BLOCK_N + (qq % CH) * 64, tc.ox0, tc.oy0, tc.img);
   };
   if (HAS_RES) {
@@ -366,10 +438,12 @@ __device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvT
   ptx::tma_store_wait<0>();
 }
 
-template <int BLOCK_N, bool QUANT>
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
-  using C = Cfg<BLOCK_N>;
+  constexpr bool I8 = MODE == 3;
+  constexpr int kChunkBytes = MODE >= 2 ? kEpiBufBytes / 2 : kEpiBufBytes;
+  using C = Cfg<BLOCK_N, I8>;
   extern __shared__ uint8_t smem_raw[];
   const int num_stages = g.stages;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -441,7 +515,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
           const uint32_t a_dst = smem_base + stage * C::kStageBytes;
           ptx::mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
           ptx::tma_load_4d(a_dst, &maps.a[g.tap_view[tap]], full_bar(stage), cc * kBlockK, ox0 + g.tap_dx[tap], oy0 + g.tap_dy[tap], img);
-          ptx::tma_load_2d(a_dst + kABytes, &maps.b, full_bar(stage), kcoord, nt * BLOCK_N);
+          ptx::tma_load_2d(a_dst + C::kA, &maps.b, full_bar(stage), kcoord, nt * BLOCK_N);
           if (++stage == num_stages) { stage = 0; phase ^= 1u; }
         };
         for (int cc = 0; cc < g.cchunks; ++cc)
@@ -453,7 +527,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BLOCK_N);
+      constexpr uint32_t idesc = I8 ? ptx::make_idesc_i8(kBlockM, BLOCK_N) : ptx::make_idesc_f16(kBlockM, BLOCK_N);
+      constexpr uint32_t kRowBytes = I8 ? 64 : 128;   // one K block of 64 channels per row
       constexpr int ACC = C::kAcc;
       int stage = 0;
       uint32_t phase = 0;
@@ -468,12 +543,13 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = smem_base + stage * C::kStageBytes;
-          const uint64_t a_desc = ptx::make_smem_desc(a_addr, 128);
-          const uint64_t b_desc = ptx::make_smem_desc(a_addr + kABytes, 128);
+          const uint64_t a_desc = ptx::make_smem_desc(a_addr, kRowBytes);
+          const uint64_t b_desc = ptx::make_smem_desc(a_addr + C::kA, kRowBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advancing 16 fp16 along K inside the swizzle span = +32 bytes = +2 in the (addr >> 4) field
-            ptx::umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int k = 0; k < (I8 ? kBlockK / 32 : kBlockK / 16); ++k) {
+            // advancing one instruction's K (16 fp16 or 32 int8) inside the swizzle span = +32 bytes = +2 in the (addr >> 4) field
+            if (I8) ptx::umma_i8(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else ptx::umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
           ptx::umma_commit(empty_bar(stage));
           if (++stage == num_stages) { stage = 0; phase ^= 1u; }
@@ -487,22 +563,22 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       if (ptx::elect_one()) {
         const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
         if (g.store_mode == 1) {
-          if (g.epi_bufs == 4) epilogue_dma<BLOCK_N, false, Sched1, 4>(maps, g, sched, eb, epi_base);
-          else epilogue_dma<BLOCK_N, false, Sched1, 2>(maps, g, sched, eb, epi_base);
-        } else if (g.store_mode == 2) epilogue_dma<BLOCK_N, true>(maps, g, sched, eb, epi_base);
+          if (g.epi_bufs == 4) epilogue_dma<BLOCK_N, false, Sched1, 4, kChunkBytes>(maps, g, sched, eb, epi_base);
+          else epilogue_dma<BLOCK_N, false, Sched1, 2, kChunkBytes>(maps, g, sched, eb, epi_base);
+        } else if (g.store_mode == 2) epilogue_dma<BLOCK_N, true, Sched1, 4, kChunkBytes>(maps, g, sched, eb, epi_base);
       }
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
     const int ew = warp - kEpiWarp0;         // ew % 4 == warp % 4: the TMEM lane quadrant this warp may read
     if (g.store_mode == 0) {
-      if (ew < 4) epilogue_direct<BLOCK_N, C::kAcc, QUANT>(g, tmem_base, tfull_bar(0), tempty_bar(0), ew, lane, ew * 32 + lane);
+      if (ew < 4) epilogue_direct<BLOCK_N, C::kAcc, MODE>(g, tmem_base, tfull_bar(0), tempty_bar(0), ew, lane, ew * 32 + lane);
     } else if constexpr (BLOCK_N >= 64) {
       const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
       if (g.store_mode == 1) {
-        if (g.epi_bufs == 4) epilogue_tma<BLOCK_N, C::kAcc, false, QUANT, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-        else epilogue_tma<BLOCK_N, C::kAcc, false, QUANT, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-      } else epilogue_tma<BLOCK_N, C::kAcc, true, QUANT, Sched1>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+        if (g.epi_bufs == 4) epilogue_tma<BLOCK_N, C::kAcc, false, MODE, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+        else epilogue_tma<BLOCK_N, C::kAcc, false, MODE, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      } else epilogue_tma<BLOCK_N, C::kAcc, true, MODE, Sched1>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
     }
   }
 
@@ -532,7 +608,7 @@ __host__ __device__ constexpr int pair_stages(int epi_bufs) {
 }
 __host__ __device__ constexpr int pair_smem_bytes(int epi_bufs) { return pair_stages(epi_bufs) * kPairStageBytes + epi_bufs * kEpiBufBytes + 1024 + kBarBytes; }
 
-template <bool QUANT>
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   constexpr int BLOCK_N = 256;
@@ -644,8 +720,8 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
     }
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;
-    if (g.store_mode == 1) epilogue_tma<BLOCK_N, ACC, false, QUANT, Sched2, true, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-    else epilogue_tma<BLOCK_N, ACC, true, QUANT, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    if (g.store_mode == 1) epilogue_tma<BLOCK_N, ACC, false, MODE, Sched2, true, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    else epilogue_tma<BLOCK_N, ACC, true, MODE, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
   }
 
   ptx::tc_fence_before();
@@ -695,7 +771,7 @@ struct HaloCfg {
   static constexpr int kTmemCols = kAcc * BLOCK_N;
 };
 
-template <int BLOCK_N, bool QUANT>
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   using C = HaloCfg<BLOCK_N>;
@@ -814,8 +890,8 @@ conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
       else epilogue_dma<BLOCK_N, false, Sched1, 2>(maps, g, sched, eb, epi_base);
     }
   } else if (warp >= kEpiWarp0) {
-    if (hp.epi_bufs == 2) epilogue_tma<BLOCK_N, ACC, false, QUANT, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
-    else epilogue_tma<BLOCK_N, ACC, false, QUANT, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
+    if (hp.epi_bufs == 2) epilogue_tma<BLOCK_N, ACC, false, MODE, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
+    else epilogue_tma<BLOCK_N, ACC, false, MODE, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, warp - kEpiWarp0, lane);
   }
 
   ptx::tc_fence_before();
@@ -841,7 +917,7 @@ constexpr int kStemTxBytes = 7 * kStemRowBytes;
 constexpr int kStemStages = 8;
 constexpr int kStemSmemBytes = kStemStages * kStemStageBytes + 4 * kEpiBufBytes + kStemWBytes + 1024 + kBarBytes;
 
-template <bool QUANT>
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   constexpr int BLOCK_N = 64;
@@ -937,9 +1013,9 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       }
     }
   } else if (warp == kDmaWarp) {
-    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false, Sched1, 4>(maps, g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, eb, epi_base);
+    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false, Sched1, 4, (MODE >= 2 ? kEpiBufBytes / 2 : kEpiBufBytes)>(maps, g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, eb, epi_base);
   } else if (warp >= kEpiWarp0) {
-    epilogue_tma<BLOCK_N, ACC, false, QUANT, Sched1, false, 4>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
+    epilogue_tma<BLOCK_N, ACC, false, MODE, Sched1, false, 4>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
                                  warp - kEpiWarp0, lane);
   }
 
@@ -972,36 +1048,41 @@ template <int BLOCK_N>
 cudaError_t launch_one(const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream) {
   const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
   if (grid <= 0) return cudaSuccess;
-  if (g.stages != Cfg<BLOCK_N>::stages(g.epi_bufs) || (g.store_mode != 0 && BLOCK_N < 64)) return cudaErrorInvalidValue;
-  if (g.quant) return launch_conv(conv_tc_kernel<BLOCK_N, true>, grid, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream, maps, g);
-  return launch_conv(conv_tc_kernel<BLOCK_N, false>, grid, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream, maps, g);
+  if (g.store_mode != 0 && BLOCK_N < 64) return cudaErrorInvalidValue;
+  if (g.mode == 3) {
+    if (g.stages != Cfg<BLOCK_N, true>::stages(g.epi_bufs)) return cudaErrorInvalidValue;
+    return launch_conv(conv_tc_kernel<BLOCK_N, 3>, grid, Cfg<BLOCK_N, true>::smem_bytes(g.epi_bufs), stream, maps, g);
+  }
+  if (g.mode == 2 || g.stages != Cfg<BLOCK_N>::stages(g.epi_bufs)) return cudaErrorInvalidValue;   // mode 2 is the stem's
+  if (g.mode == 1) return launch_conv(conv_tc_kernel<BLOCK_N, 1>, grid, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream, maps, g);
+  return launch_conv(conv_tc_kernel<BLOCK_N, 0>, grid, Cfg<BLOCK_N>::smem_bytes(g.epi_bufs), stream, maps, g);
 }
 
 }  // namespace
 
 int conv_tc_pair_stages(int epi_bufs) { return pair_stages(epi_bufs); }
 
-int conv_tc_stages(int block_n, int epi_bufs) {
+int conv_tc_stages(int block_n, int epi_bufs, bool i8) {
   switch (block_n) {
-    case 32: return Cfg<32>::stages(epi_bufs);
-    case 64: return Cfg<64>::stages(epi_bufs);
-    case 128: return Cfg<128>::stages(epi_bufs);
-    default: return Cfg<256>::stages(epi_bufs);
+    case 32: return i8 ? Cfg<32, true>::stages(epi_bufs) : Cfg<32>::stages(epi_bufs);
+    case 64: return i8 ? Cfg<64, true>::stages(epi_bufs) : Cfg<64>::stages(epi_bufs);
+    case 128: return i8 ? Cfg<128, true>::stages(epi_bufs) : Cfg<128>::stages(epi_bufs);
+    default: return i8 ? Cfg<256, true>::stages(epi_bufs) : Cfg<256>::stages(epi_bufs);
   }
 }
 
 cudaError_t conv_tc_init() {
   cudaError_t e = cudaSuccess;
   auto opt_in = [&](auto kernel, int bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
-  opt_in(conv_tc_kernel<32, false>, kSmemLimit); opt_in(conv_tc_kernel<32, true>, kSmemLimit);
-  opt_in(conv_tc_kernel<64, false>, kSmemLimit); opt_in(conv_tc_kernel<64, true>, kSmemLimit);
-  opt_in(conv_tc_kernel<128, false>, kSmemLimit); opt_in(conv_tc_kernel<128, true>, kSmemLimit);
-  opt_in(conv_tc_kernel<256, false>, kSmemLimit); opt_in(conv_tc_kernel<256, true>, kSmemLimit);
-  opt_in(stem_tc_kernel<false>, kStemSmemBytes); opt_in(stem_tc_kernel<true>, kStemSmemBytes);
-  opt_in(conv_halo_kernel<64, false>, kSmemLimit); opt_in(conv_halo_kernel<64, true>, kSmemLimit);
-  opt_in(conv_halo_kernel<128, false>, kSmemLimit); opt_in(conv_halo_kernel<128, true>, kSmemLimit);
-  opt_in(conv_halo_kernel<256, false>, kSmemLimit); opt_in(conv_halo_kernel<256, true>, kSmemLimit);
-  opt_in(conv_tc_pair_kernel<false>, kSmemLimit); opt_in(conv_tc_pair_kernel<true>, kSmemLimit);
+  opt_in(conv_tc_kernel<32, 0>, kSmemLimit); opt_in(conv_tc_kernel<32, 1>, kSmemLimit); opt_in(conv_tc_kernel<32, 3>, kSmemLimit);
+  opt_in(conv_tc_kernel<64, 0>, kSmemLimit); opt_in(conv_tc_kernel<64, 1>, kSmemLimit); opt_in(conv_tc_kernel<64, 3>, kSmemLimit);
+  opt_in(conv_tc_kernel<128, 0>, kSmemLimit); opt_in(conv_tc_kernel<128, 1>, kSmemLimit); opt_in(conv_tc_kernel<128, 3>, kSmemLimit);
+  opt_in(conv_tc_kernel<256, 0>, kSmemLimit); opt_in(conv_tc_kernel<256, 1>, kSmemLimit); opt_in(conv_tc_kernel<256, 3>, kSmemLimit);
+  opt_in(stem_tc_kernel<0>, kStemSmemBytes); opt_in(stem_tc_kernel<1>, kStemSmemBytes); opt_in(stem_tc_kernel<2>, kStemSmemBytes);
+  opt_in(conv_halo_kernel<64, 0>, kSmemLimit); opt_in(conv_halo_kernel<64, 1>, kSmemLimit);
+  opt_in(conv_halo_kernel<128, 0>, kSmemLimit); opt_in(conv_halo_kernel<128, 1>, kSmemLimit);
+  opt_in(conv_halo_kernel<256, 0>, kSmemLimit); opt_in(conv_halo_kernel<256, 1>, kSmemLimit);
+  opt_in(conv_tc_pair_kernel<0>, kSmemLimit); opt_in(conv_tc_pair_kernel<1>, kSmemLimit);
   return e;
 }
 
@@ -1010,23 +1091,25 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
     if (block_n != 64 || g.store_mode != 1 || g.bw_log2 != 7) return cudaErrorInvalidValue;
-    if (g.quant) return launch_conv(stem_tc_kernel<true>, grid, kStemSmemBytes, stream, maps, g);
-    return launch_conv(stem_tc_kernel<false>, grid, kStemSmemBytes, stream, maps, g);
+    if (g.mode == 2) return launch_conv(stem_tc_kernel<2>, grid, kStemSmemBytes, stream, maps, g);
+    if (g.mode == 1) return launch_conv(stem_tc_kernel<1>, grid, kStemSmemBytes, stream, maps, g);
+    if (g.mode != 0) return cudaErrorInvalidValue;
+    return launch_conv(stem_tc_kernel<0>, grid, kStemSmemBytes, stream, maps, g);
   }
   if (g.halo) {
     const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
-    if (g.store_mode != 1 || g.bw_log2 != 3 || g.main_taps != 9 || g.num_taps != 9) return cudaErrorInvalidValue;
+    if (g.store_mode != 1 || g.bw_log2 != 3 || g.main_taps != 9 || g.num_taps != 9 || g.mode > 1) return cudaErrorInvalidValue;
     switch (block_n) {
       case 64:
-        return g.quant ? launch_conv(conv_halo_kernel<64, true>, grid, halo_plan(g.halo_dil, 64).smem_bytes, stream, maps, g)
-                       : launch_conv(conv_halo_kernel<64, false>, grid, halo_plan(g.halo_dil, 64).smem_bytes, stream, maps, g);
+        return g.mode ? launch_conv(conv_halo_kernel<64, 1>, grid, halo_plan(g.halo_dil, 64).smem_bytes, stream, maps, g)
+                       : launch_conv(conv_halo_kernel<64, 0>, grid, halo_plan(g.halo_dil, 64).smem_bytes, stream, maps, g);
       case 128:
-        return g.quant ? launch_conv(conv_halo_kernel<128, true>, grid, halo_plan(g.halo_dil, 128).smem_bytes, stream, maps, g)
-                       : launch_conv(conv_halo_kernel<128, false>, grid, halo_plan(g.halo_dil, 128).smem_bytes, stream, maps, g);
+        return g.mode ? launch_conv(conv_halo_kernel<128, 1>, grid, halo_plan(g.halo_dil, 128).smem_bytes, stream, maps, g)
+                       : launch_conv(conv_halo_kernel<128, 0>, grid, halo_plan(g.halo_dil, 128).smem_bytes, stream, maps, g);
       case 256:
-        return g.quant ? launch_conv(conv_halo_kernel<256, true>, grid, halo_plan(g.halo_dil, 256).smem_bytes, stream, maps, g)
-                       : launch_conv(conv_halo_kernel<256, false>, grid, halo_plan(g.halo_dil, 256).smem_bytes, stream, maps, g);
+        return g.mode ? launch_conv(conv_halo_kernel<256, 1>, grid, halo_plan(g.halo_dil, 256).smem_bytes, stream, maps, g)
+                       : launch_conv(conv_halo_kernel<256, 0>, grid, halo_plan(g.halo_dil, 256).smem_bytes, stream, maps, g);
       default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -1034,9 +1117,9 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
   if (g.pair) {
     const int clusters = g.num_work < num_sms / 2 ? g.num_work : num_sms / 2;
     if (clusters <= 0) return cudaSuccess;
-    if (block_n != 256 || g.store_mode == 0 || g.stages != pair_stages(g.epi_bufs)) return cudaErrorInvalidValue;
-    if (g.quant) return launch_conv(conv_tc_pair_kernel<true>, 2 * clusters, pair_smem_bytes(g.epi_bufs), stream, maps, g);
-    return launch_conv(conv_tc_pair_kernel<false>, 2 * clusters, pair_smem_bytes(g.epi_bufs), stream, maps, g);
+    if (block_n != 256 || g.store_mode == 0 || g.stages != pair_stages(g.epi_bufs) || g.mode > 1) return cudaErrorInvalidValue;
+    if (g.mode == 1) return launch_conv(conv_tc_pair_kernel<1>, 2 * clusters, pair_smem_bytes(g.epi_bufs), stream, maps, g);
+    return launch_conv(conv_tc_pair_kernel<0>, 2 * clusters, pair_smem_bytes(g.epi_bufs), stream, maps, g);
   }
   switch (block_n) {
     case 32: return launch_one<32>(maps, g, num_sms, stream);

@@ -45,6 +45,12 @@ struct ConvTcGeom {
   int32_t quant;
   const float* qmul;          // [tiles_n * BLOCK_N]
   float q_lo, q_hi, q_ra, q_rb, q_lo2, q_hi2, q_deq;
+  // int8 plans: mode 2 = fp16-carried operands, u8 output (the stem); mode 3 = u8 activations x s8 weights, s32 accumulators,
+  // u8 output / residual (or f32 head).  mode 0 / 1 = !quant / quant with fp16 tensors.  u8 tensors hold the raw q:
+  // q_zres = zero point of the residual tensor, q_zmagic = zero point of the output tensor + 1.5 * 2^23.
+  int32_t mode;
+  const int32_t* bias_i32;    // mode 3: [tiles_n * BLOCK_N]
+  float q_zres, q_zmagic;
   int8_t tap_view[kMaxTaps + 3];
   uint8_t tap_cc[kMaxTaps + 3];  // 64-channel chunks of each tap (a fused shortcut tap may differ from the main taps)
   int16_t tap_dx[kMaxTaps + 1];
@@ -62,7 +68,7 @@ struct alignas(64) ConvTcMaps {
 cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream);
 // One-time: opt in to the dynamic shared memory each instantiation needs.
 cudaError_t conv_tc_init();
-int conv_tc_stages(int block_n, int epi_bufs);
+int conv_tc_stages(int block_n, int epi_bufs, bool i8 = false);
 int conv_tc_pair_stages(int epi_bufs);
 
 }  // namespace infur

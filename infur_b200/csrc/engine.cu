@@ -36,16 +36,17 @@ static EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-static Status make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                            const uint32_t* box, bool swizzle128 = true) {
+// esz = 2: fp16 elements, 128B swizzle (or none); esz = 1: u8 elements, 64B swizzle (a 64-channel K block is a 64-byte row) or none
+static Status make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box, bool swizzle, int esz) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return Status::error(INFUR_E_RUNTIME, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (esz == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r = enc(m, esz == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx,
+                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     std::ostringstream os;
     os << "cuTensorMapEncodeTiled failed (CUresult " << (int)r << ") rank " << rank << " dims";
@@ -57,6 +58,11 @@ static Status make_tmap_f16(CUtensorMap* m, const void* base, int rank, const ui
     return Status::error(INFUR_E_RUNTIME, os.str());
   }
   return Status();
+}
+
+static Status make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box, bool swizzle128 = true) {
+  return make_tmap(m, base, rank, dims, strides_bytes, box, swizzle128, 2);
 }
 
 DeviceModel::~DeviceModel() { if (arena) cudaFree(arena); }
@@ -77,6 +83,7 @@ static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((
 static bool skip_fusion_env() { const char* e = getenv("INFUR_B200_NO_SHORTCUT_FUSION"); return e && e[0] == '1'; }
 
 static bool halo_disabled_env() { const char* e = getenv("INFUR_B200_NO_HALO"); return e && e[0] == '1'; }
+static bool i8_enabled_env() { const char* e = getenv("INFUR_B200_I8"); return e && e[0] == '1'; }
 static bool pair_disabled_env() { const char* e = getenv("INFUR_B200_NO_CTA_PAIR"); return e && e[0] == '1'; }
 
 static void classify_conv(const ConvOp& c, bool reads_input, bool is_head, DevConv& d) {
@@ -131,12 +138,28 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
   for (auto& h : m.heads) is_head_tensor[h.tensor] = 1;
 
   dm->convs.resize(m.ops.size());
+  // Int8 plan: quantised model whose activations can live in HBM as raw u8 and whose convolutions (all but the RGB stem)
+  // can run on tcgen05.mma.kind::i8: every tensor u8, every non-stem convolution input with zero point 0 (so that TMA's
+  // zero fill is the padding value), weights within s8 after subtracting their zero point, 3x3/s2/p1 pooling only.
+  bool i8 = m.quant && cfg.conv_impl == INFUR_CONV_TCGEN05 && i8_enabled_env();
+  for (size_t i = 0; i < m.ops.size() && i8; ++i) {
+    if (!dm->needed[i]) continue;
+    if (m.ops[i].kind == OpKind::MaxPool) { i8 = m.ops[i].pool_k == 3 && m.ops[i].pool_s == 2 && m.ops[i].pool_p == 1; continue; }
+    const ConvOp& c = m.ops[i].conv;
+    const bool stem = m.ops[i].in == m.input_tensor;
+    if (!c.all_u8 || (stem && !(c.cin == 3 && c.kh == 7 && c.stride == 2 && c.pad == 3)) || (!stem && c.x_zp != 0) ||
+        (is_head_tensor[m.ops[i].out] && c.residual >= 0))
+      i8 = false;
+    if (!stem) for (float w : c.weight) if (w < -128.f || w > 127.f) { i8 = false; break; }
+  }
+  dm->i8 = i8;
   size_t off = 0;
   for (size_t i = 0; i < m.ops.size(); ++i) {
     if (m.ops[i].kind != OpKind::Conv || !dm->needed[i]) continue;
     const ConvOp& c = m.ops[i].conv;
     DevConv& d = dm->convs[i];
     classify_conv(c, m.ops[i].in == m.input_tensor, is_head_tensor[m.ops[i].out] != 0, d);
+    if (i8) { d.mode = d.stem ? 2 : 3; d.res_zp = c.res_zp; d.out_zp = c.out_zp; }
     if (!d.tc_ok && cfg.conv_impl == INFUR_CONV_TCGEN05)
       return Status::error(INFUR_E_MODEL_LOAD, "convolution '" + m.ops[i].name + "' cannot run on the tcgen05 path: " + d.why_not);
     d.w_off = off; off = align_up(off + (size_t)d.cout_pad * d.kdim * 2, 256);
@@ -146,6 +169,7 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
     if (d.quant) {
       if (cfg.conv_impl != INFUR_CONV_TCGEN05) return Status::error(INFUR_E_UNSUPPORTED, "quantised models run on the tcgen05 path only (cfg.conv_impl)");
       d.q_off = off; off = align_up(off + (size_t)d.cout_pad * 4, 256);
+      if (d.mode == 3) { d.bi_off = off; off = align_up(off + (size_t)d.cout_pad * 4, 256); }
     }
   }
   if (m.quant) { dm->lut_q_off = off; off = align_up(off + 768 * 2, 256); }
@@ -168,6 +192,12 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
                 w16[stem_w_index(co, ky, kx, ci)] = __float2half_rn(c.weight[(((size_t)co * 7 + ky) * 7 + kx) * 3 + ci]);
         __half* wv = reinterpret_cast<__half*>(host.data() + d.wv_off);
         for (size_t j = 0; j < c.weight.size(); ++j) wv[j] = __float2half_rn(c.weight[j]);
+      } else if (d.mode == 3) {
+        // native int8: s8 [cout][kdim] (one byte per weight, zero point already subtracted) and the int32 bias
+        int8_t* w8 = reinterpret_cast<int8_t*>(host.data() + d.w_off);
+        for (size_t j = 0; j < c.weight.size(); ++j) w8[j] = (int8_t)c.weight[j];
+        int32_t* bi = reinterpret_cast<int32_t*>(host.data() + d.bi_off);
+        for (int co = 0; co < c.cout; ++co) bi[co] = (int32_t)c.bias[co];
       } else {
         // [cout][kh][kw][cin] (+ [cout][cin2] of a fused shortcut) == [cout][kdim]
         const size_t k1 = (size_t)c.kh * c.kw * c.cin;
@@ -220,6 +250,7 @@ struct ConvIO {
   float* y_f32 = nullptr;
   int out_ld = 0;
   const float* qmul = nullptr;   // quantised layer (DevConv::quant)
+  const int32_t* bias_i32 = nullptr;   // mode 3
 };
 
 enum { kVarPlain = 0, kVarPair = 1, kVarHalo = 2 };
@@ -254,7 +285,11 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   // (<= 8 blocks) that the epilogue, not the operand pipeline, sets the pace; else 2
   g.epi_bufs = g.store_mode == 0 ? 0 : 4;
   if (g.store_mode == 1 && !pair && !halo && !d.stem && conv_tc_stages(block_n, 4) < 4 && g.num_kb > 8) g.epi_bufs = 2;
-  g.stages = pair ? conv_tc_pair_stages(g.epi_bufs) : conv_tc_stages(block_n, g.epi_bufs);
+  const int esz = d.mode == 3 ? 1 : 2;      // operand element size
+  const int osz = d.mode >= 2 ? 1 : 2;      // output / residual element size
+  if (d.mode >= 2 && (pair || halo)) return Status::error(INFUR_E_UNSUPPORTED, "int8 plans use the plain and stem kernels only");
+  if (d.mode == 3) g.epi_bufs = g.store_mode == 0 ? 0 : 4;
+  g.stages = pair ? conv_tc_pair_stages(g.epi_bufs) : conv_tc_stages(block_n, g.epi_bufs, d.mode == 3);
   g.pair = pair ? 1 : 0;
   g.halo = halo ? 1 : 0; g.halo_dil = d.dil;
   if (halo) { if (!halo_ok(d) || io.y_f32 || io.residual) return Status::error(INFUR_E_UNSUPPORTED, "halo variant: needs a 3x3 / stride 1 / pad = dilation convolution without residual"); g.stages = 0; }
@@ -263,6 +298,8 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   if (d.quant) {
     g.quant = 1; g.qmul = io.qmul;
     g.q_lo = d.q_lo; g.q_hi = d.q_hi; g.q_ra = d.q_ra; g.q_rb = d.q_rb; g.q_lo2 = d.q_lo2; g.q_hi2 = d.q_hi2; g.q_deq = d.q_deq;
+    g.mode = d.mode ? d.mode : 1;
+    g.bias_i32 = io.bias_i32; g.q_zres = (float)d.res_zp; g.q_zmagic = (float)d.out_zp + 12582912.f;
   }
   Status st;
   const uint32_t box[4] = {64, (uint32_t)(d.stem ? 128 : bw), (uint32_t)(d.stem ? 1 : bh), 1};
@@ -295,8 +332,8 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
         const int vw = (io.w - px + s - 1) / s, vh = (io.h - py + s - 1) / s;
         if (vw <= 0 || vh <= 0) continue;
         const uint64_t dims[4] = {(uint64_t)d.cin, (uint64_t)vw, (uint64_t)vh, (uint64_t)io.n};
-        const uint64_t strides[3] = {(uint64_t)s * d.cin * 2, (uint64_t)s * io.w * d.cin * 2, (uint64_t)io.h * io.w * d.cin * 2};
-        st = make_tmap_f16(&po.maps.a[py * s + px], io.x + ((size_t)py * io.w + px) * d.cin, 4, dims, strides, box);
+        const uint64_t strides[3] = {(uint64_t)s * d.cin * esz, (uint64_t)s * io.w * d.cin * esz, (uint64_t)io.h * io.w * d.cin * esz};
+        st = make_tmap(&po.maps.a[py * s + px], reinterpret_cast<const uint8_t*>(io.x) + ((size_t)py * io.w + px) * d.cin * esz, 4, dims, strides, box, true, esz);
         if (!st.ok()) return st;
         have[py * s + px] = true;
       }
@@ -330,9 +367,9 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   }
   if (!d.stem) {
     const uint64_t dims[2] = {(uint64_t)d.kdim, (uint64_t)d.cout_pad};
-    const uint64_t strides[1] = {(uint64_t)d.kdim * 2};
+    const uint64_t strides[1] = {(uint64_t)d.kdim * esz};
     const uint32_t bbox[2] = {64, (uint32_t)(pair ? 128 : block_n)};   // a CTA pair splits the weight tile between its CTAs
-    st = make_tmap_f16(&po.maps.b, io.wgt, 2, dims, strides, bbox);
+    st = make_tmap(&po.maps.b, io.wgt, 2, dims, strides, bbox, true, esz);
     if (!st.ok()) return st;
   } else {
     po.maps.b = po.maps.a[0];
@@ -341,11 +378,12 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   if (g.store_mode != 0) {
     // output / residual: NHWC fp16 [n][oh][ow][out_ld], stored (loaded) in 64-channel x tile boxes
     const uint64_t dims[4] = {(uint64_t)d.cout, (uint64_t)io.ow, (uint64_t)io.oh, (uint64_t)io.n};
-    const uint64_t strides[3] = {(uint64_t)io.out_ld * 2, (uint64_t)io.ow * io.out_ld * 2, (uint64_t)io.oh * io.ow * io.out_ld * 2};
-    st = make_tmap_f16(&po.maps.c, io.y, 4, dims, strides, box);
+    const uint64_t strides[3] = {(uint64_t)io.out_ld * osz, (uint64_t)io.ow * io.out_ld * osz, (uint64_t)io.oh * io.ow * io.out_ld * osz};
+    // fp16 chunks are 128B-swizzled in smem, u8 chunks (int8 plans) are plain 64-byte rows
+    st = make_tmap(&po.maps.c, io.y, 4, dims, strides, box, osz == 2, osz);
     if (!st.ok()) return st;
     if (io.residual) {
-      st = make_tmap_f16(&po.maps.r, io.residual, 4, dims, strides, box);
+      st = make_tmap(&po.maps.r, io.residual, 4, dims, strides, box, osz == 2, osz);
       if (!st.ok()) return st;
     }
   }
@@ -382,6 +420,7 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
   for (int round = 0; round < 3 && st.ok(); ++round) {
     for (const Cand& c : cands) {
       if (c.bn > d.block_n || d.cout_pad % c.bn != 0 || (c.var == kVarPair && !allow_pair) || (c.var == kVarHalo && !allow_halo)) continue;
+      if (d.mode >= 2 && c.var != kVarPlain) continue;   // int8 plans: plain kernel only
       PlanOp trial;
       if (!(st = setup_conv_tc(d, io, trial, c.bn, c.var)).ok()) break;
       cudaError_t e = conv_tc_launch(c.bn, trial.maps, trial.geom, H->num_sms, H->stream);   // warm-up
@@ -501,7 +540,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
     if (eh < 0 || ew < 0) return Status::error(INFUR_E_SHAPE, "Invalid input shape: image too small for '" + op.name + "'");
     to.h = eh / s + 1; to.w = ew / s + 1;
     if (op.kind == OpKind::Conv && is_head_tensor[op.out]) { to.f32 = true; to.ld = M->convs[i].cout_pad; to.bytes = (size_t)n * to.h * to.w * to.ld * 4; }
-    else { to.ld = to.c; to.bytes = (size_t)n * to.h * to.w * to.c * 2; }
+    else { to.ld = to.c; to.bytes = (size_t)n * to.h * to.w * to.c * (M->i8 ? 1 : 2); }
     last_use[op.in] = (int)i;
     if (op.kind == OpKind::Conv && op.conv.residual >= 0) {
       const TensorInfo& tr = p.tensors[op.conv.residual];
@@ -515,7 +554,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
         return Status::error(INFUR_E_SHAPE, "Invalid input shape: shortcut size mismatch at '" + op.name + "'");
       last_use[op.conv.in2] = (int)i;
     }
-    if (op.kind == OpKind::MaxPool && ti.c % 8 != 0) return Status::error(INFUR_E_UNSUPPORTED, "MaxPool needs channels % 8 == 0");
+    if (op.kind == OpKind::MaxPool && ti.c % (M->i8 ? 16 : 8) != 0) return Status::error(INFUR_E_UNSUPPORTED, "MaxPool needs channels % 8 == 0 (16 in an int8 plan)");
   }
   for (auto& hd : m.heads) last_use[hd.tensor] = 1 << 30;
 
@@ -568,6 +607,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       io.wgt = reinterpret_cast<const __half*>(M->arena + d.w_off);
       io.bias = reinterpret_cast<const float*>(M->arena + d.b_off);
       if (d.quant) io.qmul = reinterpret_cast<const float*>(M->arena + d.q_off);
+      if (d.mode == 3) io.bias_i32 = reinterpret_cast<const int32_t*>(M->arena + d.bi_off);
       io.residual = op.conv.residual >= 0 ? reinterpret_cast<const __half*>(p.tensors[op.conv.residual].ptr) : nullptr;
       if (op.conv.in2 >= 0) {
         const TensorInfo& t2 = p.tensors[op.conv.in2];
@@ -670,8 +710,11 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
     } else {
       const TensorInfo& ti = p.tensors[op.in];
       const TensorInfo& to = p.tensors[op.out];
-      CU_TRY(launch_maxpool(reinterpret_cast<const __half*>(ti.ptr), reinterpret_cast<__half*>(to.ptr), p.n, ti.h, ti.w, ti.c, to.h, to.w,
-                            op.pool_k, op.pool_s, op.pool_p, s));
+      if (H->model->i8)
+        CU_TRY(launch_maxpool3s2_u8(reinterpret_cast<const uint8_t*>(ti.ptr), reinterpret_cast<uint8_t*>(to.ptr), p.n, ti.h, ti.w, ti.c, to.h, to.w, s));
+      else
+        CU_TRY(launch_maxpool(reinterpret_cast<const __half*>(ti.ptr), reinterpret_cast<__half*>(to.ptr), p.n, ti.h, ti.w, ti.c, to.h, to.w,
+                              op.pool_k, op.pool_s, op.pool_p, s));
     }
     H->launches++;
     if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
@@ -722,7 +765,13 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   classify_conv(c, c.cin == 3, f32out, d);
   const bool pair = cd->impl == INFUR_CONV_TCGEN05_PAIR;
   const bool halo = cd->impl == INFUR_CONV_TCGEN05_HALO;
-  const bool tc = cd->impl == INFUR_CONV_TCGEN05 || pair || halo;
+  const bool i8 = cd->impl == INFUR_CONV_TCGEN05_I8;
+  const bool tc = cd->impl == INFUR_CONV_TCGEN05 || pair || halo || i8;
+  if (i8) {
+    // int8 plan form of the layer: the RGB stem keeps fp16-carried operands and writes u8 (mode 2), everything else is native int8
+    if (!c.quant) return Status::error(INFUR_E_INVALID_ARG, "conv_test: INFUR_CONV_TCGEN05_I8 needs the quantisation parameters (qmul)");
+    d.mode = d.stem ? 2 : 3; d.res_zp = cd->q_zres; d.out_zp = cd->q_zout;
+  }
   if (c.quant && !tc) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: quantised layers run on the tcgen05 implementations only");
   if (tc && !d.tc_ok) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: shape not supported by the tcgen05 kernel: " + d.why_not);
   Plan tmp;
@@ -744,6 +793,21 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   std::vector<float> bp((size_t)d.cout_pad, 0.f);
   for (int co = 0; co < c.cout; ++co) bp[co] = bias[co];
   if (!(st = dev_upload(tmp, &d_w, wp)).ok() || !(st = dev_upload(tmp, &d_b, bp)).ok()) return st;
+  int32_t* d_bi = nullptr;
+  if (d.mode == 3) {   // native int8: s8 weights [cout_pad][kdim], int32 bias
+    std::vector<int8_t> w8((size_t)d.cout_pad * d.kdim, 0);
+    for (size_t j = 0; j < wcount; ++j) {
+      const float f = __half2float(wh[j]);
+      if (f < -128.f || f > 127.f || f != nearbyintf(f)) return Status::error(INFUR_E_INVALID_ARG, "conv_test: int8 weights must be integers in [-128, 127]");
+      w8[j] = (int8_t)f;
+    }
+    int8_t* d_w8 = nullptr;
+    if (!(st = dev_upload(tmp, &d_w8, w8)).ok()) return st;
+    d_w = reinterpret_cast<__half*>(d_w8);
+    std::vector<int32_t> bi((size_t)d.cout_pad, 0);
+    for (int co = 0; co < c.cout; ++co) bi[co] = (int32_t)bias[co];
+    if (!(st = dev_upload(tmp, &d_bi, bi)).ok()) return st;
+  }
   if (c.quant) {
     std::vector<float> qp((size_t)d.cout_pad, 0.f);
     for (int co = 0; co < c.cout; ++co) qp[co] = cd->qmul[co];
@@ -764,6 +828,17 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
           for (int ci = 0; ci < 3; ++ci)
             xp[(((size_t)i * rows + yy + kStemPadTop) * pitch + xx + kStemPadLeft) * 4 + ci] = xh[(((size_t)i * h + yy) * w + xx) * 3 + ci];
     if (!(st = dev_upload(tmp, &d_x, xp)).ok()) return st;
+  } else if (d.mode == 3) {   // u8 activations (zero point 0: the caller's centred values are the raw q)
+    const __half* xh = reinterpret_cast<const __half*>(x);
+    std::vector<uint8_t> x8((size_t)n * h * w * c.cin);
+    for (size_t j = 0; j < x8.size(); ++j) {
+      const float f = __half2float(xh[j]);
+      if (f < 0.f || f > 255.f) return Status::error(INFUR_E_INVALID_ARG, "conv_test: int8 activations must be in [0, 255] (input zero point 0)");
+      x8[j] = (uint8_t)f;
+    }
+    uint8_t* d_x8 = nullptr;
+    if (!(st = dev_upload(tmp, &d_x8, x8)).ok()) return st;
+    d_x = reinterpret_cast<__half*>(d_x8);
   } else {
     std::vector<__half> xv(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(x) + (size_t)n * h * w * c.cin);
     if (!(st = dev_upload(tmp, &d_x, xv)).ok()) return st;
@@ -773,13 +848,19 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   if (residual) {
     std::vector<__half> rv(reinterpret_cast<const __half*>(residual), reinterpret_cast<const __half*>(residual) + (size_t)n * oh * ow * c.cout);
     if (f32out) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: residual with f32 output is not supported");
-    if (!(st = dev_upload(tmp, &d_res, rv)).ok()) return st;
+    if (d.mode >= 2) {   // u8 residual tensor: raw q = centred value + its zero point
+      std::vector<uint8_t> r8(rv.size());
+      for (size_t j = 0; j < rv.size(); ++j) r8[j] = (uint8_t)(__half2float(rv[j]) + (float)d.res_zp);
+      uint8_t* d_r8 = nullptr;
+      if (!(st = dev_upload(tmp, &d_r8, r8)).ok()) return st;
+      d_res = reinterpret_cast<__half*>(d_r8);
+    } else if (!(st = dev_upload(tmp, &d_res, rv)).ok()) return st;
   }
   if (f32out) { if (!(st = dev_alloc(tmp, &d_yf, ocount)).ok()) return st; CU_TRY(cudaMemset(d_yf, 0, ocount * 4)); }
   else { if (!(st = dev_alloc(tmp, &d_y, ocount)).ok()) return st; CU_TRY(cudaMemset(d_y, 0, ocount * 2)); }
   ConvIO io;
   io.x = d_x; io.n = n; io.h = h; io.w = w; io.oh = oh; io.ow = ow; io.wgt = d_w; io.bias = d_b; io.residual = d_res; io.y = d_y; io.y_f32 = d_yf;
-  io.out_ld = out_ld; io.qmul = d_q;
+  io.out_ld = out_ld; io.qmul = d_q; io.bias_i32 = d_bi;
   PlanOp po;
   if (pair && (d.block_n != 256 || d.stem || f32out)) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the CTA-pair variant needs cout % 256 == 0 and an fp16 output");
   if (halo && !halo_ok(d)) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the halo variant needs a 3x3 / stride 1 / pad = dilation convolution");
@@ -807,6 +888,12 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
     for (size_t px = 0; px < (size_t)n * oh * ow; ++px)
       for (int co = 0; co < c.cout; ++co) y_f32[px * c.cout + co] = tmpo[px * out_ld + co];
   } else {
+    if (d.mode >= 2) {   // u8 output: hand back the centred values (q - zero point) like the fp16-carried form does
+      std::vector<uint8_t> y8(ocount);
+      CU_TRY(cudaMemcpy(y8.data(), d_y, ocount, cudaMemcpyDeviceToHost));
+      __half* yh = reinterpret_cast<__half*>(y);
+      for (size_t j = 0; j < ocount; ++j) yh[j] = __float2half_rn((float)((int)y8[j] - d.out_zp));
+    } else
     CU_TRY(cudaMemcpy(y, d_y, ocount * 2, cudaMemcpyDeviceToHost));
   }
   return Status();

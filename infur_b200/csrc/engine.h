@@ -40,6 +40,11 @@ struct DevConv {
   bool quant = false;
   size_t q_off = 0;
   float q_lo = 0.f, q_hi = 0.f, q_ra = 0.f, q_rb = 0.f, q_lo2 = 0.f, q_hi2 = 0.f, q_deq = 0.f;
+  // int8 plan (DeviceModel::i8): mode 2 = fp16-carried operands with u8 output (stem), 3 = native int8 (u8 x s8 -> s32);
+  // 0 = follow `quant` with fp16 tensors.  u8 tensors hold the raw q: zero points of the residual and of the output.
+  int mode = 0;
+  int res_zp = 0, out_zp = 0;
+  size_t bi_off = 0;       // mode 3: int32 bias [cout_pad]
 };
 
 struct DeviceModel {
@@ -49,6 +54,7 @@ struct DeviceModel {
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   int out_head = -1, aux_head = -1;
+  bool i8 = false;               // quantised model run as an int8 plan: u8 activation tensors, native int8 convolutions
   size_t lut_q_off = 0;          // quantised models: fp16 [3][256] pre-kernel table of QuantizeLinear(input) - zero point
   ~DeviceModel();
 };

@@ -190,6 +190,35 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const __half* __restric
   }
 }
 
+// The same pool on u8 tensors (int8 plans: the raw quantised values; max commutes with the affine quantisation map):
+// thread = (16 channels, output column), __vmaxu4 on packed bytes.
+__global__ void __launch_bounds__(256) maxpool3s2_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int h, int w, int c16, int oh, int ow) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ow * c16) return;
+  const int cg = idx % c16, ox = idx / c16;
+  const int img = blockIdx.z;
+  const int oy0 = blockIdx.y * kPoolStrip, oy1 = min(oy0 + kPoolStrip, oh);
+  const uint4* src = reinterpret_cast<const uint4*>(in) + (size_t)img * h * w * c16 + cg;
+  uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)img * oh * ow * c16 + (size_t)ox * c16 + cg;
+  const int ix = 2 * ox;
+  auto vmax = [](uint4 a, uint4 b) { return make_uint4(__vmaxu4(a.x, b.x), __vmaxu4(a.y, b.y), __vmaxu4(a.z, b.z), __vmaxu4(a.w, b.w)); };
+  auto hrow = [&](int iy) {
+    const uint4* row = src + (size_t)iy * w * c16;
+    uint4 r = __ldg(row + (size_t)ix * c16);
+    if (ix > 0) r = vmax(r, __ldg(row + (size_t)(ix - 1) * c16));
+    if (ix + 1 < w) r = vmax(r, __ldg(row + (size_t)(ix + 1) * c16));
+    return r;
+  };
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);   // identity of max on u8
+  uint4 prev = oy0 > 0 ? hrow(2 * oy0 - 1) : zero;
+  for (int oy = oy0; oy < oy1; ++oy) {
+    const uint4 a = hrow(2 * oy);
+    const uint4 b = 2 * oy + 1 < h ? hrow(2 * oy + 1) : zero;
+    dst[(size_t)oy * ow * c16] = vmax(vmax(prev, a), b);
+    prev = b;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: the network's final Resize(linear, half_pixel) fused with ColorCode::advance
 // (infur/src/decode_predict.rs:53-79) and color_code (:32-36).  One CTA = one 32 x 32 output tile:
@@ -520,6 +549,13 @@ cudaError_t launch_maxpool(const __half* in, __half* out, int n, int h, int w, i
   }
   const size_t total = (size_t)n * oh * ow * (c / 8);
   maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, n, h, w, c / 8, oh, ow, k, stride, pad);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool3s2_u8(const uint8_t* in, uint8_t* out, int n, int h, int w, int c, int oh, int ow, cudaStream_t s) {
+  const int c16 = c / 16;
+  dim3 grid((unsigned)((ow * c16 + 255) / 256), (unsigned)((oh + kPoolStrip - 1) / kPoolStrip), (unsigned)n);
+  maxpool3s2_u8_kernel<<<grid, 256, 0, s>>>(in, out, h, w, c16, oh, ow);
   return cudaGetLastError();
 }
 

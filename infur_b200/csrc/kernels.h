@@ -36,6 +36,8 @@ cudaError_t launch_pre(const PreArgs& a, cudaStream_t s);
 cudaError_t launch_preprocess_f32(const uint8_t* bgr, int h, int w, const float* lut_f, float* out, cudaStream_t s);
 
 // MaxPool k x k / stride / pad over NHWC fp16, c % 8 == 0
+// 3x3 / stride 2 / pad 1 pooling of a u8 NHWC tensor (int8 plans), c % 16 == 0
+cudaError_t launch_maxpool3s2_u8(const uint8_t* in, uint8_t* out, int n, int h, int w, int c, int oh, int ow, cudaStream_t s);
 cudaError_t launch_maxpool(const __half* in, __half* out, int n, int h, int w, int c, int oh, int ow, int k, int stride, int pad,
                            cudaStream_t s);
 

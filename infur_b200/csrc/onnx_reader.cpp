@@ -464,6 +464,7 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
         c.qmul[o] = q;
       }
       c.q_lo = (float)(yq.qmin - yq.zp); c.q_hi = (float)(yq.qmax - yq.zp);
+      c.x_zp = xq.zp; c.out_zp = yq.zp; c.all_u8 = xq.qmin == 0 && yq.qmin == 0;
       op.in = need(n.in[0], n);
       need_q(op.in, xq, n, "x");
       if (m.tensor_channels[op.in] != c.cin) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearConv '" + n.name + "': input has " + std::to_string(m.tensor_channels[op.in]) + " channels, weight expects " + std::to_string(c.cin));
@@ -496,6 +497,7 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       // ONNX Runtime's QLinearAdd: C = sat(rne(A_scale / C_scale * (A - A_zp) + B_scale / C_scale * (B - B_zp)) + C_zp), f32
       { volatile float ra = ms / cs, rb = os_ / cs; op.conv.q_ra = ra; op.conv.q_rb = rb; }
       op.conv.q_lo2 = (float)(cq.qmin - cq.zp); op.conv.q_hi2 = (float)(cq.qmax - cq.zp);
+      op.conv.out_zp = cq.zp; op.conv.res_zp = oq.zp; op.conv.all_u8 = op.conv.all_u8 && cq.qmin == 0 && oq.qmin == 0;
       std::string final_name;
       op.conv.relu = take_relu(n.out[0], final_name);
       emit(std::move(op), final_name);

@@ -89,6 +89,10 @@ struct ConvOp {
   std::vector<float> qmul;           // [cout]
   float q_lo = 0.f, q_hi = 0.f, q_ra = 0.f, q_rb = 0.f, q_lo2 = 0.f, q_hi2 = 0.f;
   float deq_scale = 0.f;
+  // zero points of the input, of the stored output (the Add's when there is one) and of the residual, and whether all of
+  // those tensors are u8: what an int8 plan (u8 activation tensors holding the raw q) needs to know
+  int x_zp = 0, out_zp = 0, res_zp = 0;
+  bool all_u8 = true;
 };
 
 struct LoweredOp {

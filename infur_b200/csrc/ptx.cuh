@@ -143,6 +143,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::i8: u8 / s8 inputs, s32 accumulation, K = 32 per instruction (twice the MAC rate of kind::f16 on sm_100a; the
+// instruction does not exist on sm_103a).
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // All previously issued tcgen05.mma of this thread arrive on the mbarrier when they retire
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -272,6 +282,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t smem_addr, uin
 //   [15] A major 0 = K   [16] B major 0 = K   [17,23) N >> 3   [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// Instruction descriptor for kind::i8: A = u8 (format 0), B = s8 (format 1), both K-major, s32 accumulate (D format 2).
+__host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t m, uint32_t n) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -320,6 +320,7 @@ class Handle:
             d.qmul = qmul.ctypes.data
             for k in ("q_lo", "q_hi", "q_ra", "q_rb", "q_lo2", "q_hi2", "q_deq"):
                 setattr(d, k, float(quant.get(k, 0.0)))
+            d.q_zres, d.q_zout = int(quant.get("q_zres", 0)), int(quant.get("q_zout", 0))
         y = np.zeros((n, oh, ow, cout), dtype=np.float32 if f32_out else np.float16)
         res = np.ascontiguousarray(residual, dtype=np.float16) if residual is not None else None
         ms = C.c_float()

@@ -34,11 +34,33 @@ QCASES = [
 ]
 
 
-@pytest.mark.parametrize("case", QCASES, ids=lambda c: "n%d_%dx%d_c%d-%d_k%d_s%d_p%d_d%d%s_impl%d%s" % (c[:9] + ("_add" if c[9] else "", c[10], "_deq" if c[11] else "")))
+def _case_id(c):
+    return "n%d_%dx%d_c%d-%d_k%d_s%d_p%d_d%d%s_impl%d%s" % (c[:9] + ("_add" if c[9] else "", c[10], "_deq" if c[11] else ""))
+
+
+@pytest.mark.parametrize("case", QCASES, ids=_case_id)
 def test_qlinear_conv_bit_exact(handle, case):
+    _run_qcase(handle, case, x_zp=117)
+
+
+# the same layers as an int8 plan runs them: u8 tensors in HBM, tcgen05.mma.kind::i8 with s32 accumulators (the RGB stem keeps
+# fp16-carried operands and writes u8).  Input zero point 0, as for every post-ReLU tensor of the network.
+I8CASES = [c[:10] + (L.CONV_TCGEN05_I8, c[11]) for c in QCASES if c[10] == L.CONV_TCGEN05] + [
+    (1, 30, 40, 256, 512, 1, 1, 0, 1, True, L.CONV_TCGEN05_I8, False),
+    (1, 33, 47, 128, 128, 3, 1, 2, 2, False, L.CONV_TCGEN05_I8, False),
+    (2, 17, 23, 1024, 256, 1, 1, 0, 1, False, L.CONV_TCGEN05_I8, False),
+]
+
+
+@pytest.mark.parametrize("case", I8CASES, ids=_case_id)
+def test_qlinear_conv_native_int8_bit_exact(handle, case):
+    _run_qcase(handle, case, x_zp=117 if case[3] == 3 else 0)
+
+
+def _run_qcase(handle, case, x_zp):
     n, h, w, cin, cout, k, stride, pad, dil, res, impl, f32 = case
-    rng = np.random.default_rng(abs(hash(case)) % 2**31)
-    x_zp, y_zp, r_zp, c_zp = 117, 128 if (res or f32) else 0, 0, 0
+    rng = np.random.default_rng(abs(hash(case[:10])) % 2**31)
+    y_zp, r_zp, c_zp = 128 if (res or f32) else 0, 37 if impl == L.CONV_TCGEN05_I8 else 0, 0
     xq = rng.integers(0, 256, size=(n, cin, h, w), dtype=np.uint8)
     wq = rng.integers(-127, 128, size=(cout, cin, k, k), dtype=np.int8)
     bq = rng.integers(-20000, 20000, size=cout, dtype=np.int32)
@@ -46,15 +68,15 @@ def test_qlinear_conv_bit_exact(handle, case):
     w_scale = (rng.random(cout).astype(np.float32) + np.float32(0.5)) * np.float32(y_scale / x_scale / (40.0 * np.sqrt(cin * k * k)))
     stats = []
     yq = qlinear.qlinear_conv(xq, x_scale, np.uint8(x_zp), wq, w_scale, np.zeros(cout, np.int8), y_scale, np.uint8(y_zp), bq, stride, pad, dil, stats)
-    assert stats[0] < 2**24                      # the exactness condition of the fp16-operand representation
-    quant = {"qmul": (x_scale * w_scale) / y_scale, "q_lo": -y_zp, "q_hi": 255 - y_zp}
+    assert stats[0] < (2**31 if impl == L.CONV_TCGEN05_I8 else 2**24)   # fp16-carried operands: exact below 2^24; native int8: int32
+    quant = {"qmul": (x_scale * w_scale) / y_scale, "q_lo": -y_zp, "q_hi": 255 - y_zp, "q_zout": y_zp}
     expect = yq.astype(np.int32) - y_zp
     rq = None
     if res:
         rq = rng.integers(0, 256, size=yq.shape, dtype=np.uint8)
         r_scale, c_scale = np.float32(0.017), np.float32(0.031)
         cq = qlinear.qlinear_add(yq, y_scale, np.uint8(y_zp), rq, r_scale, np.uint8(r_zp), c_scale, np.uint8(c_zp))
-        quant.update(q_ra=y_scale / c_scale, q_rb=r_scale / c_scale, q_lo2=-c_zp, q_hi2=255 - c_zp)
+        quant.update(q_ra=y_scale / c_scale, q_rb=r_scale / c_scale, q_lo2=-c_zp, q_hi2=255 - c_zp, q_zres=r_zp, q_zout=c_zp)
         expect = cq.astype(np.int32) - c_zp
     if f32:
         quant["q_deq"] = y_scale
