@@ -34,6 +34,7 @@ CONV_VALIDATE = 1
 CONV_TCGEN05_PAIR = 2   # conv_test only
 CONV_TCGEN05_HALO = 3   # conv_test only
 CONV_TCGEN05_I8 = 4     # conv_test only: int8 plan form of a quantised layer
+CONV_TCGEN05_I8_PAIR = 5
 LOAD_DEFAULT = 0
 LOAD_SKIP_WEIGHTS = 1
 

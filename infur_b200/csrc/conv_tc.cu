@@ -267,6 +267,17 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
         } else if (use >= 1) {
           ptx::mbar_wait(eb.free_ + 8u * b, (use - 1u) & 1u);
         }
+        // Requantisation in f32 exactly as in the fp16-carried form; what differs is getting integers in and out cheaply:
+        //  * a residual byte b becomes the float 2^23 + b by placing it in the low mantissa byte of 0x4B000000 (PRMT), so
+        //    b - zero_point is ONE add of -(2^23 + zero_point)  (exact);
+        //  * rne(v) for the clamped v is v + 1.5 * 2^23 (one add); the result's low mantissa bits hold rne(v) as an integer, the
+        //    output zero point is added to those bits with an integer add, and PRMT gathers the four low bytes of a word.
+        //    (Adding the zero point before rounding would break ties differently whenever it is odd.)
+        const float lo1 = g.q_lo, hi1 = g.q_hi;
+        const float lo2 = g.relu ? fmaxf(g.q_lo2, 0.f) : g.q_lo2, hi2 = g.q_hi2;
+        const float lo_out = (!HAS_RES && g.relu) ? fmaxf(lo1, 0.f) : lo1;
+        const float res_bias = -(8388608.f + g.q_zres);
+        const uint32_t zout = (uint32_t)(int)(g.q_zmagic - kRneMagic);
         uint32_t ow[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {            // 4 channels -> one 32-bit word of u8
@@ -278,20 +289,30 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
             t[2] = __int2float_rn((int)acc[4 * j + 2] + bi.z); t[3] = __int2float_rn((int)acc[4 * j + 3] + bi.w);
           } else {
             const float4 bf = __ldg(reinterpret_cast<const float4*>(g.bias + cofs) + j);
-            t[0] = __uint_as_float(acc[4 * j + 0]) + bf.x; t[1] = __uint_as_float(acc[4 * j + 1]) + bf.y;
-            t[2] = __uint_as_float(acc[4 * j + 2]) + bf.z; t[3] = __uint_as_float(acc[4 * j + 3]) + bf.w;
+            t[0] = __uint_as_float(acc[4 * j + 0]); t[1] = __uint_as_float(acc[4 * j + 1]);
+            t[2] = __uint_as_float(acc[4 * j + 2]); t[3] = __uint_as_float(acc[4 * j + 3]);
+            ptx::add_f32x2(t[0], t[1], bf.x, bf.y); ptx::add_f32x2(t[2], t[3], bf.z, bf.w);
           }
-          const float mm[4] = {m.x, m.y, m.z, m.w};
-          uint32_t word = 0;
+          ptx::mul_f32x2(t[0], t[1], m.x, m.y); ptx::mul_f32x2(t[2], t[3], m.z, m.w);
+          uint32_t bits[4];
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            float r = requant(t[x], mm[x], g.q_lo, g.q_hi);
-            if (HAS_RES) r = requant_add(r, g.q_ra, __uint2float_rn((rw[j] >> (8 * x)) & 0xffu) - g.q_zres, g.q_rb, g.q_lo2, g.q_hi2);
-            if (g.relu) r = fmaxf(r, 0.f);
-            // r + zero point is an integer in [0, 255]: with 1.5 * 2^23 added it sits in the low mantissa bits
-            word |= (__float_as_uint(__fadd_rn(r, g.q_zmagic)) & 0xffu) << (8 * x);
+          for (int x = 0; x < 4; x += 2) {
+            float a0 = fminf(fmaxf(t[x], lo_out), hi1), a1 = fminf(fmaxf(t[x + 1], lo_out), hi1);
+            ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);                       // rne(v) + 1.5 * 2^23
+            if (HAS_RES) {
+              ptx::add_f32x2(a0, a1, -kRneMagic, -kRneMagic);                   // rne(v) as a float
+              float b0 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x));        // 2^23 + residual byte
+              float b1 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x + 1));
+              ptx::add_f32x2(b0, b1, res_bias, res_bias);                         // residual - its zero point
+              ptx::mul_f32x2(a0, a1, g.q_ra, g.q_ra);
+              ptx::mul_f32x2(b0, b1, g.q_rb, g.q_rb);
+              ptx::add_f32x2(a0, a1, b0, b1);
+              a0 = fminf(fmaxf(a0, lo2), hi2); a1 = fminf(fmaxf(a1, lo2), hi2);
+              ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);
+            }
+            bits[x] = __float_as_uint(a0) + zout; bits[x + 1] = __float_as_uint(a1) + zout;
           }
-          ow[j] = word;
+          ow[j] = __byte_perm(__byte_perm(bits[0], bits[1], 0x0040), __byte_perm(bits[2], bits[3], 0x0040), 0x5410);
         }
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowq), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowq + 16u), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
@@ -600,23 +621,29 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
 //   full[s]   lives in the leader: its producer arms 64 KB; both CTAs' TMA loads complete_tx on it
 //   empty[s], tmem_full[a]   one per CTA, signalled by the leader's multicast tcgen05.commit
 //   tmem_empty[a]   in the leader, counts the epilogue warps of BOTH CTAs (remote mbarrier arrive)
-constexpr int kPairStageBytes = kABytes + 128 * kBlockK * 2;   // 32 KB
+constexpr int kPairStageBytes = kABytes + 128 * kBlockK * 2;   // 32 KB; int8 plans: half of it
 
-__host__ __device__ constexpr int pair_stages(int epi_bufs) {
-  const int s = (kSmemLimit - 1024 - kBarBytes - epi_bufs * kEpiBufBytes) / kPairStageBytes;
+__host__ __device__ constexpr int pair_stages(int epi_bufs, bool i8 = false) {
+  const int s = (kSmemLimit - 1024 - kBarBytes - epi_bufs * kEpiBufBytes) / (i8 ? kPairStageBytes / 2 : kPairStageBytes);
   return s > kMaxStages ? kMaxStages : s;
 }
-__host__ __device__ constexpr int pair_smem_bytes(int epi_bufs) { return pair_stages(epi_bufs) * kPairStageBytes + epi_bufs * kEpiBufBytes + 1024 + kBarBytes; }
+__host__ __device__ constexpr int pair_smem_bytes(int epi_bufs, bool i8 = false) {
+  return pair_stages(epi_bufs, i8) * (i8 ? kPairStageBytes / 2 : kPairStageBytes) + epi_bufs * kEpiBufBytes + 1024 + kBarBytes;
+}
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   constexpr int BLOCK_N = 256;
+  constexpr bool I8 = MODE == 3;
+  constexpr int kStage = I8 ? kPairStageBytes / 2 : kPairStageBytes;   // A (128 px) + half of B (128 channels) per CTA
+  constexpr int kAB = I8 ? kABytes / 2 : kABytes;
+  constexpr uint32_t kRowBytes = I8 ? 64 : 128;
   constexpr int ACC = 2;
   extern __shared__ uint8_t smem_raw[];
   const int num_stages = g.stages;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem_base + num_stages * kPairStageBytes;
+  const uint32_t epi_base = smem_base + num_stages * kStage;
   const uint32_t bar_base = epi_base + g.epi_bufs * kEpiBufBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -671,11 +698,11 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
         const TileCoord tc = decode_tile(g, tile);
         auto load_kblock = [&](int tap, int cc, int kcoord) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = smem_base + stage * kPairStageBytes;
+          const uint32_t a_dst = smem_base + stage * kStage;
           const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
-          if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2u * (uint32_t)kPairStageBytes);
+          if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2u * (uint32_t)kStage);
           ptx::tma_load_4d_2sm(a_dst, &maps.a[g.tap_view[tap]], lead_full, cc * kBlockK, tc.ox0 + g.tap_dx[tap], tc.oy0 + g.tap_dy[tap], tc.img);
-          ptx::tma_load_2d_2sm(a_dst + kABytes, &maps.b, lead_full, kcoord, tc.nt * BLOCK_N + rank * 128);
+          ptx::tma_load_2d_2sm(a_dst + kAB, &maps.b, lead_full, kcoord, tc.nt * BLOCK_N + rank * 128);
           if (++stage == num_stages) { stage = 0; phase ^= 1u; }
         };
         for (int cc = 0; cc < g.cchunks; ++cc)      // chunk-major K order, see conv_tc_kernel
@@ -687,7 +714,7 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0 && ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kBlockM, BLOCK_N);
+      constexpr uint32_t idesc = I8 ? ptx::make_idesc_i8(2 * kBlockM, BLOCK_N) : ptx::make_idesc_f16(2 * kBlockM, BLOCK_N);
       const int num_kb = g.num_kb;
       int stage = 0;
       uint32_t phase = 0;
@@ -701,12 +728,14 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * kPairStageBytes;
-          const uint64_t a_desc = ptx::make_smem_desc(a_addr, 128);
-          const uint64_t b_desc = ptx::make_smem_desc(a_addr + kABytes, 128);
+          const uint32_t a_addr = smem_base + stage * kStage;
+          const uint64_t a_desc = ptx::make_smem_desc(a_addr, kRowBytes);
+          const uint64_t b_desc = ptx::make_smem_desc(a_addr + kAB, kRowBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            ptx::umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int k = 0; k < (I8 ? kBlockK / 32 : kBlockK / 16); ++k) {
+            if (I8) ptx::umma_i8_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else ptx::umma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
           ptx::umma_commit_2sm(empty_bar(stage), 3);
           if (++stage == num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -715,8 +744,8 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
     }
   } else if (warp == kDmaWarp) {
     if (ptx::elect_one()) {
-      if (g.store_mode == 1) epilogue_dma<BLOCK_N, false, Sched2, 4>(maps, g, sched, eb, epi_base);
-      else epilogue_dma<BLOCK_N, true, Sched2, 4>(maps, g, sched, eb, epi_base);
+      if (g.store_mode == 1) epilogue_dma<BLOCK_N, false, Sched2, 4, (MODE >= 2 ? kEpiBufBytes / 2 : kEpiBufBytes)>(maps, g, sched, eb, epi_base);
+      else epilogue_dma<BLOCK_N, true, Sched2, 4, (MODE >= 2 ? kEpiBufBytes / 2 : kEpiBufBytes)>(maps, g, sched, eb, epi_base);
     }
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;
@@ -1060,7 +1089,7 @@ cudaError_t launch_one(const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms,
 
 }  // namespace
 
-int conv_tc_pair_stages(int epi_bufs) { return pair_stages(epi_bufs); }
+int conv_tc_pair_stages(int epi_bufs, bool i8) { return pair_stages(epi_bufs, i8); }
 
 int conv_tc_stages(int block_n, int epi_bufs, bool i8) {
   switch (block_n) {
@@ -1082,7 +1111,7 @@ cudaError_t conv_tc_init() {
   opt_in(conv_halo_kernel<64, 0>, kSmemLimit); opt_in(conv_halo_kernel<64, 1>, kSmemLimit);
   opt_in(conv_halo_kernel<128, 0>, kSmemLimit); opt_in(conv_halo_kernel<128, 1>, kSmemLimit);
   opt_in(conv_halo_kernel<256, 0>, kSmemLimit); opt_in(conv_halo_kernel<256, 1>, kSmemLimit);
-  opt_in(conv_tc_pair_kernel<0>, kSmemLimit); opt_in(conv_tc_pair_kernel<1>, kSmemLimit);
+  opt_in(conv_tc_pair_kernel<0>, kSmemLimit); opt_in(conv_tc_pair_kernel<1>, kSmemLimit); opt_in(conv_tc_pair_kernel<3>, kSmemLimit);
   return e;
 }
 
@@ -1117,7 +1146,8 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
   if (g.pair) {
     const int clusters = g.num_work < num_sms / 2 ? g.num_work : num_sms / 2;
     if (clusters <= 0) return cudaSuccess;
-    if (block_n != 256 || g.store_mode == 0 || g.stages != pair_stages(g.epi_bufs) || g.mode > 1) return cudaErrorInvalidValue;
+    if (block_n != 256 || g.store_mode == 0 || g.stages != pair_stages(g.epi_bufs, g.mode == 3) || g.mode == 2) return cudaErrorInvalidValue;
+    if (g.mode == 3) return launch_conv(conv_tc_pair_kernel<3>, 2 * clusters, pair_smem_bytes(g.epi_bufs, true), stream, maps, g);
     if (g.mode == 1) return launch_conv(conv_tc_pair_kernel<1>, 2 * clusters, pair_smem_bytes(g.epi_bufs), stream, maps, g);
     return launch_conv(conv_tc_pair_kernel<0>, 2 * clusters, pair_smem_bytes(g.epi_bufs), stream, maps, g);
   }

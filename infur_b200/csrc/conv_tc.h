@@ -69,6 +69,6 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
 // One-time: opt in to the dynamic shared memory each instantiation needs.
 cudaError_t conv_tc_init();
 int conv_tc_stages(int block_n, int epi_bufs, bool i8 = false);
-int conv_tc_pair_stages(int epi_bufs);
+int conv_tc_pair_stages(int epi_bufs, bool i8 = false);
 
 }  // namespace infur

@@ -287,9 +287,9 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   if (g.store_mode == 1 && !pair && !halo && !d.stem && conv_tc_stages(block_n, 4) < 4 && g.num_kb > 8) g.epi_bufs = 2;
   const int esz = d.mode == 3 ? 1 : 2;      // operand element size
   const int osz = d.mode >= 2 ? 1 : 2;      // output / residual element size
-  if (d.mode >= 2 && (pair || halo)) return Status::error(INFUR_E_UNSUPPORTED, "int8 plans use the plain and stem kernels only");
+  if ((d.mode >= 2 && halo) || (d.mode == 2 && pair)) return Status::error(INFUR_E_UNSUPPORTED, "int8 plans use the plain, CTA-pair and stem kernels only");
   if (d.mode == 3) g.epi_bufs = g.store_mode == 0 ? 0 : 4;
-  g.stages = pair ? conv_tc_pair_stages(g.epi_bufs) : conv_tc_stages(block_n, g.epi_bufs, d.mode == 3);
+  g.stages = pair ? conv_tc_pair_stages(g.epi_bufs, d.mode == 3) : conv_tc_stages(block_n, g.epi_bufs, d.mode == 3);
   g.pair = pair ? 1 : 0;
   g.halo = halo ? 1 : 0; g.halo_dil = d.dil;
   if (halo) { if (!halo_ok(d) || io.y_f32 || io.residual) return Status::error(INFUR_E_UNSUPPORTED, "halo variant: needs a 3x3 / stride 1 / pad = dilation convolution without residual"); g.stages = 0; }
@@ -420,7 +420,7 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
   for (int round = 0; round < 3 && st.ok(); ++round) {
     for (const Cand& c : cands) {
       if (c.bn > d.block_n || d.cout_pad % c.bn != 0 || (c.var == kVarPair && !allow_pair) || (c.var == kVarHalo && !allow_halo)) continue;
-      if (d.mode >= 2 && c.var != kVarPlain) continue;   // int8 plans: plain kernel only
+      if (d.mode >= 2 && c.var == kVarHalo) continue;   // int8 plans: plain and CTA-pair kernels
       PlanOp trial;
       if (!(st = setup_conv_tc(d, io, trial, c.bn, c.var)).ok()) break;
       cudaError_t e = conv_tc_launch(c.bn, trial.maps, trial.geom, H->num_sms, H->stream);   // warm-up
@@ -763,9 +763,9 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   const bool f32out = y_f32 != nullptr;
   DevConv d;
   classify_conv(c, c.cin == 3, f32out, d);
-  const bool pair = cd->impl == INFUR_CONV_TCGEN05_PAIR;
+  const bool pair = cd->impl == INFUR_CONV_TCGEN05_PAIR || cd->impl == INFUR_CONV_TCGEN05_I8_PAIR;
   const bool halo = cd->impl == INFUR_CONV_TCGEN05_HALO;
-  const bool i8 = cd->impl == INFUR_CONV_TCGEN05_I8;
+  const bool i8 = cd->impl == INFUR_CONV_TCGEN05_I8 || cd->impl == INFUR_CONV_TCGEN05_I8_PAIR;
   const bool tc = cd->impl == INFUR_CONV_TCGEN05 || pair || halo || i8;
   if (i8) {
     // int8 plan form of the layer: the RGB stem keeps fp16-carried operands and writes u8 (mode 2), everything else is native int8

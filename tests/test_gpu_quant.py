@@ -49,6 +49,10 @@ I8CASES = [c[:10] + (L.CONV_TCGEN05_I8, c[11]) for c in QCASES if c[10] == L.CON
     (1, 30, 40, 256, 512, 1, 1, 0, 1, True, L.CONV_TCGEN05_I8, False),
     (1, 33, 47, 128, 128, 3, 1, 2, 2, False, L.CONV_TCGEN05_I8, False),
     (2, 17, 23, 1024, 256, 1, 1, 0, 1, False, L.CONV_TCGEN05_I8, False),
+    (1, 30, 40, 256, 512, 1, 1, 0, 1, True, L.CONV_TCGEN05_I8_PAIR, False),
+    (1, 30, 40, 512, 256, 1, 1, 0, 1, False, L.CONV_TCGEN05_I8_PAIR, False),
+    (1, 33, 47, 256, 256, 3, 1, 2, 2, False, L.CONV_TCGEN05_I8_PAIR, False),
+    (2, 31, 45, 512, 512, 3, 1, 4, 4, False, L.CONV_TCGEN05_I8_PAIR, False),
 ]
 
 
@@ -60,7 +64,8 @@ def test_qlinear_conv_native_int8_bit_exact(handle, case):
 def _run_qcase(handle, case, x_zp):
     n, h, w, cin, cout, k, stride, pad, dil, res, impl, f32 = case
     rng = np.random.default_rng(abs(hash(case[:10])) % 2**31)
-    y_zp, r_zp, c_zp = 128 if (res or f32) else 0, 37 if impl == L.CONV_TCGEN05_I8 else 0, 0
+    i8 = impl in (L.CONV_TCGEN05_I8, L.CONV_TCGEN05_I8_PAIR)
+    y_zp, r_zp, c_zp = 128 if (res or f32) else 0, 37 if i8 else 0, 0
     xq = rng.integers(0, 256, size=(n, cin, h, w), dtype=np.uint8)
     wq = rng.integers(-127, 128, size=(cout, cin, k, k), dtype=np.int8)
     bq = rng.integers(-20000, 20000, size=cout, dtype=np.int32)
@@ -68,7 +73,7 @@ def _run_qcase(handle, case, x_zp):
     w_scale = (rng.random(cout).astype(np.float32) + np.float32(0.5)) * np.float32(y_scale / x_scale / (40.0 * np.sqrt(cin * k * k)))
     stats = []
     yq = qlinear.qlinear_conv(xq, x_scale, np.uint8(x_zp), wq, w_scale, np.zeros(cout, np.int8), y_scale, np.uint8(y_zp), bq, stride, pad, dil, stats)
-    assert stats[0] < (2**31 if impl == L.CONV_TCGEN05_I8 else 2**24)   # fp16-carried operands: exact below 2^24; native int8: int32
+    assert stats[0] < (2**31 if i8 else 2**24)   # fp16-carried operands: exact below 2^24; native int8: int32
     quant = {"qmul": (x_scale * w_scale) / y_scale, "q_lo": -y_zp, "q_hi": 255 - y_zp, "q_zout": y_zp}
     expect = yq.astype(np.int32) - y_zp
     rq = None
