@@ -348,10 +348,13 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         n_conv = sum(1 for ln in op_lines if ln.startswith("conv "))
         flops = B * FLOPS_NO_AUX[(W, H)]
         achieved = flops / (conv_ms * 1e-3) / 1e12
+        # int8 plan: MEASURED_PEAKS.json has no int8 figure; kind::i8 issues at exactly twice the kind::f16 MAC rate on this part
+        # (tools/ubench_mma.cu, profiles/r1_ubench_mma.txt), so the denominator is twice the measured sustained bf16 peak
+        tensor_peak = pk["bf16_tflops_sustained"] * (2.0 if args.model == "int8" else 1.0)
         roofline = {
             "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv+bias+ReLU(+residual)), all %d launches of one step" % n_conv,
-            "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": CONV_DRAM_BYTES_PER_LAUNCH if args.model == "f16" else None,
+            "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TOP/s" if args.model == "int8" else "TFLOP/s",
+            "frac": achieved / tensor_peak, "traffic": CONV_DRAM_BYTES_PER_LAUNCH if args.model == "f16" else None,
             "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of one step (8 frames) / launches, from "
                              "profiles/r1_launches_step_b8_1080p.csv; algorithmic bytes per launch = 8 x 3546.9 MB (layer-wise, shortcuts fused) / launches")
                             if args.model == "f16" else "no ncu capture of the quantised plan yet; algorithmic bytes per launch from plan_text",
@@ -393,7 +396,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         out = {
             "metric": "1080p frames/sec through FCN-ResNet50", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": dtype if dtype == "f16" else "int8 (integers carried exactly in f16 tensor-core operands, f32 accumulators < 2^24)", "data": "synthetic",
+            "dtype": dtype if dtype == "f16" else "int8 (u8 activations x s8 weights -> s32 on tcgen05.mma.kind::i8; the RGB stem on fp16-carried integers)", "data": "synthetic",
             "config": {"workload": "configs[2]: 1080p synthetic stream, batch=8 frames per step per GPU, " + model_label +
                                    ", scale 1.0, out head only, class map + premultiplied RGBA out",
                        "frames_per_step_per_gpu": B, "width": W, "height": H, "ring_depth": depth, "sharding": "frames by rank, no collective",

@@ -83,7 +83,7 @@ static inline int floordiv(int a, int b) { int q = a / b; if ((a % b != 0) && ((
 static bool skip_fusion_env() { const char* e = getenv("INFUR_B200_NO_SHORTCUT_FUSION"); return e && e[0] == '1'; }
 
 static bool halo_disabled_env() { const char* e = getenv("INFUR_B200_NO_HALO"); return e && e[0] == '1'; }
-static bool i8_enabled_env() { const char* e = getenv("INFUR_B200_I8"); return e && e[0] == '1'; }
+static bool i8_enabled_env() { const char* e = getenv("INFUR_B200_I8"); return !(e && e[0] == '0'); }   // INFUR_B200_I8=0: keep quantised models on fp16-carried tensors
 static bool pair_disabled_env() { const char* e = getenv("INFUR_B200_NO_CTA_PAIR"); return e && e[0] == '1'; }
 
 static void classify_conv(const ConvOp& c, bool reads_input, bool is_head, DevConv& d) {
@@ -621,17 +621,19 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       }
       setup_direct(d, io, reinterpret_cast<const __half*>(M->arena + d.wv_off), po.direct);
       po.flops = 2.0 * n * to.h * to.w * (double)d.cout * (d.kh * d.kw * d.cin + d.cin2);
-      po.bytes = (double)n * ti.h * ti.w * d.cin * 2 + (double)to.bytes + (io.residual ? (double)n * to.h * to.w * to.c * 2 : 0.0) +
-                 (double)d.cout * (d.kh * d.kw * d.cin + d.cin2) * 2 + (io.x2 ? (double)n * io.h2 * io.w2 * d.cin2 * 2 : 0.0);
+      const double xsz = d.mode == 3 ? 1.0 : 2.0, rsz = d.mode >= 2 ? 1.0 : 2.0;   // element sizes of the operands / of the residual
+      po.bytes = (double)n * ti.h * ti.w * d.cin * xsz + (double)to.bytes + (io.residual ? (double)n * to.h * to.w * to.c * rsz : 0.0) +
+                 (double)d.cout * (d.kh * d.kw * d.cin + d.cin2) * xsz + (io.x2 ? (double)n * io.h2 * io.w2 * d.cin2 * 2 : 0.0);
       os << "conv " << op.name << " [" << n << "x" << ti.h << "x" << ti.w << "x" << d.cin << "] -> [" << to.h << "x" << to.w << "x" << d.cout
          << "] k" << d.kh << " s" << d.stride << " p" << d.pad << " d" << d.dil << (io.residual ? " +res" : "") << (d.cin2 ? " +shortcut1x1" : "") << (d.relu ? " relu" : "");
+      if (d.mode == 3) os << " int8";
       if (d.tc_ok)
         os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << po.block_n << (po.variant == kVarPair ? " pair" : (po.variant == kVarHalo ? " halo" : "")) << " tiles "
            << po.geom.num_tiles << " kblocks " << po.geom.num_kb;
       os << " | GFLOP " << po.flops * 1e-9 << " MB " << po.bytes * 1e-6;
     } else {
       po.flops = 0;
-      po.bytes = (double)n * ti.h * ti.w * ti.c * 2 + (double)to.bytes;
+      po.bytes = (double)n * ti.h * ti.w * ti.c * (M->i8 ? 1 : 2) + (double)to.bytes;
       os << "maxpool " << op.name << " [" << n << "x" << ti.h << "x" << ti.w << "x" << ti.c << "] -> [" << to.h << "x" << to.w << "] k" << op.pool_k
          << " s" << op.pool_s << " | MB " << po.bytes * 1e-6;
     }

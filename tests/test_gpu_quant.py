@@ -102,6 +102,20 @@ def tiny_int8():
     return quantize.ensure_fixture("fcn_tiny_int8")
 
 
+@pytest.fixture(params=["int8 plan", "fp16-carried"])
+def plan_kind(request):
+    """Quantised models run as an int8 plan (u8 tensors, native int8 MMA) by default; INFUR_B200_I8=0, read when a model is
+    loaded, keeps them on fp16-carried tensors (also the fallback for models an int8 plan cannot express).  Both are exact."""
+    import os
+    old = os.environ.get("INFUR_B200_I8")
+    os.environ["INFUR_B200_I8"] = "1" if request.param == "int8 plan" else "0"
+    yield request.param
+    if old is None:
+        os.environ.pop("INFUR_B200_I8", None)
+    else:
+        os.environ["INFUR_B200_I8"] = old
+
+
 def test_quantised_model_info(handle, tiny_int8):
     handle.model_load(tiny_int8)
     info = handle.model_info()
@@ -109,8 +123,10 @@ def test_quantised_model_info(handle, tiny_int8):
 
 
 @pytest.mark.parametrize("w,h", [(128, 96), (320, 240), (200, 136)])
-def test_quantised_model_lowres_bit_exact(handle, tiny_int8, w, h):
+def test_quantised_model_lowres_bit_exact(handle, tiny_int8, plan_kind, w, h):
+    handle.model_load("")
     handle.model_load(tiny_int8)
+    assert (" int8 " in handle.plan_text(1, w, h)) == (plan_kind == "int8 plan")
     g = onnx_min.load(tiny_int8)
     frame = synth.synth_frame(w, h, 3)
     env = qlinear.run(g, oracle.preprocess_f32(frame)[None])
@@ -121,10 +137,11 @@ def test_quantised_model_lowres_bit_exact(handle, tiny_int8, w, h):
     assert (got == want).all(), f"{(got != want).sum()} of {got.size} low-resolution logits differ (max {np.abs(got - want).max()})"
 
 
-def test_quantised_pipeline_vs_oracle(handle, tiny_int8):
+def test_quantised_pipeline_vs_oracle(handle, tiny_int8, plan_kind):
     from test_gpu_pipeline import check_against_oracle
     g = onnx_min.load(tiny_int8)
     pipe = P.GpuPipeline(handle)
+    pipe.control(("Model", ""))
     pipe.control(("Model", tiny_int8))
     pipe.control(("Scale", 0.5))
     frame = synth.synth_frame(640, 480, 5)
@@ -152,12 +169,13 @@ def test_quantised_batch_matches_single(handle, tiny_int8):
     assert (res[5]["class_map"] == one["class_map"]).all() and (res[5]["decoded_rgba"] == one["decoded_rgba"]).all()
 
 
-def test_quantised_fcn50_config1(handle):
+def test_quantised_fcn50_config1(handle, plan_kind):
     """configs[0] analogue on the kind of model the reference's tests load (int8 FCN-ResNet50, 320x240): the low-resolution
     logits of all 53 quantised convolutions + 16 quantised adds are bit-exact, the class map follows."""
     from test_gpu_pipeline import check_against_oracle
     path = quantize.ensure_fixture("fcn50_int8")
     g = onnx_min.load(path)
+    handle.model_load("")
     handle.model_load(path)
     handle.scale_control(1.0)
     frame = synth.synth_frame(320, 240, 7)
