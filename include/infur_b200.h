@@ -92,7 +92,11 @@ const char* infur_b200_last_error(const infur_b200_handle* h);
 int32_t infur_b200_scale_control(infur_b200_handle* h, float factor);
 
 /* Model::control(ModelCmd::Load(path)) (predict_onnx.rs:283-315): "" unloads.  On any failure the
- * previously loaded model stays active (:289-308). */
+ * previously loaded model stays active (:289-308).  Accepted graphs: float FCN-style (Conv / Relu / Add / MaxPool / Resize,
+ * computed in fp16 with f32 accumulation) and QOperator-quantised ones (QuantizeLinear / QLinearConv / QLinearAdd /
+ * DequantizeLinear -- the operator set of fcn-resnet50-12-int8.onnx, the file the reference's tests load, :350-381), which
+ * run natively in int8 (u8 x s8 -> s32 tensor-core MMA) when every tensor is u8 with zero-point-0 convolution inputs, else
+ * with the integers carried exactly in fp16; both forms reproduce the integer arithmetic of those operators bit for bit. */
 int32_t infur_b200_model_load(infur_b200_handle* h, const char* utf8_path);
 
 /* Same, from an in-memory copy of the .onnx file (used after a rank-0 broadcast of the file). */
