@@ -47,7 +47,7 @@ constexpr int kDmaWarp = 3;
 
 constexpr int kMaxStages = 8;
 constexpr int kEpiBufBytes = kBlockM * 64 * 2;      // one 64-channel output chunk: 128 rows x 128 B
-constexpr int kMaxEpiBufs = 4;
+constexpr int kMaxEpiBufs = 8;                       // int8 plans split the same 64 KB into eight 8 KB chunk buffers
 constexpr int kMaxAcc = 4;
 constexpr int kSmemLimit = 232448;                  // 227 KB per CTA
 constexpr int kBarBytes = 512;
@@ -227,8 +227,12 @@ struct EpiBars { uint32_t res, ready, free_; };
 template <int BLOCK_N, int ACC, bool HAS_RES, int MODE, class Sched, bool PAIR = false, int EB = 4>
 __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sched, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                              const EpiBars eb, uint32_t epi_base, int ew, int lane) {
-  constexpr int CH = BLOCK_N / 64;            // chunks per tile
-  static_assert(!HAS_RES || EB == 4, "the residual prefetch uses four chunk buffers");
+  // Output chunk: 64 channels (128-byte fp16 rows); u8 outputs use 128-channel chunks where the tile has them, so that a chunk
+  // row is again a full 128-byte line (64-byte rows are partial-line writes: the TMA stores of an int8 plan's HBM-bound layers
+  // ran at half the byte rate of the fp16 ones).
+  constexpr int CW = (MODE >= 2 && BLOCK_N >= 128) ? 128 : 64;
+  constexpr int CH = BLOCK_N / CW;            // chunks per tile
+  static_assert(!HAS_RES || EB == 4 || EB == 8, "the residual prefetch cycles through all chunk buffers");
   const int quad = ew & 3, half = ew >> 2;
   const int row = quad * 32 + lane;
   const uint32_t sw = (uint32_t)(row & 7);
@@ -245,77 +249,89 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
       const int b = q % EB;
       const uint32_t use = (uint32_t)(q / EB);
       if (MODE >= 2) {
-        // ---- u8 outputs (int8 plan): the chunk is 128 rows x 64 bytes, unswizzled; a thread owns 32 bytes of its row
-        const uint32_t rowq = epi_base + b * kEpiBufBytes + (uint32_t)row * 64u + (uint32_t)half * 32u;
-        const int cofs = n0 + c * 64 + half * 32;
-        uint32_t acc[32];
-        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), acc);
-        ptx::tmem_ld_wait();
-        if (c == CH - 1) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(tempty0 + 8u * as, 0));
-            else ptx::mbar_arrive(tempty0 + 8u * as);
-          }
-        }
-        uint32_t rw[8];
-        if (HAS_RES) {
-          ptx::mbar_wait(eb.res + 8u * b, use & 1u);
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(rowq));
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "r"(rowq + 16u));
-        } else if (use >= 1) {
-          ptx::mbar_wait(eb.free_ + 8u * b, (use - 1u) & 1u);
-        }
-        // Requantisation in f32 exactly as in the fp16-carried form; what differs is getting integers in and out cheaply:
-        //  * a residual byte b becomes the float 2^23 + b by placing it in the low mantissa byte of 0x4B000000 (PRMT), so
-        //    b - zero_point is ONE add of -(2^23 + zero_point)  (exact);
-        //  * rne(v) for the clamped v is v + 1.5 * 2^23 (one add); the result's low mantissa bits hold rne(v) as an integer, the
-        //    output zero point is added to those bits with an integer add, and PRMT gathers the four low bytes of a word.
-        //    (Adding the zero point before rounding would break ties differently whenever it is odd.)
+        // ---- u8 outputs (int8 plan).  CW = 128: rows of 128 bytes, 128B-swizzled like the fp16 chunks, a thread owns 64 bytes of
+        // its row (two passes of 32 channels); CW = 64 (64-channel tiles): rows of 64 bytes, unswizzled, 32 bytes per thread.
+        constexpr int PASSES = CW / 64;
+        constexpr uint32_t kChunk = CW == 128 ? kEpiBufBytes : kEpiBufBytes / 2;
+        const uint32_t rowb = epi_base + b * kChunk + (uint32_t)row * (uint32_t)CW;
         const float lo1 = g.q_lo, hi1 = g.q_hi;
         const float lo2 = g.relu ? fmaxf(g.q_lo2, 0.f) : g.q_lo2, hi2 = g.q_hi2;
         const float lo_out = (!HAS_RES && g.relu) ? fmaxf(lo1, 0.f) : lo1;
         const float res_bias = -(8388608.f + g.q_zres);
         const uint32_t zout = (uint32_t)(int)(g.q_zmagic - kRneMagic);
-        uint32_t ow[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {            // 4 channels -> one 32-bit word of u8
-          const float4 m = __ldg(reinterpret_cast<const float4*>(g.qmul + cofs) + j);
-          float t[4];
-          if (MODE == 3) {
-            const int4 bi = __ldg(reinterpret_cast<const int4*>(g.bias_i32 + cofs) + j);
-            t[0] = __int2float_rn((int)acc[4 * j + 0] + bi.x); t[1] = __int2float_rn((int)acc[4 * j + 1] + bi.y);
-            t[2] = __int2float_rn((int)acc[4 * j + 2] + bi.z); t[3] = __int2float_rn((int)acc[4 * j + 3] + bi.w);
-          } else {
-            const float4 bf = __ldg(reinterpret_cast<const float4*>(g.bias + cofs) + j);
-            t[0] = __uint_as_float(acc[4 * j + 0]); t[1] = __uint_as_float(acc[4 * j + 1]);
-            t[2] = __uint_as_float(acc[4 * j + 2]); t[3] = __uint_as_float(acc[4 * j + 3]);
-            ptx::add_f32x2(t[0], t[1], bf.x, bf.y); ptx::add_f32x2(t[2], t[3], bf.z, bf.w);
-          }
-          ptx::mul_f32x2(t[0], t[1], m.x, m.y); ptx::mul_f32x2(t[2], t[3], m.z, m.w);
-          uint32_t bits[4];
+        for (int hh = 0; hh < PASSES; ++hh) {
+          const int cofs = n0 + c * CW + half * (CW / 2) + hh * 32;
+          // 16-byte group addresses of this pass
+          uint32_t ga[2];
 #pragma unroll
-          for (int x = 0; x < 4; x += 2) {
-            float a0 = fminf(fmaxf(t[x], lo_out), hi1), a1 = fminf(fmaxf(t[x + 1], lo_out), hi1);
-            ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);                       // rne(v) + 1.5 * 2^23
-            if (HAS_RES) {
-              ptx::add_f32x2(a0, a1, -kRneMagic, -kRneMagic);                   // rne(v) as a float
-              float b0 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x));        // 2^23 + residual byte
-              float b1 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x + 1));
-              ptx::add_f32x2(b0, b1, res_bias, res_bias);                         // residual - its zero point
-              ptx::mul_f32x2(a0, a1, g.q_ra, g.q_ra);
-              ptx::mul_f32x2(b0, b1, g.q_rb, g.q_rb);
-              ptx::add_f32x2(a0, a1, b0, b1);
-              a0 = fminf(fmaxf(a0, lo2), hi2); a1 = fminf(fmaxf(a1, lo2), hi2);
-              ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);
+          for (int jj = 0; jj < 2; ++jj)
+            ga[jj] = CW == 128 ? rowb + (((uint32_t)(half * 4 + hh * 2 + jj) ^ sw) << 4) : rowb + (uint32_t)(half * 32 + jj * 16);
+          uint32_t acc[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c * CW + half * (CW / 2) + hh * 32), acc);
+          ptx::tmem_ld_wait();
+          if (c == CH - 1 && hh == PASSES - 1) {   // accumulator stage fully read
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(tempty0 + 8u * as, 0));
+              else ptx::mbar_arrive(tempty0 + 8u * as);
             }
-            bits[x] = __float_as_uint(a0) + zout; bits[x + 1] = __float_as_uint(a1) + zout;
           }
-          ow[j] = __byte_perm(__byte_perm(bits[0], bits[1], 0x0040), __byte_perm(bits[2], bits[3], 0x0040), 0x5410);
+          uint32_t rw[8];
+          if (hh == 0) {
+            if (HAS_RES) ptx::mbar_wait(eb.res + 8u * b, use & 1u);
+            else if (use >= 1) ptx::mbar_wait(eb.free_ + 8u * b, (use - 1u) & 1u);
+          }
+          if (HAS_RES) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(ga[0]));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "r"(ga[1]));
+          }
+          // Requantisation in f32 exactly as in the fp16-carried form; what differs is getting integers in and out cheaply:
+          //  * a residual byte b becomes the float 2^23 + b by placing it in the low mantissa byte of 0x4B000000 (PRMT), so
+          //    b - zero_point is ONE add of -(2^23 + zero_point)  (exact);
+          //  * rne(v) for the clamped v is v + 1.5 * 2^23 (one add); the result's low mantissa bits hold rne(v) as an integer, the
+          //    output zero point is added to those bits with an integer add, and PRMT gathers the four low bytes of a word.
+          //    (Adding the zero point before rounding would break ties differently whenever it is odd.)
+          uint32_t ow[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {            // 4 channels -> one 32-bit word of u8
+            const float4 m = __ldg(reinterpret_cast<const float4*>(g.qmul + cofs) + j);
+            float t[4];
+            if (MODE == 3) {
+              const int4 bi = __ldg(reinterpret_cast<const int4*>(g.bias_i32 + cofs) + j);
+              t[0] = __int2float_rn((int)acc[4 * j + 0] + bi.x); t[1] = __int2float_rn((int)acc[4 * j + 1] + bi.y);
+              t[2] = __int2float_rn((int)acc[4 * j + 2] + bi.z); t[3] = __int2float_rn((int)acc[4 * j + 3] + bi.w);
+            } else {
+              const float4 bf = __ldg(reinterpret_cast<const float4*>(g.bias + cofs) + j);
+              t[0] = __uint_as_float(acc[4 * j + 0]); t[1] = __uint_as_float(acc[4 * j + 1]);
+              t[2] = __uint_as_float(acc[4 * j + 2]); t[3] = __uint_as_float(acc[4 * j + 3]);
+              ptx::add_f32x2(t[0], t[1], bf.x, bf.y); ptx::add_f32x2(t[2], t[3], bf.z, bf.w);
+            }
+            ptx::mul_f32x2(t[0], t[1], m.x, m.y); ptx::mul_f32x2(t[2], t[3], m.z, m.w);
+            uint32_t bits[4];
+#pragma unroll
+            for (int x = 0; x < 4; x += 2) {
+              float a0 = fminf(fmaxf(t[x], lo_out), hi1), a1 = fminf(fmaxf(t[x + 1], lo_out), hi1);
+              ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);                       // rne(v) + 1.5 * 2^23
+              if (HAS_RES) {
+                ptx::add_f32x2(a0, a1, -kRneMagic, -kRneMagic);                   // rne(v) as a float
+                float b0 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x));        // 2^23 + residual byte
+                float b1 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x + 1));
+                ptx::add_f32x2(b0, b1, res_bias, res_bias);                         // residual - its zero point
+                ptx::mul_f32x2(a0, a1, g.q_ra, g.q_ra);
+                ptx::mul_f32x2(b0, b1, g.q_rb, g.q_rb);
+                ptx::add_f32x2(a0, a1, b0, b1);
+                a0 = fminf(fmaxf(a0, lo2), hi2); a1 = fminf(fmaxf(a1, lo2), hi2);
+                ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);
+              }
+              bits[x] = __float_as_uint(a0) + zout; bits[x + 1] = __float_as_uint(a1) + zout;
+            }
+            ow[j] = __byte_perm(__byte_perm(bits[0], bits[1], 0x0040), __byte_perm(bits[2], bits[3], 0x0040), 0x5410);
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ga[0]), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ga[1]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
         }
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowq), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowq + 16u), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(eb.ready + 8u * b);
@@ -422,15 +438,18 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
 // The single thread that owns every bulk copy of the epilogue: stores chunk q when all eight warps have
 // written it, then (one store later, so it never waits on the store it just issued) recycles the previous
 // buffer: HAS_RES -> prefetch the residual of chunk q-1+EB into it, else -> mark it free.
-template <int BLOCK_N, bool HAS_RES, class Sched, int EB = 4, int CHUNK_BYTES = kEpiBufBytes>
+template <int BLOCK_N, bool HAS_RES, class Sched, int EB = 4, int CHUNK_BYTES = kEpiBufBytes, int CW = 64>
 __device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvTcGeom& g, const Sched sched, const EpiBars eb, uint32_t epi_base) {
-  constexpr int CH = BLOCK_N / 64;
+  constexpr int CH = BLOCK_N / CW;   // CW = channels per chunk (epilogue_tma)
+  // stores kept in flight: their read-out of smem takes ~2 us to observe, so the chunk rate is (stores in flight) / that.  With
+  // a residual the buffers are shared between stores in flight and prefetched residual chunks: half each.
+  constexpr int D = HAS_RES ? EB / 2 : EB - 1;
   const int total = sched.count() * CH;
   auto issue_res = [&](int qq) {
     const TileCoord tc = decode_tile(g, sched.tile(qq / CH));
     const int b = qq % EB;
     ptx::mbar_expect_tx(eb.res + 8u * b, (uint32_t)CHUNK_BYTES);
-    ptx::tma_load_4d(epi_base + b * kEpiBufBytes, &maps.r, eb.res + 8u * b, tc.nt * BLOCK_N + (qq % CH) * 64, tc.ox0, tc.oy0, tc.img);
+    ptx::tma_load_4d(epi_base + b * CHUNK_BYTES, &maps.r, eb.res + 8u * b, tc.nt * BLOCK_N + (qq % CH) * CW, tc.ox0, tc.oy0, tc.img);
   };
   if (HAS_RES) {
     for (int p = 0; p < EB && p < total; ++p) issue_res(p);
@@ -441,18 +460,16 @@ __device__ __forceinline__ void epilogue_dma(const ConvTcMaps& maps, const ConvT
     for (int c = 0; c < CH; ++c, ++q) {
       const int b = q % EB;
       ptx::mbar_wait(eb.ready + 8u * b, (uint32_t)(q / EB) & 1u);
-      ptx::tma_store_4d(&maps.c, epi_base + b * kEpiBufBytes, tc.nt * BLOCK_N + c * 64, tc.ox0, tc.oy0, tc.img);
+      ptx::tma_store_4d(&maps.c, epi_base + b * CHUNK_BYTES, tc.nt * BLOCK_N + c * CW, tc.ox0, tc.oy0, tc.img);
       ptx::tma_store_commit();
       if (HAS_RES) {
-        if (q >= 1) {
-          ptx::tma_store_wait_read<1>();          // the store of chunk q-1 has left its buffer
-          if (q - 1 + EB < total) issue_res(q - 1 + EB);
+        if (q >= D - 1) {
+          ptx::tma_store_wait_read<D - 1>();      // the store of chunk q-(D-1) has left its buffer: prefetch into it
+          if (q - (D - 1) + EB < total) issue_res(q - (D - 1) + EB);
         }
-      } else if (q >= EB - 1) {
-        // up to EB-1 stores stay in flight; the one issued EB-1 chunks ago has been read out of smem by now (its
-        // completion is slow to observe, ~1 us, which is why a single store in flight throttled the epilogue)
-        ptx::tma_store_wait_read<EB - 1>();
-        ptx::mbar_arrive(eb.free_ + 8u * ((q - (EB - 1)) % EB));
+      } else if (q >= D) {
+        ptx::tma_store_wait_read<D>();
+        ptx::mbar_arrive(eb.free_ + 8u * ((q - D) % EB));
       }
     }
   }
@@ -463,7 +480,9 @@ template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
   constexpr bool I8 = MODE == 3;
-  constexpr int kChunkBytes = MODE >= 2 ? kEpiBufBytes / 2 : kEpiBufBytes;
+  constexpr int kCW = (MODE >= 2 && BLOCK_N >= 128) ? 128 : 64;                           // channels per output chunk (epilogue_tma)
+  constexpr int kChunkBytes = (MODE >= 2 && kCW == 64) ? kEpiBufBytes / 2 : kEpiBufBytes;
+  constexpr int kEB4 = kChunkBytes == kEpiBufBytes ? 4 : 8, kEB2 = kEB4 / 2;               // chunk buffers in 64 KB / 32 KB of smem
   using C = Cfg<BLOCK_N, I8>;
   extern __shared__ uint8_t smem_raw[];
   const int num_stages = g.stages;
@@ -584,9 +603,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       if (ptx::elect_one()) {
         const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
         if (g.store_mode == 1) {
-          if (g.epi_bufs == 4) epilogue_dma<BLOCK_N, false, Sched1, 4, kChunkBytes>(maps, g, sched, eb, epi_base);
-          else epilogue_dma<BLOCK_N, false, Sched1, 2, kChunkBytes>(maps, g, sched, eb, epi_base);
-        } else if (g.store_mode == 2) epilogue_dma<BLOCK_N, true, Sched1, 4, kChunkBytes>(maps, g, sched, eb, epi_base);
+          if (g.epi_bufs == 4) epilogue_dma<BLOCK_N, false, Sched1, kEB4, kChunkBytes, kCW>(maps, g, sched, eb, epi_base);
+          else epilogue_dma<BLOCK_N, false, Sched1, kEB2, kChunkBytes, kCW>(maps, g, sched, eb, epi_base);
+        } else if (g.store_mode == 2) epilogue_dma<BLOCK_N, true, Sched1, kEB4, kChunkBytes, kCW>(maps, g, sched, eb, epi_base);
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -597,9 +616,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
     } else if constexpr (BLOCK_N >= 64) {
       const Sched1 sched{(int)blockIdx.x, (int)gridDim.x, g.num_tiles};
       if (g.store_mode == 1) {
-        if (g.epi_bufs == 4) epilogue_tma<BLOCK_N, C::kAcc, false, MODE, Sched1, false, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-        else epilogue_tma<BLOCK_N, C::kAcc, false, MODE, Sched1, false, 2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-      } else epilogue_tma<BLOCK_N, C::kAcc, true, MODE, Sched1>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+        if (g.epi_bufs == 4) epilogue_tma<BLOCK_N, C::kAcc, false, MODE, Sched1, false, kEB4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+        else epilogue_tma<BLOCK_N, C::kAcc, false, MODE, Sched1, false, kEB2>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+      } else epilogue_tma<BLOCK_N, C::kAcc, true, MODE, Sched1, false, kEB4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
     }
   }
 
@@ -744,13 +763,13 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
     }
   } else if (warp == kDmaWarp) {
     if (ptx::elect_one()) {
-      if (g.store_mode == 1) epilogue_dma<BLOCK_N, false, Sched2, 4, (MODE >= 2 ? kEpiBufBytes / 2 : kEpiBufBytes)>(maps, g, sched, eb, epi_base);
-      else epilogue_dma<BLOCK_N, true, Sched2, 4, (MODE >= 2 ? kEpiBufBytes / 2 : kEpiBufBytes)>(maps, g, sched, eb, epi_base);
+      if (g.store_mode == 1) epilogue_dma<BLOCK_N, false, Sched2, 4, kEpiBufBytes, (MODE >= 2 ? 128 : 64)>(maps, g, sched, eb, epi_base);
+      else epilogue_dma<BLOCK_N, true, Sched2, 4, kEpiBufBytes, (MODE >= 2 ? 128 : 64)>(maps, g, sched, eb, epi_base);
     }
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;
     if (g.store_mode == 1) epilogue_tma<BLOCK_N, ACC, false, MODE, Sched2, true, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
-    else epilogue_tma<BLOCK_N, ACC, true, MODE, Sched2, true>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    else epilogue_tma<BLOCK_N, ACC, true, MODE, Sched2, true, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
   }
 
   ptx::tc_fence_before();
@@ -1042,9 +1061,9 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
       }
     }
   } else if (warp == kDmaWarp) {
-    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false, Sched1, 4, (MODE >= 2 ? kEpiBufBytes / 2 : kEpiBufBytes)>(maps, g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, eb, epi_base);
+    if (ptx::elect_one()) epilogue_dma<BLOCK_N, false, Sched1, (MODE >= 2 ? 8 : 4), (MODE >= 2 ? kEpiBufBytes / 2 : kEpiBufBytes)>(maps, g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, eb, epi_base);
   } else if (warp >= kEpiWarp0) {
-    epilogue_tma<BLOCK_N, ACC, false, MODE, Sched1, false, 4>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
+    epilogue_tma<BLOCK_N, ACC, false, MODE, Sched1, false, (MODE >= 2 ? 8 : 4)>(g, Sched1{(int)blockIdx.x, (int)gridDim.x, g.num_tiles}, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base,
                                  warp - kEpiWarp0, lane);
   }
 

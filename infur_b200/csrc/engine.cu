@@ -38,13 +38,13 @@ static EncodeTiledFn get_encode_tiled() {
 
 // esz = 2: fp16 elements, 128B swizzle (or none); esz = 1: u8 elements, 64B swizzle (a 64-channel K block is a 64-byte row) or none
 static Status make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                        const uint32_t* box, bool swizzle, int esz) {
+                        const uint32_t* box, int swizzle_bytes, int esz) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return Status::error(INFUR_E_RUNTIME, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  const CUtensorMapSwizzle sw = !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : (esz == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
   CUresult r = enc(m, esz == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx,
                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -62,7 +62,7 @@ static Status make_tmap(CUtensorMap* m, const void* base, int rank, const uint64
 
 static Status make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                             const uint32_t* box, bool swizzle128 = true) {
-  return make_tmap(m, base, rank, dims, strides_bytes, box, swizzle128, 2);
+  return make_tmap(m, base, rank, dims, strides_bytes, box, swizzle128 ? 128 : 0, 2);
 }
 
 DeviceModel::~DeviceModel() { if (arena) cudaFree(arena); }
@@ -333,7 +333,7 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
         if (vw <= 0 || vh <= 0) continue;
         const uint64_t dims[4] = {(uint64_t)d.cin, (uint64_t)vw, (uint64_t)vh, (uint64_t)io.n};
         const uint64_t strides[3] = {(uint64_t)s * d.cin * esz, (uint64_t)s * io.w * d.cin * esz, (uint64_t)io.h * io.w * d.cin * esz};
-        st = make_tmap(&po.maps.a[py * s + px], reinterpret_cast<const uint8_t*>(io.x) + ((size_t)py * io.w + px) * d.cin * esz, 4, dims, strides, box, true, esz);
+        st = make_tmap(&po.maps.a[py * s + px], reinterpret_cast<const uint8_t*>(io.x) + ((size_t)py * io.w + px) * d.cin * esz, 4, dims, strides, box, esz == 1 ? 64 : 128, esz);
         if (!st.ok()) return st;
         have[py * s + px] = true;
       }
@@ -369,7 +369,7 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
     const uint64_t dims[2] = {(uint64_t)d.kdim, (uint64_t)d.cout_pad};
     const uint64_t strides[1] = {(uint64_t)d.kdim * esz};
     const uint32_t bbox[2] = {64, (uint32_t)(pair ? 128 : block_n)};   // a CTA pair splits the weight tile between its CTAs
-    st = make_tmap(&po.maps.b, io.wgt, 2, dims, strides, bbox, true, esz);
+    st = make_tmap(&po.maps.b, io.wgt, 2, dims, strides, bbox, esz == 1 ? 64 : 128, esz);
     if (!st.ok()) return st;
   } else {
     po.maps.b = po.maps.a[0];
@@ -379,11 +379,15 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
     // output / residual: NHWC fp16 [n][oh][ow][out_ld], stored (loaded) in 64-channel x tile boxes
     const uint64_t dims[4] = {(uint64_t)d.cout, (uint64_t)io.ow, (uint64_t)io.oh, (uint64_t)io.n};
     const uint64_t strides[3] = {(uint64_t)io.out_ld * osz, (uint64_t)io.ow * io.out_ld * osz, (uint64_t)io.oh * io.ow * io.out_ld * osz};
-    // fp16 chunks are 128B-swizzled in smem, u8 chunks (int8 plans) are plain 64-byte rows
-    st = make_tmap(&po.maps.c, io.y, 4, dims, strides, box, osz == 2, osz);
+    // output chunks (conv_tc.cu epilogue_tma): fp16: 64 channels = 128-byte rows, 128B-swizzled; u8 (int8 plans): 128 channels =
+    // 128-byte rows, 128B-swizzled, when the N tile has them, else 64 channels = 64-byte rows, unswizzled
+    const uint32_t cw = (osz == 1 && block_n >= 128) ? 128u : 64u;
+    const uint32_t cbox[4] = {cw, box[1], box[2], box[3]};
+    const int csw = (osz == 2 || cw == 128) ? 128 : 0;
+    st = make_tmap(&po.maps.c, io.y, 4, dims, strides, cbox, csw, osz);
     if (!st.ok()) return st;
     if (io.residual) {
-      st = make_tmap(&po.maps.r, io.residual, 4, dims, strides, box, osz == 2, osz);
+      st = make_tmap(&po.maps.r, io.residual, 4, dims, strides, cbox, csw, osz);
       if (!st.ok()) return st;
     }
   }
