@@ -216,12 +216,15 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
   }
 }
 
-// TMA-staged epilogue for fp16 NHWC outputs.  The tile's output is produced in 64-channel chunks; chunk q of
-// this CTA (running count over all its tiles) lives in smem buffer q % EB as 128 rows (pixels) x 128 B with
-// the 128B swizzle the tensor maps expect.  Eight warps: warp ew owns TMEM lane quadrant ew % 4 (32 pixels) and
-// channel half ew / 4 (32 of the chunk's 64 channels).  HAS_RES: the residual chunk was TMA-loaded into the
-// buffer ahead of time by the DMA warp; the sum is written back in place.  No CTA-wide barrier: a warp
-// announces its part through the chunk_ready mbarrier and moves on.
+// TMA-staged epilogue for NHWC outputs (fp16, or u8 in int8 plans: MODE >= 2).  The tile's output is produced in chunks
+// of CW channels (64 for fp16; 128 for u8 where the N tile has them); chunk q of this CTA (running count over all its
+// tiles) lives in smem buffer q % EB as 128 rows (pixels) x 128 B with the 128B swizzle the tensor maps expect
+// (u8 chunks of 64-channel tiles: 64-byte rows, unswizzled).  Eight warps: warp ew owns TMEM lane quadrant ew % 4
+// (32 pixels) and channel half ew / 4 of the chunk.  HAS_RES: the residual chunk was TMA-loaded into the buffer
+// ahead of time by the DMA warp; the sum is written back in place.  No CTA-wide barrier: a warp announces its part
+// through the chunk_ready mbarrier and moves on.
+// MODE: 0 float model; 1 quantised, fp16-carried integers in and out; 2 the same accumulators, u8 out (stem of an int8
+// plan); 3 s32 accumulators of tcgen05.mma.kind::i8 + int32 bias, u8 residual and output.
 struct EpiBars { uint32_t res, ready, free_; };
 
 template <int BLOCK_N, int ACC, bool HAS_RES, int MODE, class Sched, bool PAIR = false, int EB = 4>
