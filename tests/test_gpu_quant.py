@@ -122,7 +122,7 @@ def test_quantised_model_info(handle, tiny_int8):
     assert info.input_names == ["input"] and info.output_names == ["out"] and info.input0_dtype == "Float"
 
 
-@pytest.mark.parametrize("w,h", [(128, 96), (320, 240), (200, 136)])
+@pytest.mark.parametrize("w,h", [(128, 96), (320, 240), (200, 136), (194, 130)])   # the last: odd feature-map widths (97, 49, 25)
 def test_quantised_model_lowres_bit_exact(handle, tiny_int8, plan_kind, w, h):
     handle.model_load("")
     handle.model_load(tiny_int8)
