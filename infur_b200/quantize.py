@@ -10,6 +10,9 @@ calibrated on synthetic frames (min / max, like ONNX Runtime's static quantiser)
 output channel.
 
 The product loads the file through csrc/onnx_reader.cpp; the oracle interprets it with ``oracle/qlinear.py``.
+Fidelity of the stand-ins (integer oracle vs the fp32 network they were quantised from, class-map agreement on synthetic
+frames): 94-95 % for the tiny network, 85-88 % for FCN-ResNet50 -- random-init weights leave many near-ties; the point of
+the fixtures is the operator set and realistic value ranges, not accuracy.
 """
 from __future__ import annotations
 

@@ -136,3 +136,16 @@ def test_golden_qlinear_vectors():
     q_add = qlinear.qlinear_add(q_conv, np.float32(0.031), np.uint8(131), g["q_res"], np.float32(0.019), np.uint8(0), np.float32(0.027), np.uint8(0))
     assert (q_add == g["q_add"]).all()
     assert (qlinear.dequantize_linear(q_add, np.float32(0.027), np.uint8(0)) == g["deq"]).all()
+
+
+def test_quantised_fixture_tracks_its_float_original():
+    """Sanity of the fixture quantiser (infur_b200/quantize.py): the int8 stand-in's class map, computed by the integer oracle,
+    agrees with the fp32 network it was quantised from on most pixels (random-init weights leave many near-ties)."""
+    from infur_b200 import synth
+    from oracle import fcn, preprocess_f32
+    path, model = synth.ensure_fixture("fcn_tiny")
+    g = onnx_min.load(quantize.ensure_fixture("fcn_tiny_int8"))
+    bgr = synth.synth_frame(128, 96, 1)
+    q = qlinear.run(g, preprocess_f32(bgr)[None])["out"][0].argmax(0)
+    f = fcn.pipeline(model, bgr, 1.0)["logits"].argmax(0)
+    assert (q == f).mean() > 0.9
