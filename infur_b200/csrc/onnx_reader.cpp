@@ -406,6 +406,14 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
     c.stride = (int)strides[0]; c.dil = (int)dil[0]; c.pad = (int)pads[0];
   };
 
+  // ONNX defines Relu on float (and signed integer) tensors only; quantisers fold a ReLU into the u8 clamp of the producing node
+  // (zero point = lowest code).  A graph that applies Relu to a quantised tensor is rejected rather than guessed at.
+  auto no_relu_on_quantised = [&](const std::string& out_name) {
+    auto it = single_consumer.find(out_name);
+    if (it != single_consumer.end() && it->second->op == "Relu")
+      throw ModelError(INFUR_E_MODEL_LOAD, "Relu '" + it->second->name + "' reads a quantised tensor: not valid ONNX (a quantiser folds ReLU into the clamp of the producing node)");
+  };
+
   for (auto* np : compute) {
     const OnnxNode& n = *np;
     if (fused.count(np)) continue;
@@ -470,10 +478,9 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       if (m.tensor_channels[op.in] != c.cin) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearConv '" + n.name + "': input has " + std::to_string(m.tensor_channels[op.in]) + " channels, weight expects " + std::to_string(c.cin));
       const std::string out_name = n.out[0];
       if (consumers[out_name] == 1 && single_consumer[out_name]->op == "QLinearAdd") { pending[out_name] = std::move(op); pending_q[out_name] = yq; continue; }
-      std::string final_name;
-      op.conv.relu = take_relu(out_name, final_name);
-      emit(std::move(op), final_name);
-      qinfo[tid[final_name]] = yq;
+      no_relu_on_quantised(out_name);
+      emit(std::move(op), out_name);
+      qinfo[tid[out_name]] = yq;
     } else if (n.op == "QLinearAdd") {
       // A, A_scale, A_zero_point, B, B_scale, B_zero_point, C_scale, C_zero_point   (com.microsoft)
       if (n.in.size() < 7) throw ModelError(INFUR_E_MODEL_LOAD, "QLinearAdd '" + n.name + "' needs 7 or 8 inputs");
@@ -498,10 +505,9 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       { volatile float ra = ms / cs, rb = os_ / cs; op.conv.q_ra = ra; op.conv.q_rb = rb; }
       op.conv.q_lo2 = (float)(cq.qmin - cq.zp); op.conv.q_hi2 = (float)(cq.qmax - cq.zp);
       op.conv.out_zp = cq.zp; op.conv.res_zp = oq.zp; op.conv.all_u8 = op.conv.all_u8 && cq.qmin == 0 && oq.qmin == 0;
-      std::string final_name;
-      op.conv.relu = take_relu(n.out[0], final_name);
-      emit(std::move(op), final_name);
-      qinfo[tid[final_name]] = cq;
+      no_relu_on_quantised(n.out[0]);
+      emit(std::move(op), n.out[0]);
+      qinfo[tid[n.out[0]]] = cq;
     } else if (n.op == "DequantizeLinear") {
       // only as the step between a head convolution and its Resize: the convolution stores the de-quantised f32 logits
       const int t = need(n.in[0], n);

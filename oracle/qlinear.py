@@ -114,6 +114,8 @@ def run(graph, x_nchw: np.ndarray) -> dict:
             ks, st, pd = a["kernel_shape"], a.get("strides", [1, 1]), a.get("pads", [0, 0, 0, 0])
             out = max_pool(i[0], ks[0], st[0], pd[0])
         elif n.op == "Relu":
+            if i[0].dtype.kind != "f":
+                raise NotImplementedError("Relu on a quantised tensor is not valid ONNX (quantisers fold it into the clamp)")
             out = np.maximum(i[0], 0)
         elif n.op == "Shape":
             out = np.array(i[0].shape, dtype=np.int64)

@@ -84,7 +84,7 @@ def test_fixture_round_trip_and_lowering(tmp_path):
     assert "head out" in text and "classes=21" in text
 
 
-def _tiny_graph(mid_quantize=False, bad_scale=False, float_conv=False):
+def _tiny_graph(mid_quantize=False, bad_scale=False, float_conv=False, u8_weights=False, relu=False):
     """input -> QuantizeLinear -> QLinearConv(3->64 7x7 s2) -> DequantizeLinear -> Resize."""
     inits = {
         "xs": np.array(0.02, np.float32), "xz": np.array(100, np.uint8),
@@ -93,6 +93,10 @@ def _tiny_graph(mid_quantize=False, bad_scale=False, float_conv=False):
         "xs2": np.array(0.03, np.float32),
         "c0": np.array([0], np.int64), "c2": np.array([2], np.int64), "c4": np.array([4], np.int64),
     }
+    if u8_weights:   # per-tensor u8 weights around zero point 128, scalar scale: the other weight convention QLinearConv allows
+        inits["w"] = np.full((64, 3, 7, 7), 131, np.uint8)
+        inits["ws"] = np.array(0.01, np.float32)
+        inits["wz"] = np.array(128, np.uint8)
     nodes = [W.node("QuantizeLinear", ["input", "xs", "xz"], ["x"])]
     src = "x"
     if mid_quantize:
@@ -100,8 +104,12 @@ def _tiny_graph(mid_quantize=False, bad_scale=False, float_conv=False):
         src = "x2"
     nodes.append(W.node("QLinearConv", [src, "xs2" if bad_scale else "xs", "xz", "w", "ws", "wz", "ys", "yz", "b"], ["y"], kernel_shape=[7, 7],
                         strides=[2, 2], pads=[3, 3, 3, 3]))
+    ysrc = "y"
+    if relu:
+        nodes.append(W.node("Relu", ["y"], ["yr"]))
+        ysrc = "yr"
     nodes += [
-        W.node("DequantizeLinear", ["y", "ys", "yz"], ["yf"]),
+        W.node("DequantizeLinear", [ysrc, "ys", "yz"], ["yf"]),
         W.node("Shape", ["input"], ["ish"]), W.node("Slice", ["ish", "c2", "c4", "c0"], ["hw"]),
         W.node("Shape", ["yf"], ["lsh"]), W.node("Slice", ["lsh", "c0", "c2", "c0"], ["nc"]),
         W.node("Concat", ["nc", "hw"], ["sizes"], axis=0),
@@ -149,3 +157,12 @@ def test_quantised_fixture_tracks_its_float_original():
     q = qlinear.run(g, preprocess_f32(bgr)[None])["out"][0].argmax(0)
     f = fcn.pipeline(model, bgr, 1.0)["logits"].argmax(0)
     assert (q == f).mean() > 0.9
+
+
+def test_lowering_weight_conventions_and_relu(tmp_path):
+    rc, text = _describe(_tiny_graph(u8_weights=True), str(tmp_path))
+    assert rc == 0 and "q[0,255] deq" in text, text
+    env = qlinear.run(onnx_min.load(_tiny_graph(u8_weights=True)), np.ones((1, 3, 16, 16), np.float32))
+    assert env["y"].dtype == np.uint8 and env["y"].max() > 0          # (131 - 128) * positive inputs
+    rc, text = _describe(_tiny_graph(relu=True), str(tmp_path))
+    assert rc == L.E_MODEL_LOAD and "quantised tensor" in text, text
