@@ -138,20 +138,8 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
   for (auto& h : m.heads) is_head_tensor[h.tensor] = 1;
 
   dm->convs.resize(m.ops.size());
-  // Int8 plan: quantised model whose activations can live in HBM as raw u8 and whose convolutions (all but the RGB stem)
-  // can run on tcgen05.mma.kind::i8: every tensor u8, every non-stem convolution input with zero point 0 (so that TMA's
-  // zero fill is the padding value), weights within s8 after subtracting their zero point, 3x3/s2/p1 pooling only.
-  bool i8 = m.quant && cfg.conv_impl == INFUR_CONV_TCGEN05 && i8_enabled_env();
-  for (size_t i = 0; i < m.ops.size() && i8; ++i) {
-    if (!dm->needed[i]) continue;
-    if (m.ops[i].kind == OpKind::MaxPool) { i8 = m.ops[i].pool_k == 3 && m.ops[i].pool_s == 2 && m.ops[i].pool_p == 1; continue; }
-    const ConvOp& c = m.ops[i].conv;
-    const bool stem = m.ops[i].in == m.input_tensor;
-    if (!c.all_u8 || (stem && !(c.cin == 3 && c.kh == 7 && c.stride == 2 && c.pad == 3)) || (!stem && c.x_zp != 0) ||
-        (is_head_tensor[m.ops[i].out] && c.residual >= 0))
-      i8 = false;
-    if (!stem) for (float w : c.weight) if (w < -128.f || w > 127.f) { i8 = false; break; }
-  }
+  // Int8 plan (onnx_reader.h int8_plan_eligible): u8 activation tensors, native int8 convolutions for all but the RGB stem
+  const bool i8 = cfg.conv_impl == INFUR_CONV_TCGEN05 && i8_enabled_env() && int8_plan_eligible(m, &dm->needed, nullptr);
   dm->i8 = i8;
   size_t off = 0;
   for (size_t i = 0; i < m.ops.size(); ++i) {

@@ -652,6 +652,31 @@ int fuse_projection_shortcuts(LoweredModel& m) {
   return fused;
 }
 
+bool int8_plan_eligible(const LoweredModel& m, const std::vector<char>* needed, std::string* why) {
+  auto no = [&](const std::string& reason) { if (why) *why = reason; return false; };
+  if (!m.quant) return no("not a quantised model");
+  std::vector<char> is_head(m.num_tensors, 0);
+  for (auto& h : m.heads) is_head[h.tensor] = 1;
+  for (size_t i = 0; i < m.ops.size(); ++i) {
+    if (needed && !(*needed)[i]) continue;
+    const LoweredOp& op = m.ops[i];
+    if (op.kind == OpKind::MaxPool) {
+      if (!(op.pool_k == 3 && op.pool_s == 2 && op.pool_p == 1)) return no("MaxPool '" + op.name + "' is not 3x3 / stride 2 / pad 1");
+      continue;
+    }
+    const ConvOp& c = op.conv;
+    const bool stem = op.in == m.input_tensor;
+    if (!c.all_u8) return no("convolution '" + op.name + "' touches a tensor that is not uint8");
+    if (stem && !(c.cin == 3 && c.kh == 7 && c.stride == 2 && c.pad == 3)) return no("the convolution on the network input, '" + op.name + "', is not the 7x7 / stride 2 RGB stem");
+    if (!stem && c.x_zp != 0) return no("input of convolution '" + op.name + "' has zero point " + std::to_string(c.x_zp) + " (zero padding would not be the padding value)");
+    if (is_head[op.out] && c.residual >= 0) return no("head convolution '" + op.name + "' carries a residual");
+    if (!stem)
+      for (float w : c.weight)
+        if (w < -128.f || w > 127.f) return no("weights of convolution '" + op.name + "' do not fit int8 after subtracting their zero point");
+  }
+  return true;
+}
+
 std::string describe(const LoweredModel& m) {
   std::ostringstream os;
   os << "inputs:";
@@ -679,6 +704,11 @@ std::string describe(const LoweredModel& m) {
     }
   }
   for (auto& h : m.heads) os << "head " << h.name << " t" << h.tensor << " classes=" << h.num_classes << "\n";
+  if (m.quant) {
+    std::string why;
+    if (int8_plan_eligible(m, nullptr, &why)) os << "plan: int8 (u8 tensors, tcgen05.mma.kind::i8)\n";
+    else os << "plan: fp16-carried integers (no int8 plan: " << why << ")\n";
+  }
   return os.str();
 }
 

@@ -145,6 +145,12 @@ void lower_model(const OnnxGraph& g, LoweredModel& m);
 // This pass turns each such pair into ONE convolution with two sources (one accumulator, K = cin3 + cin_down),
 // removing the shortcut tensor's round trip through memory.  Returns the number of pairs fused.
 int fuse_projection_shortcuts(LoweredModel& m);
+// Can a quantised model run as an int8 plan (u8 activation tensors in HBM, tcgen05.mma.kind::i8 convolutions; engine.h
+// DeviceModel::i8)?  Every tensor must be u8, every convolution input except the RGB stem's must have zero point 0 (TMA's
+// zero fill is then the padding value), weights must fit s8 once their zero point is subtracted, the pool must be 3x3 / s2 /
+// p1, and a head convolution must not carry a residual.  `needed` (optional) masks the ops on the path of a computed head.
+// On false, *why names the first obstacle; such models run with the integers carried exactly in fp16 instead.
+bool int8_plan_eligible(const LoweredModel& m, const std::vector<char>* needed, std::string* why);
 std::string describe(const LoweredModel& m);
 
 }  // namespace infur

@@ -82,6 +82,7 @@ def test_fixture_round_trip_and_lowering(tmp_path):
     assert rc == 0, text
     assert "quantised(zp=" in text and text.count(" conv ") == 19 and text.count(" add[") == 4 and text.count(" deq") == 1
     assert "head out" in text and "classes=21" in text
+    assert "plan: int8" in text      # all tensors u8, every non-stem convolution input has zero point 0: runs natively in int8
 
 
 def _tiny_graph(mid_quantize=False, bad_scale=False, float_conv=False, u8_weights=False, relu=False):
@@ -166,3 +167,39 @@ def test_lowering_weight_conventions_and_relu(tmp_path):
     assert env["y"].dtype == np.uint8 and env["y"].max() > 0          # (131 - 128) * positive inputs
     rc, text = _describe(_tiny_graph(relu=True), str(tmp_path))
     assert rc == L.E_MODEL_LOAD and "quantised tensor" in text, text
+
+
+def _two_conv_graph(mid_zp=0, w_dtype=np.int8):
+    """stem (3->64 7x7 s2) -> QLinearConv 64->64 1x1 -> DequantizeLinear -> Resize; the tensor between has zero point mid_zp."""
+    inits = {
+        "xs": np.array(0.02, np.float32), "xz": np.array(100, np.uint8),
+        "w0": np.ones((64, 3, 7, 7), np.int8), "ws0": np.full(64, 0.01, np.float32), "wz0": np.zeros(64, np.int8), "b0": np.zeros(64, np.int32),
+        "ms": np.array(0.05, np.float32), "mz": np.array(mid_zp, np.uint8),
+        "w1": (np.full((64, 64, 1, 1), 250, np.uint8) if w_dtype == np.uint8 else np.ones((64, 64, 1, 1), np.int8)),
+        "ws1": np.array(0.01, np.float32), "wz1": np.array(0, w_dtype), "b1": np.zeros(64, np.int32),
+        "ys": np.array(0.1, np.float32), "yz": np.array(7, np.uint8),
+        "c0": np.array([0], np.int64), "c2": np.array([2], np.int64), "c4": np.array([4], np.int64),
+    }
+    nodes = [
+        W.node("QuantizeLinear", ["input", "xs", "xz"], ["x"]),
+        W.node("QLinearConv", ["x", "xs", "xz", "w0", "ws0", "wz0", "ms", "mz", "b0"], ["m"], kernel_shape=[7, 7], strides=[2, 2], pads=[3, 3, 3, 3]),
+        W.node("QLinearConv", ["m", "ms", "mz", "w1", "ws1", "wz1", "ys", "yz", "b1"], ["y"], kernel_shape=[1, 1]),
+        W.node("DequantizeLinear", ["y", "ys", "yz"], ["yf"]),
+        W.node("Shape", ["input"], ["ish"]), W.node("Slice", ["ish", "c2", "c4", "c0"], ["hw"]),
+        W.node("Shape", ["yf"], ["lsh"]), W.node("Slice", ["lsh", "c0", "c2", "c0"], ["nc"]),
+        W.node("Concat", ["nc", "hw"], ["sizes"], axis=0),
+        W.node("Resize", ["yf", "", "", "sizes"], ["out"], mode="linear", coordinate_transformation_mode="half_pixel"),
+    ]
+    return W.model(nodes, inits, [W.value_info("input", W.FLOAT, ["n", 3, "h", "w"])], [W.value_info("out", W.FLOAT, ["n", 64, "h", "w"])],
+                   opsets=(("", 12), ("com.microsoft", 1)))
+
+
+def test_int8_plan_eligibility_is_reported(tmp_path):
+    rc, text = _describe(_two_conv_graph(), str(tmp_path))
+    assert rc == 0 and "plan: int8" in text, text
+    rc, text = _describe(_two_conv_graph(mid_zp=3), str(tmp_path))      # a convolution input whose zero point is not 0
+    assert rc == 0 and "plan: fp16-carried" in text and "zero point 3" in text, text
+    rc, text = _describe(_two_conv_graph(w_dtype=np.uint8), str(tmp_path))   # u8 weights 250 with zero point 0 do not fit s8
+    assert rc == 0 and "plan: fp16-carried" in text and "do not fit int8" in text, text
+    env = qlinear.run(onnx_min.load(_two_conv_graph(mid_zp=3)), np.zeros((1, 3, 16, 16), np.float32))   # the oracle runs either
+    assert env["out"].shape == (1, 64, 16, 16)
