@@ -107,3 +107,21 @@ def test_describe_other_input_conventions(lib):
         buf = C.create_string_buffer(need.value)
         assert lib.infur_b200_onnx_describe(path.encode(), buf, need.value, C.byref(need)) == 0
         assert want in buf.value.decode()
+
+
+def test_header_is_plain_c99(lib, tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 (-pedantic) and a C program must link and run against
+    the library without any C++ or CUDA toolchain on the consumer's side."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "include/infur_b200.h"\n'
+                   "int main(void) { infur_b200_config c; infur_b200_default_config(&c);\n"
+                   "  return (infur_b200_abi_version() == 1 && c.max_batch > 0) ? 0 : 1; }\n")
+    exe = tmp_path / "cabi"
+    libdir = os.path.join(root, "infur_b200", "lib")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", root, str(src), "-o", str(exe), "-L", libdir,
+                        "-linfur_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
