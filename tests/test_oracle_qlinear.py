@@ -203,3 +203,15 @@ def test_int8_plan_eligibility_is_reported(tmp_path):
     assert rc == 0 and "plan: fp16-carried" in text and "do not fit int8" in text, text
     env = qlinear.run(onnx_min.load(_two_conv_graph(mid_zp=3)), np.zeros((1, 3, 16, 16), np.float32))   # the oracle runs either
     assert env["out"].shape == (1, 64, 16, 16)
+
+
+def test_two_head_quantised_model_lowers(tmp_path):
+    """The zoo model has two outputs (`out`, `aux`; infur/src/gui.rs:229-233 prints both): the quantised form of both heads lowers,
+    gets an int8 plan, and the oracle produces both."""
+    from infur_b200 import synth
+    from oracle import preprocess_f32
+    data = quantize.quantize_fcn(synth.build_fcn(seed=0, layers=(1, 1, 1, 1)), aux=True)
+    rc, text = _describe(data, str(tmp_path))
+    assert rc == 0 and "head out" in text and "head aux" in text and text.count(" deq") == 2 and "plan: int8" in text, text
+    env = qlinear.run(onnx_min.load(data), preprocess_f32(synth.synth_frame(64, 48, 0))[None])
+    assert env["out"].shape == env["aux"].shape == (1, 21, 48, 64)
