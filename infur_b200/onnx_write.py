@@ -44,7 +44,7 @@ def _str(field: int, s: str) -> bytes:
 
 
 def tensor(name: str, arr: np.ndarray) -> bytes:
-    arr = np.ascontiguousarray(arr)
+    arr = np.asarray(arr, order="C")   # (ascontiguousarray would turn a 0-d scalar into shape [1])
     out = b"".join(_int(1, int(d)) for d in arr.shape)
     out += _int(2, _NP2ONNX[arr.dtype]) + _str(8, name) + _bytes(9, arr.tobytes())
     return out

@@ -215,3 +215,23 @@ def test_two_head_quantised_model_lowers(tmp_path):
     assert rc == 0 and "head out" in text and "head aux" in text and text.count(" deq") == 2 and "plan: int8" in text, text
     env = qlinear.run(onnx_min.load(data), preprocess_f32(synth.synth_frame(64, 48, 0))[None])
     assert env["out"].shape == env["aux"].shape == (1, 21, 48, 64)
+
+
+def test_onnx_writer_reader_round_trip():
+    """The fixture writer (infur_b200/onnx_write.py) and the oracle's independent reader (oracle/onnx_min.py) agree on every
+    tensor type, attribute kind and graph field the quantised fixtures use."""
+    inits = {
+        "f": np.arange(6, dtype=np.float32).reshape(2, 3) * 0.5, "u": np.array([0, 7, 255], np.uint8), "s": np.array([-128, 0, 127], np.int8),
+        "i": np.array([-(2**31), 5, 2**31 - 1], np.int32), "l": np.array([-3, 2**40], np.int64), "scalar": np.array(0.25, np.float32),
+    }
+    nodes = [W.node("QLinearAdd", ["a", "b"], ["c"], name="n0", domain="com.microsoft"),
+             W.node("Conv", ["c", "f"], ["d"], kernel_shape=[3, 3], strides=[2, 2], group=1, auto_pad="NOTSET", alpha=0.5)]
+    data = W.model(nodes, inits, [W.value_info("a", W.FLOAT, ["n", 3, "h", 7])], [W.value_info("d", W.UINT8, [1, 2])],
+                   opsets=(("", 12), ("com.microsoft", 1)))
+    g = onnx_min.load(data)
+    for k, v in inits.items():
+        assert g.inits[k].dtype == v.dtype and g.inits[k].shape == v.shape and (g.inits[k] == v).all(), k
+    assert [n.op for n in g.nodes] == ["QLinearAdd", "Conv"] and g.nodes[0].domain == "com.microsoft" and g.nodes[0].name == "n0"
+    assert g.nodes[1].inputs == ["c", "f"] and g.nodes[1].outputs == ["d"]
+    assert g.nodes[1].attrs == {"kernel_shape": [3, 3], "strides": [2, 2], "group": 1, "auto_pad": "NOTSET", "alpha": 0.5}
+    assert g.inputs == [("a", 1, ["n", 3, "h", 7])] and g.outputs == [("d", 2, [1, 2])]
