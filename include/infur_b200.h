@@ -10,8 +10,10 @@
  * Conventions: C99, `int32_t` status (0 = OK; nothing throws or aborts across the boundary),
  * opaque handle, caller-owned buffers with explicit capacities, no callbacks.  One owner thread per
  * handle (the reference creates its ORT session on the "Proc" thread because it cannot be sent,
- * infur/src/main.rs:38-40).  All work runs on one CUDA device chosen at create(); multi-GPU is one
- * handle (one process) per GPU with frames sharded by id (DESIGN.md "Multi-GPU").
+ * infur/src/main.rs:38-40).  A handle drives one CUDA device, or -- cfg.num_devices > 1 -- the GPUs of one box from that
+ * single owner thread: one worker thread + stream set + pinned ring per GPU inside the library, the packed weights broadcast
+ * with NCCL at model_load, frames / ring slots routed round-robin by id, results handed back in submission order
+ * (DESIGN.md "Multi-GPU").  One process per GPU with one single-device handle each remains possible (torchrun).
  *
  * There is NO CPU fallback: without a CUDA device create() returns INFUR_E_NO_DEVICE.
  */
@@ -25,7 +27,8 @@
 extern "C" {
 #endif
 
-#define INFUR_B200_ABI_VERSION 1
+#define INFUR_B200_ABI_VERSION 2
+#define INFUR_B200_MAX_DEVICES 8
 
 typedef struct infur_b200_handle infur_b200_handle;
 
@@ -50,6 +53,7 @@ enum {
 
 enum { INFUR_RESIZE_NEAREST = 0 /* fr::ResizeAlg::Nearest, processing.rs:189 (the reference's only mode; the default) */,
        INFUR_RESIZE_BILINEAR = 1 /* opt-in extension (README.md:74 TODO): half-pixel bilinear, un-fused f32, round-half-up to u8 */ };
+enum { INFUR_CONF_RAW = 0, INFUR_CONF_SOFTMAX = 1 };
 enum { INFUR_CONV_TCGEN05 = 0, INFUR_CONV_VALIDATE = 1 /* slow CUDA-core kernel, validation only; never selected implicitly */,
        INFUR_CONV_TCGEN05_PAIR = 2 /* conv_test only: force the CTA-pair (cta_group::2) variant of the tcgen05 kernel */,
        INFUR_CONV_TCGEN05_HALO = 3, /* conv_test only: force the halo-patch variant (3x3 / stride 1 convolutions) */
@@ -65,9 +69,18 @@ typedef struct infur_b200_config {
   int32_t compute_aux;   /* also evaluate the `aux` head (the reference's caller discards it, app.rs:116) */
   int32_t blend;         /* also produce blended_rgba (new feature; gui.rs:324-329 "todo: blend somehow?") */
   int32_t conv_impl;     /* INFUR_CONV_TCGEN05 */
-  int32_t use_cuda_graph;/* reserved, must be 0 (the ~54 launches of a frame are hidden behind > 2 ms of kernels) */
-  int32_t autotune;      /* time the N-tile candidates of every convolution once per (shape, batch) plan and keep the fastest
-                          * (default 1; results are bit-identical for every choice) */
+  int32_t use_cuda_graph;/* 1: the kernel sequence of a plan is captured once into a CUDA graph and replayed with one launch per
+                          * step (host-buffer and ring entry points; default 1).  0: plain stream launches */
+  int32_t autotune;      /* time the N-tile candidates of every convolution once per layer-shape class and keep the fastest
+                          * (default 1; results are bit-identical for every choice).  Decisions are cached per handle and across
+                          * plans, so a new Scale factor re-tunes nothing whose tile grid it does not change */
+  int32_t num_devices;   /* 0 or 1: one GPU, `device`.  2..INFUR_B200_MAX_DEVICES: the GPUs devices[0..num_devices) of this box behind
+                          * ONE handle: weights are packed on devices[0] and ncclBroadcast to the others inside model_load; frame id
+                          * (1-based, ff-video/src/decoder.rs:163-164) goes to devices[(id - 1) % n], ring ticket t to devices[(t - 1) % n] */
+  int32_t devices[INFUR_B200_MAX_DEVICES];
+  int32_t frame_rgba;    /* ring / submit path: also return GUIFrame.buffer (app.rs:132-144), the scaled frame as (r,g,b,255); default 1 */
+  int32_t confidence;    /* INFUR_CONF_RAW (the reference: raw logits as confidence, decode_predict.rs:67-77) or INFUR_CONF_SOFTMAX
+                          * (README.md:76 TODO: alpha from the softmax probability of the winning class) */
 } infur_b200_config;
 
 /* Fills *cfg with the defaults of the three stages: factor 1.0, dirty, no model
@@ -107,17 +120,30 @@ int32_t infur_b200_model_load_bytes(infur_b200_handle* h, const void* onnx, size
  * (get_info() == None), INFUR_E_BUFFER_TOO_SMALL (with *required set) when cap is too small. */
 int32_t infur_b200_model_info(const infur_b200_handle* h, char* buf, size_t cap, size_t* required);
 
-/* Multi-GPU initialisation ("NCCL broadcast of weights at init only"): every rank parses the file for
- * the graph structure, but only the root packs and uploads weights; the others pass
- * INFUR_LOAD_SKIP_WEIGHTS (arena allocated, zero-filled), then receive the root's packed arena through
- * model_weights_export -> ncclBroadcast (torch.distributed) -> model_weights_import.  Both copy
- * device-to-device between the library's arena and a caller-owned DEVICE buffer of *bytes. */
+/* Multi-GPU initialisation ("NCCL broadcast of weights at init only").
+ * (a) One handle, several GPUs (cfg.num_devices > 1): model_load parses the file once, every device builds its plan structures,
+ *     ONLY devices[0] packs and uploads the weight arena, and the arena reaches the other devices with ncclBroadcast over the
+ *     library's own communicator (ncclCommInitAll at create; libnccl.so.2 is loaded at run time).  The load is atomic across
+ *     devices: if any device fails, every device keeps its previous model (predict_onnx.rs:289-308).
+ * (b) One process per GPU (torchrun): every rank parses the file for the graph structure, but only the root packs and uploads
+ *     weights; the others pass INFUR_LOAD_SKIP_WEIGHTS (arena allocated, zero-filled), then receive the root's packed arena through
+ *     model_weights_export -> the caller's broadcast -> model_weights_import.  Both copy device-to-device between the library's
+ *     arena and a caller-owned DEVICE buffer of *bytes (single-device handles only). */
 enum { INFUR_LOAD_DEFAULT = 0, INFUR_LOAD_SKIP_WEIGHTS = 1 };
 int32_t infur_b200_model_load_opts(infur_b200_handle* h, const char* utf8_path, int32_t flags);
 int32_t infur_b200_model_weights_size(const infur_b200_handle* h, size_t* bytes);
 int32_t infur_b200_model_weights_export(infur_b200_handle* h, void* d_dst, size_t bytes);
 int32_t infur_b200_model_weights_import(infur_b200_handle* h, const void* d_src, size_t bytes);
+/* Diagnostics (multi-device handles): 64-bit FNV-1a checksum of device `index`'s weight arena, to check the broadcast. */
+int32_t infur_b200_model_weights_checksum(infur_b200_handle* h, int32_t index, uint64_t* sum);
+/* Number of GPUs behind the handle (1 for a single-device handle). */
+int32_t infur_b200_num_devices(const infur_b200_handle* h);
 
+/* Class-label captions (README.md:77 TODO "class-label captions"; the reference only colour-codes, decode_predict.rs:9-36).
+ * Writes a NUL-terminated text, one line per class 0..K-1 of the loaded model: "index\tlabel\tr,g,b" with the palette colour
+ * COLORS_PALETTE[index % 20] (decode_predict.rs:9-30,34).  Labels: the 21 Pascal-VOC names torchvision's fcn_resnet50 is
+ * trained on when K == 21 ("__background__", "aeroplane", ... "tvmonitor"), else "class <index>".  No model: INFUR_E_INVALID_ARG. */
+int32_t infur_b200_class_legend(const infur_b200_handle* h, char* buf, size_t cap, size_t* required);
 /* Scale::is_dirty (processing.rs:228-230); Model and ColorCode are never dirty
  * (predict_onnx.rs:336-338, decode_predict.rs:81-83). */
 int32_t infur_b200_is_dirty(const infur_b200_handle* h);
@@ -163,13 +189,16 @@ typedef struct infur_b200_slot {
   uint32_t out_w, out_h;     /* valid after ring_wait */
   uint32_t num_classes;
   int32_t has_decoded;
+  int32_t device;            /* CUDA ordinal the slot runs on: devices[(ticket - 1) % num_devices] */
   uint8_t* bgr_in;           /* PINNED host memory: the frame source writes n*w*h*3 bytes here */
   const uint8_t* class_map;  /* PINNED, [n][out_h][out_w]      valid after ring_wait until the slot is re-acquired */
-  const uint8_t* decoded_rgba; /* PINNED, [n][out_h][out_w][4] */
-  const uint8_t* blended_rgba; /* PINNED or NULL */
+  const uint8_t* decoded_rgba; /* PINNED, [n][out_h][out_w][4]   GUIFrame.decoded_buffer */
+  const uint8_t* blended_rgba; /* PINNED or NULL (cfg.blend) */
+  const uint8_t* frame_rgba;   /* PINNED or NULL (cfg.frame_rgba): GUIFrame.buffer, app.rs:132-144 */
 } infur_b200_slot;
 
-/* Next free slot sized for n frames of w x h; INFUR_E_TICKET when all ring_depth slots are in flight. */
+/* Next free slot sized for n frames of w x h; INFUR_E_TICKET when all ring_depth slots (per device) are in flight.
+ * Tickets are 1-based and consecutive; with several devices ticket t lives on devices[(t - 1) % num_devices]. */
 int32_t infur_b200_ring_acquire(infur_b200_handle* h, uint32_t n, uint32_t w, uint32_t hgt, infur_b200_slot* slot);
 /* Frame source -> pinned memory without a staging copy (FFMpegDecoder::read_frame, ff-video/src/decoder.rs:150-165, for a
  * whole slot): reads up to the slot's n frames of w*h*3 bytes each from file descriptor `fd` (the rawvideo bgr24 pipe of
@@ -180,19 +209,55 @@ int32_t infur_b200_ring_acquire(infur_b200_handle* h, uint32_t n, uint32_t w, ui
  * (1-based counter, decoder.rs:163-164). */
 int32_t infur_b200_ring_read(infur_b200_handle* h, uint64_t ticket, int32_t fd, uint32_t* frames_read, size_t* partial_bytes);
 
-/* Enqueue H2D copy, the whole path, and the D2H copies of the slot; returns immediately. */
+/* Enqueue H2D copy, the whole path (with the Scale factor current at this call; the slot's output buffers grow if a factor
+ * raised since ring_acquire needs it), and the D2H copies of the slot; returns immediately.  On failure the slot is released. */
 int32_t infur_b200_ring_submit(infur_b200_handle* h, uint64_t ticket);
-/* Block until the slot's results are in pinned memory; tickets complete in submission order. */
+/* Block until the slot's results are in pinned memory.  Tickets may be waited in any order; each device completes its own
+ * tickets in submission order, so waiting in submission order never blocks longer than necessary. */
 int32_t infur_b200_ring_wait(infur_b200_handle* h, uint64_t ticket, infur_b200_slot* slot);
+/* Give an acquired (not yet submitted) slot back to the ring. */
+int32_t infur_b200_ring_release(infur_b200_handle* h, uint64_t ticket);
+
+/* ---- frame-level asynchronous API on top of the ring (what a "Proc" thread calls per frame) ------------------------------
+ * submit: copies the frame (tight HWC B,G,R u8) into the open pinned slot of devices[(id - 1) % num_devices] (id = 0 is treated
+ * as the submission counter); when that slot holds cfg.max_batch frames it is enqueued.  wait: results of one frame; frames may
+ * be waited in any order, a frame whose slot is still open is flushed first.  Result pointers are PINNED host memory owned by
+ * the library, valid until the second-next infur_b200_wait / infur_b200_flush call on the handle (the slot is recycled only
+ * after every frame of it has been waited and one more wait has passed).  All frames between two flushes must share w x h. */
+typedef struct infur_b200_result {
+  uint64_t ticket, id;
+  uint32_t out_w, out_h, num_classes;
+  int32_t has_decoded;       /* 0 when no model is loaded: decoded_img = None, app.rs:127-129 */
+  int32_t device;
+  const uint8_t* class_map;    /* [out_h][out_w] */
+  const uint8_t* decoded_rgba; /* [out_h][out_w][4] premultiplied (GUIFrame.decoded_buffer) */
+  const uint8_t* blended_rgba; /* or NULL */
+  const uint8_t* frame_rgba;   /* or NULL (GUIFrame.buffer) */
+} infur_b200_result;
+int32_t infur_b200_submit(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, uint64_t id, uint64_t* ticket);
+int32_t infur_b200_flush(infur_b200_handle* h);
+int32_t infur_b200_wait(infur_b200_handle* h, uint64_t ticket, infur_b200_result* out);
 
 /* ---- device-resident path (bench `value`: inputs already in HBM) --------------------------- */
 
-/* d_bgr: device pointer to n tight BGR frames.  d_class_map / d_decoded_rgba (/ d_blended, may be
- * NULL): device outputs [n][out_h][out_w]( [4] ).  Enqueued on the handle's compute stream;
- * `sync` != 0 waits for completion. */
+/* d_bgr: device pointer to n tight BGR frames (n <= cfg.max_batch).  Outputs are caller-owned DEVICE buffers with capacities in
+ * bytes: class map [n][out_h][out_w], decoded / blended RGBA [n][out_h][out_w][4].  The output size follows the current Scale
+ * factor; a call with every buffer NULL is a size query (fills out_w / out_h / num_classes / has_decoded / required[], runs
+ * nothing); a buffer that is too small returns INFUR_E_BUFFER_TOO_SMALL with required[] filled and nothing enqueued.  Without
+ * a loaded model has_decoded = 0 and the buffers are left untouched (app.rs:127-129).  Enqueued on the handle's compute stream
+ * (device 0 of a multi-device handle); `sync` != 0 waits for completion. */
+typedef struct infur_b200_device_out {
+  uint32_t struct_size;      /* sizeof(infur_b200_device_out) */
+  uint8_t* d_class_map;    size_t class_map_cap;
+  uint8_t* d_decoded_rgba; size_t decoded_rgba_cap;
+  uint8_t* d_blended_rgba; size_t blended_rgba_cap;   /* NULL unless cfg.blend */
+  /* written by the library */
+  uint32_t out_w, out_h, num_classes;
+  int32_t has_decoded;
+  size_t required[3];        /* bytes needed for the three buffers above */
+} infur_b200_device_out;
 int32_t infur_b200_advance_device(infur_b200_handle* h, const uint8_t* d_bgr, uint32_t n, uint32_t w, uint32_t hgt,
-                                  uint8_t* d_class_map, uint8_t* d_decoded_rgba, uint8_t* d_blended_rgba,
-                                  uint32_t* out_w, uint32_t* out_h, int32_t sync);
+                                  infur_b200_device_out* out, int32_t sync);
 
 /* CUDA stream (cudaStream_t) the device-resident path launches on, for event timing by the caller. */
 void* infur_b200_compute_stream(const infur_b200_handle* h);
@@ -277,6 +342,17 @@ int32_t infur_b200_plan_text(infur_b200_handle* h, uint32_t n, uint32_t w, uint3
  * *count = number of entries written (ops + 2). */
 int32_t infur_b200_profile_ops(infur_b200_handle* h, const uint8_t* d_bgr, uint32_t n, uint32_t w, uint32_t hgt,
                                int32_t iters, float* ms, int32_t cap, int32_t* count);
+
+/* The same timing without stalling the pipeline, for use INSIDE a sustained loop: profile_step enqueues one device-resident
+ * step (like advance_device into the plan's own output buffers) with a CUDA event after every kernel and returns
+ * immediately; profile_collect waits for the stream, averages every step recorded since the last collect into ms[] (same
+ * layout as profile_ops) and writes the number of steps averaged to *steps. */
+int32_t infur_b200_profile_step(infur_b200_handle* h, const uint8_t* d_bgr, uint32_t n, uint32_t w, uint32_t hgt);
+int32_t infur_b200_profile_collect(infur_b200_handle* h, float* ms, int32_t cap, int32_t* count, int32_t* steps);
+
+/* Milliseconds the most recent plan build took (tensor maps, buffers, autotune of tile shapes not seen before), and how many
+ * autotune measurements it launched; 0 / 0 when the last entry point found its plan in the cache. */
+int32_t infur_b200_plan_build_stats(const infur_b200_handle* h, float* ms, int32_t* tuned_convs);
 
 /* Parses an .onnx file on the CPU only (no device needed) and writes the fused op list as text;
  * lets the loader be tested without a GPU. */

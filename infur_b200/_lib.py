@@ -37,6 +37,10 @@ CONV_TCGEN05_I8 = 4     # conv_test only: int8 plan form of a quantised layer
 CONV_TCGEN05_I8_PAIR = 5
 LOAD_DEFAULT = 0
 LOAD_SKIP_WEIGHTS = 1
+CONF_RAW = 0
+CONF_SOFTMAX = 1
+ABI_VERSION = 2
+MAX_DEVICES = 8
 
 
 class Config(C.Structure):
@@ -44,6 +48,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("max_batch", C.c_int32), ("ring_depth", C.c_int32),
         ("resize_mode", C.c_int32), ("compute_aux", C.c_int32), ("blend", C.c_int32), ("conv_impl", C.c_int32),
         ("use_cuda_graph", C.c_int32), ("autotune", C.c_int32),
+        ("num_devices", C.c_int32), ("devices", C.c_int32 * 8), ("frame_rgba", C.c_int32), ("confidence", C.c_int32),
     ]
 
 
@@ -65,8 +70,27 @@ class Out(C.Structure):
 class Slot(C.Structure):
     _fields_ = [
         ("ticket", C.c_uint64), ("n", C.c_uint32), ("w", C.c_uint32), ("h", C.c_uint32),
+        ("out_w", C.c_uint32), ("out_h", C.c_uint32), ("num_classes", C.c_uint32), ("has_decoded", C.c_int32), ("device", C.c_int32),
+        ("bgr_in", C.c_void_p), ("class_map", C.c_void_p), ("decoded_rgba", C.c_void_p), ("blended_rgba", C.c_void_p), ("frame_rgba", C.c_void_p),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("ticket", C.c_uint64), ("id", C.c_uint64), ("out_w", C.c_uint32), ("out_h", C.c_uint32), ("num_classes", C.c_uint32),
+        ("has_decoded", C.c_int32), ("device", C.c_int32),
+        ("class_map", C.c_void_p), ("decoded_rgba", C.c_void_p), ("blended_rgba", C.c_void_p), ("frame_rgba", C.c_void_p),
+    ]
+
+
+class DeviceOut(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("d_class_map", C.c_void_p), ("class_map_cap", C.c_size_t),
+        ("d_decoded_rgba", C.c_void_p), ("decoded_rgba_cap", C.c_size_t),
+        ("d_blended_rgba", C.c_void_p), ("blended_rgba_cap", C.c_size_t),
         ("out_w", C.c_uint32), ("out_h", C.c_uint32), ("num_classes", C.c_uint32), ("has_decoded", C.c_int32),
-        ("bgr_in", C.c_void_p), ("class_map", C.c_void_p), ("decoded_rgba", C.c_void_p), ("blended_rgba", C.c_void_p),
+        ("required", C.c_size_t * 3),
     ]
 
 
@@ -99,8 +123,17 @@ SYMBOLS = {
     "infur_b200_ring_read": (C.c_int32, [_H, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]),
     "infur_b200_ring_submit": (C.c_int32, [_H, C.c_uint64]),
     "infur_b200_ring_wait": (C.c_int32, [_H, C.c_uint64, C.POINTER(Slot)]),
-    "infur_b200_advance_device": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int32]),
+    "infur_b200_ring_release": (C.c_int32, [_H, C.c_uint64]),
+    "infur_b200_submit": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "infur_b200_flush": (C.c_int32, [_H]),
+    "infur_b200_wait": (C.c_int32, [_H, C.c_uint64, C.POINTER(Result)]),
+    "infur_b200_advance_device": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(DeviceOut), C.c_int32]),
+    "infur_b200_num_devices": (C.c_int32, [_H]),
+    "infur_b200_model_weights_checksum": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_uint64)]),
+    "infur_b200_class_legend": (C.c_int32, [_H, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "infur_b200_profile_step": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "infur_b200_profile_collect": (C.c_int32, [_H, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "infur_b200_plan_build_stats": (C.c_int32, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "infur_b200_compute_stream": (C.c_void_p, [_H]),
     "infur_b200_launch_count": (C.c_uint64, [_H]),
     "infur_b200_scale_advance": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

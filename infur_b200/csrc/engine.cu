@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -217,6 +218,7 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
     }
     CU_TRY(cudaMemcpy(dm->arena, host.data(), off, cudaMemcpyHostToDevice));
   }
+  CU_TRY(cudaDeviceSynchronize());   // legacy-stream uploads do not order with the handle's non-blocking streams
   for (auto& op : m.ops) { std::vector<float>().swap(op.conv.weight); std::vector<float>().swap(op.conv.weight2); }
   out = std::move(dm);
   return Status();
@@ -400,6 +402,19 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
   struct Cand { int bn; int var; };
   static const Cand cands[7] = {{256, kVarPair}, {256, kVarPlain}, {128, kVarPlain}, {64, kVarPlain}, {256, kVarHalo}, {128, kVarHalo}, {64, kVarHalo}};
   if (d.stem) return Status();
+  // Decisions are kept per layer-shape class: layer parameters + the number of 128-pixel M tiles of the whole batch in
+  // half-octave buckets (what decides waves per SM and hence which variant wins).  The 91 positions of the reference's scale
+  // slider (gui.rs:278-285) span 100x in area = 14 buckets, so most ticks -- and every re-visited factor -- tune nothing.
+  const double mtiles = (double)io.n * ((io.ow + 15) / 16) * ((io.oh + 7) / 8);
+  const TuneKey key{d.cin, d.cout, d.kh, d.stride, d.dil, d.mode, io.residual ? 1 : 0, d.cin2, (int)lround(2.0 * log2(std::max(1.0, mtiles)))};
+  {
+    auto it = H->tune_cache.find(key);
+    if (it != H->tune_cache.end()) {
+      if (it->second.block_n != po.block_n || it->second.variant != po.variant) return setup_conv_tc(d, io, po, it->second.block_n, it->second.variant);
+      return Status();
+    }
+  }
+  H->last_build_tuned++;
   const bool allow_pair = !pair_disabled_env();
   cudaEvent_t e0, e1;
   CU_TRY(cudaEventCreate(&e0));
@@ -431,12 +446,14 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (!st.ok()) return st;
+  H->tune_cache[key] = TuneChoice{best.bn, best.var};
   if (best.bn != po.block_n || best.var != po.variant) st = setup_conv_tc(d, io, po, best.bn, best.var);
   return st;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Plan
+constexpr size_t kMaxPlans = 6;
 
 template <typename T>
 static Status dev_alloc(Plan& p, T** ptr, size_t count) {
@@ -648,14 +665,28 @@ Status get_plan(infur_b200_handle* H, int n, int w, int h, Plan** out) {
   uint32_t fbits; memcpy(&fbits, &H->factor, 4);
   auto key = std::make_tuple(n, w, h, fbits, H->model_gen);
   auto it = H->plans.find(key);
+  H->last_build_ms = 0.f; H->last_build_tuned = 0;
   if (it == H->plans.end()) {
-    // keep the cache small: a size / scale / model change retires the old plans
-    if (H->plans.size() >= 4) { cudaStreamSynchronize(H->stream); H->plans.clear(); }
+    // bounded cache, least recently used plan retired first (a plan owns its activation buffers: ~0.3 GB per 1080p frame of batch)
+    while (H->plans.size() >= kMaxPlans) {
+      auto victim = H->plans.begin();
+      for (auto p = H->plans.begin(); p != H->plans.end(); ++p)
+        if (H->plan_used[p->first] < H->plan_used[victim->first]) victim = p;
+      cudaStreamSynchronize(H->stream); cudaStreamSynchronize(H->d2h);
+      H->plan_used.erase(victim->first);
+      H->plans.erase(victim);
+    }
+    const auto t0 = std::chrono::steady_clock::now();
     std::unique_ptr<Plan> p;
     Status st = build_plan(H, n, w, h, p);
     if (!st.ok()) return st;
+    // build_plan uploads tables and clears borders on the legacy stream, which does not order with the handle's
+    // non-blocking streams: make all of it visible before the first forward
+    if (cudaDeviceSynchronize() != cudaSuccess) return Status::error(INFUR_E_RUNTIME, "plan build: device synchronisation failed");
+    H->last_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     it = H->plans.emplace(key, std::move(p)).first;
   }
+  H->plan_used[key] = ++H->plan_clock;
   *out = it->second.get();
   return Status();
 }

@@ -4,9 +4,15 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -119,22 +125,63 @@ struct OutPtrs {
 };
 
 struct RingSlot {
-  int state = 0;  // 0 free, 1 acquired, 2 submitted
+  int state = 0;  // 0 free, 1 acquired, 2 submitted, 3 waited but still lent to the frame-level API (infur_b200_wait)
   uint64_t ticket = 0;
   uint32_t n = 0, w = 0, h = 0, ow = 0, oh = 0;
   size_t in_cap = 0, out_cap_px = 0;
+  bool out_blend = false, out_frame = false;   // which optional output buffers exist
   uint8_t* h_in = nullptr;      // pinned
   uint8_t* h_class = nullptr;
   uint8_t* h_decoded = nullptr;
   uint8_t* h_blended = nullptr;
+  uint8_t* h_frame = nullptr;
   uint8_t* d_in = nullptr;
   uint8_t* d_class = nullptr;
   uint32_t* d_decoded = nullptr;
   uint32_t* d_blended = nullptr;
+  uint32_t* d_frame = nullptr;
   cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_out = nullptr;
   int has_decoded = 0;
   uint32_t k = 0;
+  // multi-device handles: ring_submit is executed by the device's worker thread; ring_wait blocks on `issued`
+  std::shared_ptr<struct SubmitState> sub;
 };
+
+struct SubmitState {
+  std::mutex m;
+  std::condition_variable cv;
+  bool done = false;
+  int32_t rc = INFUR_OK;
+  std::string err;
+};
+
+// One worker thread per GPU of a multi-device handle: every CUDA call for that GPU is made by its worker, in FIFO order.
+struct Worker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<std::function<void()>> q;
+  bool stop = false;
+  void start();
+  void post(std::function<void()> f);
+  void run_sync(const std::function<void()>& f);   // post + wait for completion
+  void shutdown();
+};
+
+// Autotune decision per layer-shape class: the layer's parameters and the amount of work (128-pixel M tiles of the whole batch,
+// in half-octave buckets) -- not the exact image size or batch
+struct TuneKey {
+  int cin, cout, kh, stride, dil, mode, has_res, cin2, bucket;
+  bool operator<(const TuneKey& o) const {
+    return std::tie(cin, cout, kh, stride, dil, mode, has_res, cin2, bucket) <
+           std::tie(o.cin, o.cout, o.kh, o.stride, o.dil, o.mode, o.has_res, o.cin2, o.bucket);
+  }
+};
+struct TuneChoice { int block_n, variant; };
+
+// frame-level API (infur_b200_submit / wait): where a frame ticket lives
+struct FrameRef { int dev = 0; uint64_t slot_ticket = 0; uint32_t index = 0; uint64_t id = 0; };
+struct OpenSlot { bool open = false; uint64_t slot_ticket = 0; uint32_t count = 0, w = 0, h = 0; uint8_t* bgr_in = nullptr; };
 
 }  // namespace infur
 
@@ -153,8 +200,28 @@ struct infur_b200_handle {
   std::unique_ptr<infur::DeviceModel> model;
   uint64_t model_gen = 0;
   std::map<std::tuple<int, int, int, uint32_t, uint64_t>, std::unique_ptr<infur::Plan>> plans;
-  uint64_t launches = 0;
+  std::map<std::tuple<int, int, int, uint32_t, uint64_t>, uint64_t> plan_used;   // LRU stamps
+  uint64_t plan_clock = 0;
+  std::map<infur::TuneKey, infur::TuneChoice> tune_cache;   // survives plan eviction; cleared with the model
+  float last_build_ms = 0.f;
+  int last_build_tuned = 0;
+  std::atomic<uint64_t> launches{0};
   std::vector<infur::RingSlot> ring;
   uint64_t next_ticket = 1;
-  uint64_t next_wait = 1;
+  // in-loop profiling (infur_b200_profile_step / _collect): one event array per recorded step
+  std::vector<std::vector<cudaEvent_t>> prof_sets;
+  // ---- multi-device handles (cfg.num_devices > 1): this handle is device 0's context and the root of the group
+  int index = 0;                                  // position in the device list
+  infur_b200_handle* root = nullptr;              // children point to the root; nullptr on the root / a single-device handle
+  std::vector<infur_b200_handle*> devs;           // root only: [this, child 1, ...]; empty for a single-device handle
+  std::vector<std::unique_ptr<infur::Worker>> workers;   // root only, parallel to devs
+  void* nccl_comms[INFUR_B200_MAX_DEVICES] = {};
+  bool dup_devices = false;                       // test hook: one GPU listed several times (no NCCL communicator)
+  // ---- frame-level API state (root / single-device handle)
+  std::map<uint64_t, infur::FrameRef> frames;     // frame ticket -> slot
+  std::map<uint64_t, uint32_t> slot_waits;        // slot ticket (submitted) -> frames of it not yet waited
+  std::vector<infur::OpenSlot> open_slots;        // per device
+  std::vector<std::pair<int, uint64_t>> lent, lent_prev;   // slots fully waited: recycled two waits later
+  uint64_t next_frame_ticket = 1, submit_counter = 0;
+  std::map<uint64_t, int> ticket_dev;             // ring ticket -> index into the device list
 };

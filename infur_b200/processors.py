@@ -106,16 +106,27 @@ def _check_bgr(img: np.ndarray) -> np.ndarray:
 
 # --------------------------------------------------------------------------- handle
 class Handle:
-    """Owner of one ``infur_b200_handle`` (one GPU, one owner thread)."""
+    """Owner of one ``infur_b200_handle``: one GPU, or -- ``devices=[...]`` -- several GPUs of the box behind one handle
+    (one owner thread either way; the library runs one worker thread per GPU)."""
 
     def __init__(self, device: int = 0, max_batch: int = 8, ring_depth: int = 3, compute_aux: bool = False, blend: bool = False,
-                 conv_impl: int = L.CONV_TCGEN05, resize_mode: int = L.RESIZE_NEAREST):
+                 conv_impl: int = L.CONV_TCGEN05, resize_mode: int = L.RESIZE_NEAREST, devices=None, frame_rgba: bool = True,
+                 use_cuda_graph: bool = True, confidence: int = L.CONF_RAW, autotune: bool = True):
         self.lib = L.load()
         cfg = L.Config()
         self.lib.infur_b200_default_config(C.byref(cfg))
         cfg.device, cfg.max_batch, cfg.ring_depth = device, max_batch, ring_depth
         cfg.compute_aux, cfg.blend, cfg.conv_impl = int(compute_aux), int(blend), conv_impl
         cfg.resize_mode = resize_mode
+        cfg.frame_rgba, cfg.use_cuda_graph, cfg.confidence, cfg.autotune = int(frame_rgba), int(use_cuda_graph), confidence, int(autotune)
+        if devices is not None:
+            devices = list(devices)
+            if not 1 <= len(devices) <= L.MAX_DEVICES:
+                raise ValueError("devices must list 1..8 CUDA ordinals")
+            cfg.num_devices = len(devices)
+            for i, d in enumerate(devices):
+                cfg.devices[i] = d
+            cfg.device = devices[0]
         self.cfg = cfg
         self._h = C.c_void_p()
         rc = self.lib.infur_b200_create(C.byref(cfg), C.byref(self._h))
@@ -345,11 +356,63 @@ class Handle:
         return int(self.lib.infur_b200_compute_stream(self._h) or 0)
 
     # -- device-resident and ring paths
-    def advance_device(self, d_bgr: int, n: int, w: int, h: int, d_class: int, d_decoded: int, d_blended: int = 0, sync: bool = False):
-        ow, oh = C.c_uint32(), C.c_uint32()
-        self._check(self.lib.infur_b200_advance_device(self._h, C.c_void_p(d_bgr), n, w, h, C.c_void_p(d_class), C.c_void_p(d_decoded),
-                                                        C.c_void_p(d_blended) if d_blended else None, C.byref(ow), C.byref(oh), int(sync)))
-        return ow.value, oh.value
+    def advance_device(self, d_bgr: int, n: int, w: int, h: int, d_class: int, d_decoded: int, d_blended: int = 0, sync: bool = False,
+                       caps=None):
+        """Device buffers in and out.  ``caps`` = (class_map, decoded, blended) capacities in bytes; default: exactly what an
+        output of the INPUT size needs (scale 1.0) -- a larger Scale factor then fails with E_BUFFER_TOO_SMALL."""
+        o = L.DeviceOut()
+        o.struct_size = C.sizeof(L.DeviceOut)
+        px = n * w * h
+        caps = caps or (px, px * 4, px * 4)
+        o.d_class_map, o.class_map_cap = d_class or None, caps[0]
+        o.d_decoded_rgba, o.decoded_rgba_cap = d_decoded or None, caps[1]
+        o.d_blended_rgba, o.blended_rgba_cap = d_blended or None, caps[2]
+        self._check(self.lib.infur_b200_advance_device(self._h, C.c_void_p(d_bgr), n, w, h, C.byref(o), int(sync)))
+        return o.out_w, o.out_h
+
+    def advance_device_query(self, n: int, w: int, h: int) -> dict:
+        """Size query of the device-resident path: nothing runs."""
+        o = L.DeviceOut()
+        o.struct_size = C.sizeof(L.DeviceOut)
+        self._check(self.lib.infur_b200_advance_device(self._h, None, n, w, h, C.byref(o), 0))
+        return {"out_w": o.out_w, "out_h": o.out_h, "num_classes": o.num_classes, "has_decoded": bool(o.has_decoded), "required": list(o.required)}
+
+    def profile_step(self, d_bgr: int, n: int, w: int, h: int):
+        self._check(self.lib.infur_b200_profile_step(self._h, C.c_void_p(d_bgr), n, w, h))
+
+    def profile_collect(self):
+        cap = 256
+        ms = (C.c_float * cap)()
+        cnt, steps = C.c_int32(), C.c_int32()
+        self._check(self.lib.infur_b200_profile_collect(self._h, ms, cap, C.byref(cnt), C.byref(steps)))
+        return [ms[i] for i in range(cnt.value)], steps.value
+
+    def plan_build_stats(self):
+        ms, tuned = C.c_float(), C.c_int32()
+        self._check(self.lib.infur_b200_plan_build_stats(self._h, C.byref(ms), C.byref(tuned)))
+        return ms.value, tuned.value
+
+    def num_devices(self) -> int:
+        return int(self.lib.infur_b200_num_devices(self._h))
+
+    def weights_checksum(self, index: int = 0) -> int:
+        v = C.c_uint64()
+        self._check(self.lib.infur_b200_model_weights_checksum(self._h, index, C.byref(v)))
+        return v.value
+
+    def class_legend(self):
+        """[(index, label, (r, g, b))] for the loaded model's classes, or None without a model."""
+        need = C.c_size_t()
+        rc = self.lib.infur_b200_class_legend(self._h, None, 0, C.byref(need))
+        if rc == L.E_INVALID_ARG:
+            return None
+        buf = C.create_string_buffer(need.value)
+        self._check(self.lib.infur_b200_class_legend(self._h, buf, need.value, C.byref(need)))
+        out = []
+        for ln in buf.value.decode().splitlines():
+            i, label, rgb = ln.split("\t")
+            out.append((int(i), label, tuple(int(v) for v in rgb.split(","))))
+        return out
 
     def profile_ops(self, d_bgr: int, n: int, w: int, h: int, iters: int = 3):
         cap = 256
@@ -379,13 +442,46 @@ class Handle:
         s = L.Slot()
         self._check(self.lib.infur_b200_ring_wait(self._h, ticket, C.byref(s)))
         n, oh, ow = s.n, s.out_h, s.out_w
-        out = {"n": n, "out_w": ow, "out_h": oh, "has_decoded": bool(s.has_decoded), "num_classes": s.num_classes,
-               "class_map": None, "decoded_rgba": None, "blended_rgba": None}
+        out = {"n": n, "out_w": ow, "out_h": oh, "has_decoded": bool(s.has_decoded), "num_classes": s.num_classes, "device": s.device,
+               "class_map": None, "decoded_rgba": None, "blended_rgba": None, "frame_rgba": None}
         if s.has_decoded and n * oh * ow:
             out["class_map"] = np.ctypeslib.as_array(C.cast(s.class_map, C.POINTER(C.c_uint8)), shape=(n, oh, ow))
             out["decoded_rgba"] = np.ctypeslib.as_array(C.cast(s.decoded_rgba, C.POINTER(C.c_uint8)), shape=(n, oh, ow, 4))
             if s.blended_rgba:
                 out["blended_rgba"] = np.ctypeslib.as_array(C.cast(s.blended_rgba, C.POINTER(C.c_uint8)), shape=(n, oh, ow, 4))
+        if s.frame_rgba and n * oh * ow:
+            out["frame_rgba"] = np.ctypeslib.as_array(C.cast(s.frame_rgba, C.POINTER(C.c_uint8)), shape=(n, oh, ow, 4))
+        return out
+
+    def ring_release(self, ticket: int):
+        self._check(self.lib.infur_b200_ring_release(self._h, ticket))
+
+    # -- frame-level asynchronous API (what a "Proc" thread calls per frame)
+    def submit(self, img: np.ndarray, id: int = 0) -> int:
+        img = _check_bgr(img)
+        h, w = img.shape[:2]
+        t = C.c_uint64()
+        self._check(self.lib.infur_b200_submit(self._h, img.ctypes.data, w, h, id, C.byref(t)))
+        return t.value
+
+    def flush(self):
+        self._check(self.lib.infur_b200_flush(self._h))
+
+    def wait(self, ticket: int) -> dict:
+        """Result of one submitted frame; the arrays are views into pinned library memory (valid until the second-next wait)."""
+        r = L.Result()
+        self._check(self.lib.infur_b200_wait(self._h, ticket, C.byref(r)))
+        oh, ow = r.out_h, r.out_w
+        out = {"id": r.id, "out_w": ow, "out_h": oh, "has_decoded": bool(r.has_decoded), "num_classes": r.num_classes, "device": r.device,
+               "class_map": None, "decoded_rgba": None, "blended_rgba": None, "frame_rgba": None}
+
+        def view(p, shape):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=shape) if p and oh * ow else None
+
+        out["class_map"] = view(r.class_map, (oh, ow))
+        out["decoded_rgba"] = view(r.decoded_rgba, (oh, ow, 4))
+        out["blended_rgba"] = view(r.blended_rgba, (oh, ow, 4))
+        out["frame_rgba"] = view(r.frame_rgba, (oh, ow, 4))
         return out
 
 

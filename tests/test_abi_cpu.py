@@ -19,7 +19,7 @@ def test_header_symbols_all_exported(lib):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
-    assert lib.infur_b200_abi_version() == 1
+    assert lib.infur_b200_abi_version() == 2
 
 
 def test_default_config(lib):
@@ -118,7 +118,7 @@ def test_header_is_plain_c99(lib, tmp_path):
     src = tmp_path / "cabi.c"
     src.write_text('#include "include/infur_b200.h"\n'
                    "int main(void) { infur_b200_config c; infur_b200_default_config(&c);\n"
-                   "  return (infur_b200_abi_version() == 1 && c.max_batch > 0) ? 0 : 1; }\n")
+                   "  return (infur_b200_abi_version() == 2 && c.max_batch > 0) ? 0 : 1; }\n")
     exe = tmp_path / "cabi"
     libdir = os.path.join(root, "infur_b200", "lib")
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", root, str(src), "-o", str(exe), "-L", libdir,
