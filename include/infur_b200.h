@@ -351,7 +351,7 @@ int32_t infur_b200_profile_step(infur_b200_handle* h, const uint8_t* d_bgr, uint
 int32_t infur_b200_profile_collect(infur_b200_handle* h, float* ms, int32_t cap, int32_t* count, int32_t* steps);
 
 /* Milliseconds the most recent plan build took (tensor maps, buffers, autotune of tile shapes not seen before), and how many
- * autotune measurements it launched; 0 / 0 when the last entry point found its plan in the cache. */
+ * convolutions it autotuned (0 when every layer-shape class was known). */
 int32_t infur_b200_plan_build_stats(const infur_b200_handle* h, float* ms, int32_t* tuned_convs);
 
 /* Parses an .onnx file on the CPU only (no device needed) and writes the fused op list as text;

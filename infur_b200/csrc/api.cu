@@ -871,8 +871,16 @@ int32_t infur_b200_submit(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, 
   return INFUR_OK;
 }
 
+// slots whose frames had all been waited two calls ago go back to the ring
+static void recycle_lent(infur_b200_handle* h) {
+  for (auto& pr : h->lent_prev) { RingSlot* s = find_slot(ctx_of(h, pr.first), pr.second); if (s && s->state == 3) slot_free(h, pr.first, s); }
+  h->lent_prev.swap(h->lent);
+  h->lent.clear();
+}
+
 int32_t infur_b200_flush(infur_b200_handle* h) {
   if (!h) return INFUR_E_INVALID_ARG;
+  recycle_lent(h);
   int32_t rc = INFUR_OK;
   for (int d = 0; d < num_devs(h); ++d) { const int32_t r = submit_open(h, d); if (rc == INFUR_OK) rc = r; }
   return rc;
@@ -880,10 +888,7 @@ int32_t infur_b200_flush(infur_b200_handle* h) {
 
 int32_t infur_b200_wait(infur_b200_handle* h, uint64_t ticket, infur_b200_result* out) {
   if (!h || !out) return INFUR_E_INVALID_ARG;
-  // slots whose frames had all been waited two calls ago go back to the ring now
-  for (auto& pr : h->lent_prev) { RingSlot* s = find_slot(ctx_of(h, pr.first), pr.second); if (s && s->state == 3) slot_free(h, pr.first, s); }
-  h->lent_prev.swap(h->lent);
-  h->lent.clear();
+  recycle_lent(h);
   auto it = h->frames.find(ticket);
   if (it == h->frames.end()) return fail(h, INFUR_E_TICKET, "wait: unknown frame ticket (never submitted, already waited, or its slot failed)");
   const FrameRef ref = it->second;

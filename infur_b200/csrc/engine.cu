@@ -409,6 +409,13 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
   const TuneKey key{d.cin, d.cout, d.kh, d.stride, d.dil, d.mode, io.residual ? 1 : 0, d.cin2, (int)lround(2.0 * log2(std::max(1.0, mtiles)))};
   {
     auto it = H->tune_cache.find(key);
+    // a measured decision of the same layer within one octave of work (+-2 buckets) is reused without measuring: moving the
+    // scale slider by a tick must not cost an autotune (the choice is about waves per SM, which changes slowly with size)
+    for (int delta = 1; delta <= 2 && it == H->tune_cache.end(); ++delta)
+      for (int sgn = -1; sgn <= 1 && it == H->tune_cache.end(); sgn += 2) {
+        TuneKey k2 = key; k2.bucket += sgn * delta;
+        it = H->tune_cache.find(k2);
+      }
     if (it != H->tune_cache.end()) {
       if (it->second.block_n != po.block_n || it->second.variant != po.variant) return setup_conv_tc(d, io, po, it->second.block_n, it->second.variant);
       return Status();
@@ -665,8 +672,8 @@ Status get_plan(infur_b200_handle* H, int n, int w, int h, Plan** out) {
   uint32_t fbits; memcpy(&fbits, &H->factor, 4);
   auto key = std::make_tuple(n, w, h, fbits, H->model_gen);
   auto it = H->plans.find(key);
-  H->last_build_ms = 0.f; H->last_build_tuned = 0;
   if (it == H->plans.end()) {
+    H->last_build_ms = 0.f; H->last_build_tuned = 0;
     // bounded cache, least recently used plan retired first (a plan owns its activation buffers: ~0.3 GB per 1080p frame of batch)
     while (H->plans.size() >= kMaxPlans) {
       auto victim = H->plans.begin();

@@ -154,6 +154,8 @@ def test_frame_level_submit_wait_in_order(which, group, single, tiny):
     h.flush()
     for i, t in enumerate(t2):
         assert (h.wait(t)["class_map"] == want[i]["class_map"]).all()
+    h.flush()
+    h.flush()                             # two more wait / flush calls: every lent slot is back in the ring
 
 
 def test_scale_raised_between_acquire_and_submit(single, tiny):
