@@ -105,8 +105,11 @@ def _preprocess(bgr: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(((x - mean) * inv).transpose(2, 0, 1))
 
 
-def quantize_fcn(model, calib_hw=(96, 128), n_calib: int = 3, aux: bool = False) -> bytes:
-    """Return the bytes of a QOperator-format ONNX model of ``model`` (a ``synth.build_fcn`` network)."""
+def quantize_fcn(model, calib_hw=(96, 128), n_calib: int = 3, aux: bool = False, static_hw=None) -> bytes:
+    """Return the bytes of a QOperator-format ONNX model of ``model`` (a ``synth.build_fcn`` network).
+
+    ``static_hw=(h, w)``: fixed input shape ``[1, 3, h, w]`` and a constant ``sizes`` input of the final Resize instead of the
+    Shape/Slice/Concat subgraph (importers without dynamic-shape support, e.g. cv2.dnn, need this)."""
     import torch
 
     model.eval()
@@ -157,6 +160,12 @@ def quantize_fcn(model, calib_hw=(96, 128), n_calib: int = 3, aux: bool = False)
         elif st[0] == "head":
             _, low, hname = st
             nodes.append(W.node("DequantizeLinear", [low, low + "_scale", low + "_zp"], [low + "_f"], name=hname + "_dequantize"))
+            if static_hw is not None:
+                kk = int(model.classifier[4].weight.shape[0])
+                inits[hname + "_sizes"] = np.array([1, kk, static_hw[0], static_hw[1]], dtype=np.int64)
+                nodes.append(W.node("Resize", [low + "_f", "", "", hname + "_sizes"], [hname], name=hname + "_resize", mode="linear",
+                                    coordinate_transformation_mode="half_pixel"))
+                continue
             # resize to the network input's H x W: sizes = concat(shape(low)[0:2], shape(input)[2:4])
             for nm, v in (("c0", [0]), ("c2", [2]), ("c4", [4])):
                 inits[nm] = np.array(v, dtype=np.int64)
@@ -171,8 +180,8 @@ def quantize_fcn(model, calib_hw=(96, 128), n_calib: int = 3, aux: bool = False)
     k = int(model.classifier[4].weight.shape[0])
     return W.model(
         nodes, inits,
-        [W.value_info("input", W.FLOAT, ["batch", 3, "height", "width"])],
-        [W.value_info(hn, W.FLOAT, ["batch", k, "height", "width"]) for hn in heads],
+        [W.value_info("input", W.FLOAT, ["batch", 3, "height", "width"] if static_hw is None else [1, 3, static_hw[0], static_hw[1]])],
+        [W.value_info(hn, W.FLOAT, ["batch", k, "height", "width"] if static_hw is None else [1, k, static_hw[0], static_hw[1]]) for hn in heads],
         opsets=(("", 12), ("com.microsoft", 1)), producer="infur_b200.quantize")
 
 
