@@ -1102,6 +1102,7 @@ static int32_t upsample_color_impl(infur_b200_handle* h, const float* lowres, ui
   q.y0 = dy0; q.y1 = dy1; q.ly0 = dly0; q.ly1 = dly1; q.x0 = dx0; q.x1 = dx1; q.lx0 = dlx0; q.lx1 = dlx1;
   q.color_lut = h->d_color_lut; q.frame_bgr = d_frame; q.class_map = d_cls; q.decoded = d_dec; q.blended = d_bl; q.logits = d_log;
   q.max_lr = max_lr; q.max_lc = max_lc;
+  q.softmax = h->cfg.confidence == INFUR_CONF_SOFTMAX ? 1 : 0;
   if (post_smem_bytes(q) > 200 * 1024) return fail(h, INFUR_E_UNSUPPORTED, "upsample_color: low-res patch per tile does not fit shared memory (upsampling ratio too small / too many classes)");
   cudaError_t e = launch_post(q, h->stream);
   h->launches++;

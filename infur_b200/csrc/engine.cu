@@ -758,6 +758,7 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
   q.color_lut = H->d_color_lut; q.frame_bgr = frame;
   q.class_map = o.class_map; q.decoded = o.decoded; q.blended = o.blended; q.frame_rgba = o.frame_rgba; q.logits = o.logits;
   q.max_lr = p.max_lr; q.max_lc = p.max_lc; q.top_code = p.top_code;
+  q.softmax = H->cfg.confidence == INFUR_CONF_SOFTMAX ? 1 : 0;
   if (!q.decoded) q.decoded = p.d_decoded;
   if (o.aux_logits && p.aux_lowres) {
     // debug path: the aux head through the same post kernel first; only its logits are kept
@@ -768,7 +769,7 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
     H->launches++;
   }
   CU_TRY(launch_post(q, s));
-  H->launches += (q.top_code && q.k == 21) ? 2 : 1;
+  H->launches += (q.top_code && q.k == 21 && !q.softmax) ? 2 : 1;
   if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
   (void)op_ms;
   return Status();

@@ -274,13 +274,25 @@ __global__ void __launch_bounds__(128) post_kernel(PostArgs a) {
     const int r0 = a.y0[y] - lr0, r1 = a.y1[y] - lr0;
     const float w0 = a.ly0[y], w1 = a.ly1[y];
     int k_max = 0;
-    float c_max = 0.f;
+    float c_max = a.softmax ? -INFINITY : 0.f;
     const size_t pix = (size_t)y * a.ow + x;
     for (int k = 0; k < a.k; ++k) {
       const float* hk = hor + (size_t)k * nrow * kPostTile + lane;
       const float v = __fadd_rn(__fmul_rn(w0, hk[r0 * kPostTile]), __fmul_rn(w1, hk[r1 * kPostTile]));
       if (a.logits) a.logits[((size_t)img * a.k + k) * plane + pix] = v;
       if (v > c_max) { k_max = k; c_max = v; }
+    }
+    if (a.softmax) {
+      // confidence = softmax probability of the winning class: p = 1 / sum_k exp(v_k - max) (the winner's own term is exp(0) = 1);
+      // every probability is > 0, so ColorCode's strict '>' scan from (0, 0.0) picks the first maximum of the logits
+      float sum = 0.f;
+      for (int k = 0; k < a.k; ++k) {
+        const float* hk = hor + (size_t)k * nrow * kPostTile + lane;
+        const float v = __fadd_rn(__fmul_rn(w0, hk[r0 * kPostTile]), __fmul_rn(w1, hk[r1 * kPostTile]));
+        sum = __fadd_rn(sum, expf(__fsub_rn(v, c_max)));
+      }
+      c_max = c_max == c_max && sum > 0.f ? __fdiv_rn(1.0f, sum) : 0.f;
+      if (!(c_max > 0.f)) k_max = 0;   // NaN logits: nothing beats (0, 0.0)
     }
     const float av = __fmul_rn(c_max, 255.0f);
     const int alpha = av >= 255.0f ? 255 : (int)av;  // c_max >= 0 always; trunc toward zero, saturate
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(256) lowres_top_kernel(const float* __restrict
   code[i] = safe ? k1 : -1;
 }
 
-template <int K>
+template <int K, bool SOFTMAX = false>
 __global__ void __launch_bounds__(128, 3) post_strip_kernel(PostArgs a) {
   constexpr int KQ = (K + 3) / 4;     // float4 per low-res pixel that carry classes
   constexpr int KP = KQ * 4;
@@ -386,7 +398,7 @@ __global__ void __launch_bounds__(128, 3) post_strip_kernel(PostArgs a) {
   float ft = 0.f, fb = 0.f;
   for (int y = Y0; y < Y1; ++y) {
     const int r0 = __ldg(a.y0 + y), r1 = __ldg(a.y1 + y);   // warp-uniform
-    if (a.top_code && !a.logits) {
+    if (!SOFTMAX && a.top_code && !a.logits) {
       // Fast path: when ONE class wins all four low-res pixels a lane's output pixel blends, by a safe margin, it wins
       // the blend too (each interpolation step is monotone in its inputs, and the margin dwarfs the rounding error),
       // so only that class needs interpolating -- with the very same operations, hence the same bits.
@@ -436,7 +448,7 @@ __global__ void __launch_bounds__(128, 3) post_strip_kernel(PostArgs a) {
     // either way).  The running maximum is fmaxf (keeps the old value on NaN and on ties, like a failed '>').
     constexpr int KB = (K + 2) / 3;
     int bk[3] = {0, KB, 2 * KB};
-    float bv[3] = {0.f, -INFINITY, -INFINITY};
+    float bv[3] = {SOFTMAX ? -INFINITY : 0.f, -INFINITY, -INFINITY};
     const size_t pix = (size_t)y * a.ow + x;
 #pragma unroll
     for (int i = 0; i < KB; ++i) {
@@ -459,6 +471,17 @@ __global__ void __launch_bounds__(128, 3) post_strip_kernel(PostArgs a) {
       const bool gt = bv[j] > c_max;
       k_max = gt ? bk[j] : k_max;
       c_max = fmaxf(c_max, bv[j]);
+    }
+    if (SOFTMAX) {
+      // see post_kernel: p(winner) = 1 / sum_k exp(v_k - max), classes summed in index order
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float v = __fadd_rn(__fmul_rn(wy0, top[k]), __fmul_rn(wy1, bot[k]));
+        sum = __fadd_rn(sum, expf(__fsub_rn(v, c_max)));
+      }
+      c_max = c_max == c_max && sum > 0.f ? __fdiv_rn(1.0f, sum) : 0.f;
+      if (!(c_max > 0.f)) k_max = 0;
     }
     if (xin) post_emit(a, img, plane, pix, k_max, c_max);
   }
@@ -565,21 +588,20 @@ size_t post_smem_bytes(const PostArgs& a) {
 
 cudaError_t launch_post(const PostArgs& a, cudaStream_t s) {
   if (a.k == 21 && a.ldk % 4 == 0 && a.ldk >= 24) {   // the 21 VOC classes of fcn-resnet50; other K: generic kernel below
+    dim3 grid((a.ow + 31) / 32, (a.oh + 4 * kPostStripRows - 1) / (4 * kPostStripRows), a.n);
+    if (a.softmax) { post_strip_kernel<21, true><<<grid, 128, 0, s>>>(a); return cudaGetLastError(); }
     if (a.top_code) {
       const size_t npix = (size_t)a.n * a.lh * a.lw;
       lowres_top_kernel<21><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(a.lowres, a.ldk, npix, a.top_code);
     }
-    dim3 grid((a.ow + 31) / 32, (a.oh + 4 * kPostStripRows - 1) / (4 * kPostStripRows), a.n);
     post_strip_kernel<21><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
   }
   const size_t smem = post_smem_bytes(a);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {   // function attributes are per device: set on every launch that needs it (cheap)
     cudaError_t e = cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   dim3 grid((a.ow + kPostTile - 1) / kPostTile, (a.oh + kPostTile - 1) / kPostTile, a.n);
   post_kernel<<<grid, 128, smem, s>>>(a);

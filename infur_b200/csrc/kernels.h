@@ -55,6 +55,7 @@ struct PostArgs {
   uint32_t* frame_rgba;       // may be nullptr
   float* logits;              // [n][k][oh][ow] f32, may be nullptr (debug)
   int max_lr, max_lc;         // largest low-res patch (rows, cols) any 32x32 output tile touches
+  int softmax;                // INFUR_CONF_SOFTMAX: confidence = softmax probability of the winning class (README.md:76), else the raw logit
   int32_t* top_code;          // scratch [n][lh][lw] (K = 21 path): winning class of a low-res pixel if it wins by a safe margin, else -1; may be nullptr
 };
 cudaError_t launch_post(const PostArgs& a, cudaStream_t s);

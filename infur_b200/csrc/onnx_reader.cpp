@@ -1,6 +1,8 @@
 // ONNX protobuf-wire reader + lowering to the fused conv list.  See onnx_reader.h.
 #include "onnx_reader.h"
 
+#include <climits>
+
 #include <cstdio>
 #include <cstring>
 #include <set>
@@ -161,9 +163,26 @@ const char* dtype_name(int32_t t) {
   }
 }
 
+// numel with every dimension checked: a malformed file must fail the load, not wrap around into a small count
+size_t checked_numel(const OnnxTensor& t, const std::string& what) {
+  size_t n = 1;
+  for (int64_t d : t.dims) {
+    if (d < 0 || d > (int64_t)INT32_MAX) throw ModelError(INFUR_E_MODEL_LOAD, what + ": initializer '" + t.name + "' has a negative or oversized dimension");
+    if (d != 0 && n > (size_t)1 << 40) throw ModelError(INFUR_E_MODEL_LOAD, what + ": initializer '" + t.name + "' is too large");
+    n *= (size_t)d;
+  }
+  return n;
+}
+
+// kernel size, stride and dilation positive and small, padding non-negative: build_plan divides by the stride
+void check_geometry(const std::string& what, int64_t k, int64_t stride, int64_t dil, int64_t pad) {
+  if (k < 1 || k > 64 || stride < 1 || stride > 64 || dil < 1 || dil > 64 || pad < 0 || pad > 4096)
+    throw ModelError(INFUR_E_MODEL_LOAD, what + ": kernel size, stride and dilation must be 1..64 and padding 0..4096");
+}
+
 std::vector<float> tensor_f32(const OnnxTensor& t, const std::string& what) {
   if (t.dtype != 1) throw ModelError(INFUR_E_MODEL_LOAD, what + ": initializer '" + t.name + "' is not FLOAT (quantised models are not supported)");
-  size_t n = t.numel();
+  size_t n = checked_numel(t, what);
   std::vector<float> v(n);
   if (t.raw && t.raw_size == n * 4) memcpy(v.data(), t.raw, n * 4);
   else if (t.float_data.size() == n) v = t.float_data;
@@ -173,7 +192,7 @@ std::vector<float> tensor_f32(const OnnxTensor& t, const std::string& what) {
 
 // Integer initializer (UINT8 / INT8 / INT32; raw_data or int32_data) widened to int32.
 std::vector<int32_t> tensor_i32(const OnnxTensor& t, const std::string& what) {
-  const size_t n = t.numel();
+  const size_t n = checked_numel(t, what);
   std::vector<int32_t> v(n);
   const size_t esz = t.dtype == 6 ? 4 : (t.dtype == 2 || t.dtype == 3) ? 1 : 0;
   if (!esz) throw ModelError(INFUR_E_MODEL_LOAD, what + ": initializer '" + t.name + "' must be UINT8, INT8 or INT32");
@@ -395,6 +414,7 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
   };
   auto conv_geometry = [&](const OnnxNode& n, const OnnxTensor& wt, ConvOp& c) {
     if (wt.dims.size() != 4) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': weight must be 4-D");
+    for (int64_t d : wt.dims) if (d < 1 || d > (1 << 20)) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': weight dimensions must be 1..2^20");
     c.cout = (int)wt.dims[0]; c.cin = (int)wt.dims[1]; c.kh = (int)wt.dims[2]; c.kw = (int)wt.dims[3];
     if (attr_i(n, "group", 1) != 1) throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': group != 1 is not supported");
     auto strides = attr_ints(n, "strides", {1, 1}), dil = attr_ints(n, "dilations", {1, 1}), pads = attr_ints(n, "pads", {0, 0, 0, 0});
@@ -403,6 +423,7 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
     if (auto* ap = n.attr("auto_pad")) if (!ap->s.empty() && ap->s != "NOTSET") throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': auto_pad is not supported");
     if (strides.size() != 2 || strides[0] != strides[1] || dil.size() != 2 || dil[0] != dil[1] || pads.size() != 4 || !all_eq(pads, pads[0]) || c.kh != c.kw)
       throw ModelError(INFUR_E_MODEL_LOAD, n.op + " '" + n.name + "': only square kernels with symmetric stride/dilation/padding are supported");
+    check_geometry(n.op + " '" + n.name + "'", c.kh, strides[0], dil[0], pads[0]);
     c.stride = (int)strides[0]; c.dil = (int)dil[0]; c.pad = (int)pads[0];
   };
 
@@ -526,6 +547,7 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       if (wit == g.inits.end()) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': weight is not an initializer (quantised / dynamic weights are not supported)");
       const OnnxTensor& wt = wit->second;
       if (wt.dims.size() != 4) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': weight must be 4-D");
+      for (int64_t d : wt.dims) if (d < 1 || d > (1 << 20)) throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': weight dimensions must be 1..2^20");
       LoweredOp op; op.kind = OpKind::Conv; op.name = n.name.empty() ? n.out[0] : n.name;
       ConvOp& c = op.conv;
       c.cout = (int)wt.dims[0]; c.cin = (int)wt.dims[1]; c.kh = (int)wt.dims[2]; c.kw = (int)wt.dims[3];
@@ -536,6 +558,7 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       if (auto* ap = n.attr("auto_pad")) if (!ap->s.empty() && ap->s != "NOTSET") throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': auto_pad is not supported");
       if (strides.size() != 2 || strides[0] != strides[1] || dil.size() != 2 || dil[0] != dil[1] || pads.size() != 4 || !all_eq(pads, pads[0]) || c.kh != c.kw)
         throw ModelError(INFUR_E_MODEL_LOAD, "Conv '" + n.name + "': only square kernels with symmetric stride/dilation/padding are supported");
+      check_geometry("Conv '" + n.name + "'", c.kh, strides[0], dil[0], pads[0]);
       c.stride = (int)strides[0]; c.dil = (int)dil[0]; c.pad = (int)pads[0];
       std::vector<float> w = tensor_f32(wt, "Conv '" + n.name + "'");
       c.weight.resize(w.size());
@@ -582,6 +605,7 @@ void lower_model(const OnnxGraph& g, LoweredModel& m) {
       auto ks = attr_ints(n, "kernel_shape", {}), st = attr_ints(n, "strides", {1, 1}), pads = attr_ints(n, "pads", {0, 0, 0, 0}), dl = attr_ints(n, "dilations", {1, 1});
       if (ks.size() != 2 || ks[0] != ks[1] || st.size() != 2 || st[0] != st[1] || pads.size() != 4 || !all_eq(pads, pads[0]) || attr_i(n, "ceil_mode", 0) != 0 || !all_eq(dl, 1))
         throw ModelError(INFUR_E_MODEL_LOAD, "MaxPool '" + n.name + "': only square, symmetric, floor-mode pooling is supported");
+      check_geometry("MaxPool '" + n.name + "'", ks[0], st[0], 1, pads[0]);
       LoweredOp op; op.kind = OpKind::MaxPool; op.name = n.name.empty() ? n.out[0] : n.name;
       op.pool_k = (int)ks[0]; op.pool_s = (int)st[0]; op.pool_p = (int)pads[0];
       op.in = need(n.in[0], n);

@@ -31,6 +31,7 @@ from .colorcode import (  # noqa: F401
     color_code_image,
     color_lut,
     frame_rgba,
+    softmax_confidence,
     blend_over,
 )
 from .upsample import bilinear_tables, upsample_bilinear  # noqa: F401

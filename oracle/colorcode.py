@@ -111,6 +111,20 @@ def color_code_image(hm: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     return k_max, color_code(k_max, c_max)
 
 
+def softmax_confidence(hm: np.ndarray) -> np.ndarray:
+    """Opt-in extension (README.md:76 TODO "softmax"; NOT a reference mode -- the reference feeds raw logits to ColorCode):
+    per-pixel softmax over the K classes in f32, ``p_k = exp(v_k - max) / sum_j exp(v_j - max)``, the sum taken in class-index
+    order.  Feeding the result to ``color_code_image`` gives the first maximum of the logits as the class (every p is > 0, so the
+    strict-``>`` scan from (0, 0.0) always moves) and the winner's probability as confidence."""
+    hm = hm.astype(np.float32, copy=False)
+    m = hm.max(axis=0)
+    e = np.exp((hm - m[None]).astype(np.float32)).astype(np.float32)
+    s = np.zeros_like(m)
+    for k in range(hm.shape[0]):
+        s = (s + e[k]).astype(np.float32)
+    return (e / s[None]).astype(np.float32)
+
+
 def frame_rgba(bgr: np.ndarray) -> np.ndarray:
     """``Color32::from_rgb(c[2], c[1], c[0])`` per pixel (app.rs:132-139) -> ``[H][W][4]`` u8, alpha 255."""
     h, w = bgr.shape[:2]

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_header_symbols_all_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "infur_b200.h")).read()
     declared = set(re.findall(r"\b(infur_b200_[a-z0-9_]+)\s*\(", hdr))
-    declared -= {"infur_b200_config", "infur_b200_out", "infur_b200_slot", "infur_b200_handle", "infur_b200_conv_desc"}
+    declared -= {"infur_b200_config", "infur_b200_out", "infur_b200_slot", "infur_b200_handle", "infur_b200_conv_desc", "infur_b200_result",
+                 "infur_b200_device_out"}
     assert len(declared) >= 30
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
@@ -125,3 +126,24 @@ def test_header_is_plain_c99(lib, tmp_path):
                         "-linfur_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_rust_ffi_matches_header(lib):
+    """rust/infur-b200/src/ffi.rs (the Rust shim cannot be compiled here: no cargo) declares the same functions and the same
+    struct fields, in the same order, as the ctypes binding -- which test_c99 / the GPU tests check against the header itself."""
+    src = open(os.path.join(ROOT, "rust", "infur-b200", "src", "ffi.rs")).read()
+    fns = set(re.findall(r"pub fn (infur_b200_[a-z0-9_]+)\(", src))
+    assert fns and fns <= set(L.SYMBOLS), fns - set(L.SYMBOLS)
+    assert {"infur_b200_create", "infur_b200_scale_control", "infur_b200_model_load", "infur_b200_is_dirty", "infur_b200_advance",
+            "infur_b200_submit", "infur_b200_wait"} <= fns
+    assert int(re.search(r"ABI_VERSION: i32 = (\d+)", src).group(1)) == L.ABI_VERSION == lib.infur_b200_abi_version()
+
+    def rust_fields(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, src, re.S).group(1)
+        return re.findall(r"pub ([a-z0-9_]+):", body)
+
+    for rname, ct in (("Config", L.Config), ("Out", L.Out), ("Result_", L.Result)):
+        assert rust_fields(rname) == [f[0] for f in ct._fields_], rname
+    # status codes
+    for k, v in re.findall(r"pub const (E_[A-Z_]+): i32 = (\d+);", src):
+        assert getattr(L, k) == int(v), k
