@@ -556,13 +556,41 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 h.scale_control(1.0)
                 one = np.ascontiguousarray(base[0])
                 h.advance(one, 1)
-                lat = []
-                for _ in range(7):
-                    t0 = time.perf_counter()
-                    h.advance(one, 1, want=("class_map", "decoded_rgba"))
-                    lat.append(time.perf_counter() - t0)
-                extra["single_frame"] = {"workload": "configs[1]: one 1080p frame, synchronous infur_b200_advance, host buffers (class map + decoded RGBA out)",
-                                         "ms": 1e3 * float(np.median(lat))}
+
+                def latency(frame, into):
+                    lat = []
+                    for _ in range(9):
+                        t0 = time.perf_counter()
+                        h.advance(frame, 1, want=("class_map", "decoded_rgba"), into=into)
+                        lat.append(time.perf_counter() - t0)
+                    return 1e3 * float(np.median(lat))
+
+                # (a) the caller's buffers are ordinary (pageable) memory, re-used across frames like the reference's `out` arguments
+                into_pg = {"class_map": np.empty((H, W), np.uint8), "decoded_rgba": np.empty((H, W, 4), np.uint8)}
+                ms_pageable = latency(one, into_pg)
+                # (b) the caller's buffers come from infur_b200_host_alloc (page-locked): copies are direct DMA
+                pin_in, pin_c, pin_d = P.PinnedArray((H, W, 3)), P.PinnedArray((H, W)), P.PinnedArray((H, W, 4))
+                pin_in.array[...] = one
+                ms_pinned = latency(pin_in.array, {"class_map": pin_c.array, "decoded_rgba": pin_d.array})
+                same = bool((pin_c.array == into_pg["class_map"]).all() and (pin_d.array == into_pg["decoded_rgba"]).all())
+                # device-resident single frame for comparison (no copies)
+                d_c1 = torch.empty((H, W), dtype=torch.uint8, device=dev); d_d1 = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+                st = torch.cuda.ExternalStream(h.compute_stream(), device=dev)
+                for _ in range(3):
+                    h.advance_device(d_sets[0].data_ptr(), 1, W, H, d_c1.data_ptr(), d_d1.data_ptr(), sync=True)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for _ in range(10):
+                    h.advance_device(d_sets[0].data_ptr(), 1, W, H, d_c1.data_ptr(), d_d1.data_ptr())
+                e1.record(st)
+                st.synchronize()
+                dev_ms = e0.elapsed_time(e1) / 10
+                extra["single_frame"] = {"workload": "configs[1]: one 1080p frame, synchronous infur_b200_advance, host buffers in and out (class map + decoded RGBA), "
+                                                     "buffers re-used across calls, CUDA graph replay",
+                                         "ms": ms_pinned, "ms_pageable_buffers": ms_pageable, "ms_device_resident_back_to_back": dev_ms,
+                                         "note": "ms: caller buffers from infur_b200_host_alloc (pinned); identical results: %s" % same,
+                                         "fraction_of_conv_roofline": (FLOPS_NO_AUX[(W, H)] / (pk["bf16_tflops_sustained"] * 1e12 * (2.0 if kind == "int8" else 1.0))) / (ms_pinned * 1e-3)}
+                pin_in.close(); pin_c.close(); pin_d.close()
                 # a new Scale factor: cost before the first result (the reference's slider, gui.rs:278-285)
                 h.scale_control(0.9)
                 t0 = time.perf_counter()

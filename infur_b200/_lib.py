@@ -123,6 +123,8 @@ SYMBOLS = {
     "infur_b200_ring_read": (C.c_int32, [_H, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]),
     "infur_b200_ring_submit": (C.c_int32, [_H, C.c_uint64]),
     "infur_b200_ring_wait": (C.c_int32, [_H, C.c_uint64, C.POINTER(Slot)]),
+    "infur_b200_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "infur_b200_host_free": (None, [C.c_void_p]),
     "infur_b200_ring_release": (C.c_int32, [_H, C.c_uint64]),
     "infur_b200_submit": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]),
     "infur_b200_flush": (C.c_int32, [_H]),

@@ -547,6 +547,15 @@ int32_t infur_b200_advance_batch(infur_b200_handle* h, const uint8_t* bgr, uint3
   });
 }
 
+int32_t infur_b200_host_alloc(size_t bytes, void** out) {
+  if (!out) return INFUR_E_INVALID_ARG;
+  *out = nullptr;
+  const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return fail(nullptr, INFUR_E_RUNTIME, std::string("host_alloc: ") + cudaGetErrorString(e)); }
+  return INFUR_OK;
+}
+void infur_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int32_t infur_b200_advance(infur_b200_handle* h, const uint8_t* bgr, uint32_t w, uint32_t hgt, uint64_t id, infur_b200_out* out) {
   return infur_b200_advance_batch(h, bgr, 1, w, hgt, &id, out);
 }

@@ -67,7 +67,10 @@ static Status make_tmap_f16(CUtensorMap* m, const void* base, int rank, const ui
 }
 
 DeviceModel::~DeviceModel() { if (arena) cudaFree(arena); }
-Plan::~Plan() { for (void* p : owned) cudaFree(p); }
+Plan::~Plan() {
+  for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  for (void* p : owned) cudaFree(p);
+}
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // Stem weights in the order stem_tc_kernel keeps them in smem: [ky][k / 8][cout][k % 8] with k = 4 * (kx + 1) + ci
@@ -422,6 +425,9 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
     }
   }
   H->last_build_tuned++;
+  if (const char* dbg = getenv("INFUR_B200_DEBUG_TUNE"))
+    if (dbg[0] == '1') fprintf(stderr, "[infur_b200] autotune: %dx%d conv %d->%d s%d d%d mode %d res %d cin2 %d, n %d out %dx%d, bucket %d\n", d.kh, d.kw, d.cin, d.cout,
+                               d.stride, d.dil, d.mode, io.residual ? 1 : 0, d.cin2, io.n, io.ow, io.oh, key.bucket);
   const bool allow_pair = !pair_disabled_env();
   cudaEvent_t e0, e1;
   CU_TRY(cudaEventCreate(&e0));
@@ -716,19 +722,71 @@ void fill_pre_args(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, PreArgs&
   pa.scaled_bgr = unit ? nullptr : p.scaled;
 }
 
+// Enqueue the kernels of one step on `s` (plain launches; `launched` counts them).
+static Status issue_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const OutPtrs& o, cudaStream_t s, cudaEvent_t* evs, uint64_t& launched);
+
+static bool graphs_disabled_env() { const char* e = getenv("INFUR_B200_NO_GRAPH"); return e && e[0] == '1'; }
+
+// One step = ~56 kernels.  With cfg.use_cuda_graph the sequence is captured ONCE per (plan, buffer set) into a CUDA graph
+// (the conv kernels' programmatic-dependent-launch edges included) and replayed with a single cudaGraphLaunch: the host cost of
+// a step drops from ~56 launches to one, which is what a single-frame call (configs[1]) waits on.
 Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const OutPtrs& o, cudaStream_t s, float* op_ms = nullptr,
                    cudaEvent_t* evs = nullptr) {
+  (void)op_ms;
   const size_t out_px = (size_t)p.n * p.ow * p.oh;
   if (out_px == 0) return Status();
+  uint64_t launched = 0;
+  if (!H->cfg.use_cuda_graph || evs || !p.has_model || p.graphs_off || o.logits || o.aux_logits || H->cfg.conv_impl != INFUR_CONV_TCGEN05 || graphs_disabled_env()) {
+    Status st = issue_forward(H, p, d_bgr, o, s, evs, launched);
+    H->launches += launched;
+    return st;
+  }
+  const GraphKey key{d_bgr, o.class_map, o.decoded, o.blended, o.frame_rgba, o.logits, o.aux_logits};
+  auto it = p.graphs.find(key);
+  if (it == p.graphs.end()) {
+    if (p.graphs.size() >= 24) {   // a caller that hands in new buffers every step: graphs would never be re-used
+      Status st = issue_forward(H, p, d_bgr, o, s, evs, launched);
+      H->launches += launched;
+      return st;
+    }
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+    Status st;
+    if (e == cudaSuccess) {
+      st = issue_forward(H, p, d_bgr, o, s, nullptr, launched);
+      e = cudaStreamEndCapture(s, &graph);
+      if (st.ok() && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+    }
+    if (!st.ok() || e != cudaSuccess || !exec) {
+      // capture is an optimisation of HOW the same kernels are launched: without it the step runs as plain launches
+      cudaGetLastError();
+      p.graphs_off = true;
+      if (!st.ok()) return st;
+      launched = 0;
+      st = issue_forward(H, p, d_bgr, o, s, evs, launched);
+      H->launches += launched;
+      return st;
+    }
+    it = p.graphs.emplace(key, PlanGraph{exec, launched}).first;
+  }
+  CU_TRY(cudaGraphLaunch(it->second.exec, s));
+  H->launches += it->second.kernels;
+  return Status();
+}
+
+static Status issue_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const OutPtrs& o, cudaStream_t s, cudaEvent_t* evs, uint64_t& launched) {
+  const size_t out_px = (size_t)p.n * p.ow * p.oh;
   const bool unit = p.factor == 1.0f;
   PreArgs pa;
   fill_pre_args(H, p, d_bgr, pa);
   const uint8_t* frame = unit ? d_bgr : p.scaled;
   int ei = 0;
   if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
-  if (pa.stem_in || pa.scaled_bgr) { CU_TRY(launch_pre(pa, s)); H->launches++; }
+  if (pa.stem_in || pa.scaled_bgr) { CU_TRY(launch_pre(pa, s)); launched++; }
   if (!p.has_model) {
-    if (o.frame_rgba) { CU_TRY(launch_frame_rgba(frame, out_px, o.frame_rgba, s)); H->launches++; }
+    if (o.frame_rgba) { CU_TRY(launch_frame_rgba(frame, out_px, o.frame_rgba, s)); launched++; }
     return Status();
   }
   const DeviceModel& M = *H->model;
@@ -748,7 +806,7 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
         CU_TRY(launch_maxpool(reinterpret_cast<const __half*>(ti.ptr), reinterpret_cast<__half*>(to.ptr), p.n, ti.h, ti.w, ti.c, to.h, to.w,
                               op.pool_k, op.pool_s, op.pool_p, s));
     }
-    H->launches++;
+    launched++;
     if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
   }
   PostArgs q;
@@ -766,12 +824,11 @@ Status run_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr, const Ou
     qa.lowres = p.aux_lowres; qa.logits = o.aux_logits; qa.class_map = nullptr; qa.blended = nullptr; qa.frame_rgba = nullptr;
     qa.decoded = p.d_decoded;
     CU_TRY(launch_post(qa, s));
-    H->launches++;
+    launched++;
   }
   CU_TRY(launch_post(q, s));
-  H->launches += (q.top_code && q.k == 21 && !q.softmax) ? 2 : 1;
+  launched += (q.top_code && q.k == 21 && !q.softmax) ? 2 : 1;
   if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
-  (void)op_ms;
   return Status();
 }
 

@@ -85,6 +85,13 @@ struct PlanOp {
   std::string text;
 };
 
+// CUDA graph of one step for one set of buffers (cfg.use_cuda_graph)
+struct GraphKey {
+  const void *in, *cls, *dec, *bl, *fr, *lg, *aux;
+  bool operator<(const GraphKey& o) const { return std::tie(in, cls, dec, bl, fr, lg, aux) < std::tie(o.in, o.cls, o.dec, o.bl, o.fr, o.lg, o.aux); }
+};
+struct PlanGraph { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; };
+
 struct Plan {
   int n = 0, w = 0, h = 0;       // input frames
   int ow = 0, oh = 0;            // after Scale
@@ -112,6 +119,8 @@ struct Plan {
   uint32_t *d_decoded = nullptr, *d_blended = nullptr, *d_frame_rgba = nullptr;
   float* d_logits = nullptr;
   size_t act_bytes = 0;
+  std::map<GraphKey, PlanGraph> graphs;   // captured steps, by buffer set
+  bool graphs_off = false;                // capture failed once: plain launches from then on
   ~Plan();
 };
 

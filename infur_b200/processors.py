@@ -98,6 +98,32 @@ class GUIFrame:
         return [self.buffer.shape[1], self.buffer.shape[0]]
 
 
+class PinnedArray:
+    """A numpy array over page-locked host memory from ``infur_b200_host_alloc`` (freed with the object)."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        self.lib = L.load()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = self.lib.infur_b200_host_alloc(n, C.byref(p))
+        if rc != L.OK:
+            raise InfurError(rc, self.lib.infur_b200_last_error(None).decode())
+        self._p = p
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(n, 1),))[:n].view(dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self.lib.infur_b200_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _check_bgr(img: np.ndarray) -> np.ndarray:
     if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
         raise TypeError("expected an [H][W][3] uint8 BGR image")
@@ -193,8 +219,9 @@ class Handle:
         self._check(self.lib.infur_b200_model_weights_import(self._h, C.c_void_p(dptr), nbytes))
 
     # -- advance (host buffers)
-    def advance_batch(self, frames: np.ndarray, ids=None, want=("frame_rgba", "class_map", "decoded_rgba")) -> list:
-        """``frames``: ``[N][H][W][3]`` u8 BGR.  Returns one dict per frame."""
+    def advance_batch(self, frames: np.ndarray, ids=None, want=("frame_rgba", "class_map", "decoded_rgba"), into=None) -> list:
+        """``frames``: ``[N][H][W][3]`` u8 BGR.  Returns one dict per frame.  ``into``: optional list (one dict per frame) of
+        preallocated output arrays by name (e.g. views of a :class:`PinnedArray`), re-used across calls like the reference's `out`."""
         frames = np.ascontiguousarray(frames)
         if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[3] != 3:
             raise TypeError("expected [N][H][W][3] uint8")
@@ -221,7 +248,9 @@ class Handle:
                 if not ok:
                     d[name] = None
                     continue
-                arr = np.empty(shape, dtype=dt)
+                arr = into[i][name] if into is not None and name in into[i] else np.empty(shape, dtype=dt)
+                if arr.shape != tuple(shape) or arr.dtype != dt or not arr.flags.c_contiguous:
+                    raise ValueError(f"preallocated '{name}' must be a C-contiguous {dt.__name__} array of shape {tuple(shape)}")
                 setattr(outs[i], name, arr.ctypes.data)
                 setattr(outs[i], capname.get(name, name + "_cap"), arr.nbytes)
                 d[name] = arr
@@ -231,8 +260,8 @@ class Handle:
             self._check(self.lib.infur_b200_advance_batch(self._h, frames.ctypes.data, n, w, h, ids_arr, outs))
         return res
 
-    def advance(self, img: np.ndarray, id: int = 0, want=("frame_rgba", "class_map", "decoded_rgba")) -> dict:
-        return self.advance_batch(_check_bgr(img)[None], [id], want)[0]
+    def advance(self, img: np.ndarray, id: int = 0, want=("frame_rgba", "class_map", "decoded_rgba"), into=None) -> dict:
+        return self.advance_batch(_check_bgr(img)[None], [id], want, into=[into] if into is not None else None)[0]
 
     # -- single stages
     def scale_advance(self, img: np.ndarray) -> np.ndarray:
