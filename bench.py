@@ -451,7 +451,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     base = np.stack([synth.synth_frame(W, H, rank * 64 + i) for i in range(B)])
     host_sets = [np.ascontiguousarray(np.roll(base, s, axis=0)) for s in range(nsets)]
     d_sets = [torch.from_numpy(x).to(dev) for x in host_sets]
-    solo = world == 1   # CPU legs, parity, single-frame latency: N = 1 only (for N > 1 the other ranks would idle in a barrier)
+    # CPU legs, parity, single-frame latency: N = 1 only for the default config (for N > 1 the other ranks would idle in a barrier and
+    # make the driver's GPU-busy sample meaningless); configs[4] asks for overlay parity in the 8-GPU run, so --config 4k keeps them
+    solo = world == 1 or args.config == "4k"
 
     def measure_model(kind, factors):
         path, label, dtype = model_fixture(kind)
@@ -541,6 +543,16 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     if len(refs) > 1:
                         rc1, rr1, rf1, rl1 = refs[1]
                         par["vs_fp32_oracle_frame1"] = parity_report(got[1]["class_map"], got[1]["decoded_rgba"], rc1, rr1, rl1)
+                    if args.config == "4k" and len(factors) > 1:   # the other arm of the sweep: one 4K frame at Scale 1.0
+                        h.scale_control(factors[1])
+                        got1 = h.advance_batch(base[:1], want=("class_map", "decoded_rgba", "frame_rgba"))
+                        t0 = time.perf_counter()
+                        qc, qr, qf, ql = cpu_frame_fp32(model, base[0], factors[1])
+                        par["scale_%g_vs_fp32_oracle" % factors[1]] = parity_report(got1[0]["class_map"], got1[0]["decoded_rgba"], qc, qr, ql)
+                        par["scale_%g_frame_rgba_equal" % factors[1]] = bool((got1[0]["frame_rgba"] == qf).all())
+                        par["scale_%g_cpu_s_per_frame" % factors[1]] = time.perf_counter() - t0
+                        del got1, qc, qr, qf, ql
+                        h.scale_control(f0)
                     emu = fcn.pipeline(model, base[0], f0, emulate_fp16=True)
                     par["vs_fp16_emulating_oracle"] = parity_report(got[0]["class_map"], got[0]["decoded_rgba"], emu["class_map"], emu["decoded_rgba"], emu["logits"])
                     par["frames_compared"] = min(2, len(refs))

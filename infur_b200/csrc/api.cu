@@ -1095,11 +1095,20 @@ static int32_t upsample_color_impl(infur_b200_handle* h, const float* lowres, ui
   float* d_low = nullptr; uint8_t* d_frame = nullptr; uint8_t* d_cls = nullptr; uint32_t *d_dec = nullptr, *d_bl = nullptr; float* d_log = nullptr;
   int32_t *dy0 = nullptr, *dy1 = nullptr, *dx0 = nullptr, *dx1 = nullptr; float *dly0 = nullptr, *dly1 = nullptr, *dlx0 = nullptr, *dlx1 = nullptr;
   bool ok = up(d_low, packed.data(), packed.size() * 4);
+  int32_t *d_xs = nullptr, *d_ys = nullptr;
+  auto cell_starts = [](const std::vector<int32_t>& t0, int n_in) {
+    std::vector<int32_t> cs((size_t)n_in + 1, (int32_t)t0.size());
+    size_t x = 0;
+    for (int c = 0; c <= n_in; ++c) { while (x < t0.size() && t0[x] < c) ++x; cs[(size_t)c] = (int32_t)x; }
+    return cs;
+  };
   build_bilinear_table((int)lh, (int)out_h, i0, i1, l0, l1);
+  { const std::vector<int32_t> cs = cell_starts(i0, (int)lh); ok = ok && up(d_ys, cs.data(), cs.size() * 4); }
   int max_lr = 1, max_lc = 1;
   for (int Y0 = 0; Y0 < (int)out_h; Y0 += 32) max_lr = std::max(max_lr, i1[std::min<int>(Y0 + 32, out_h) - 1] - i0[Y0] + 1);
   ok = ok && up(dy0, i0.data(), out_h * 4) && up(dy1, i1.data(), out_h * 4) && up(dly0, l0.data(), out_h * 4) && up(dly1, l1.data(), out_h * 4);
   build_bilinear_table((int)lw, (int)out_w, i0, i1, l0, l1);
+  { const std::vector<int32_t> cs = cell_starts(i0, (int)lw); ok = ok && up(d_xs, cs.data(), cs.size() * 4); }
   for (int X0 = 0; X0 < (int)out_w; X0 += 32) max_lc = std::max(max_lc, i1[std::min<int>(X0 + 32, out_w) - 1] - i0[X0] + 1);
   ok = ok && up(dx0, i0.data(), out_w * 4) && up(dx1, i1.data(), out_w * 4) && up(dlx0, l0.data(), out_w * 4) && up(dlx1, l1.data(), out_w * 4);
   if (frame_bgr) ok = ok && up(d_frame, frame_bgr, px * 3);
@@ -1112,9 +1121,10 @@ static int32_t upsample_color_impl(infur_b200_handle* h, const float* lowres, ui
   q.color_lut = h->d_color_lut; q.frame_bgr = d_frame; q.class_map = d_cls; q.decoded = d_dec; q.blended = d_bl; q.logits = d_log;
   q.max_lr = max_lr; q.max_lc = max_lc;
   q.softmax = h->cfg.confidence == INFUR_CONF_SOFTMAX ? 1 : 0;
+  q.xs = d_xs; q.ys = d_ys;
   if (post_smem_bytes(q) > 200 * 1024) return fail(h, INFUR_E_UNSUPPORTED, "upsample_color: low-res patch per tile does not fit shared memory (upsampling ratio too small / too many classes)");
   cudaError_t e = launch_post(q, h->stream);
-  h->launches++;
+  h->launches += (uint64_t)post_launch_count(q);
   if (e == cudaSuccess) e = cudaMemcpyAsync(decoded_rgba, d_dec, px * 4, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess && class_map) e = cudaMemcpyAsync(class_map, d_cls, px, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess && blended_rgba) e = cudaMemcpyAsync(blended_rgba, d_bl, px * 4, cudaMemcpyDeviceToHost, h->stream);

@@ -484,16 +484,29 @@ static Status dev_upload(Plan& p, T** ptr, const std::vector<T>& v) {
   return Status();
 }
 
+// first output index of every low-res cell: cell c = the run of outputs whose left tap is c (post_cell_kernel)
+static std::vector<int32_t> cell_starts(const std::vector<int32_t>& i0, int n_in) {
+  std::vector<int32_t> s((size_t)n_in + 1, (int32_t)i0.size());
+  size_t x = 0;
+  for (int c = 0; c <= n_in; ++c) {
+    while (x < i0.size() && i0[x] < c) ++x;
+    s[(size_t)c] = (int32_t)x;
+  }
+  return s;
+}
+
 static Status build_bilinear(Plan& p, int lh, int lw) {
   std::vector<int32_t> i0, i1; std::vector<float> l0, l1;
   Status st;
   build_bilinear_table(lh, p.oh, i0, i1, l0, l1);
+  if (!(st = dev_upload(p, &p.cell_ys, cell_starts(i0, lh))).ok()) return st;
   p.max_lr = 1;
   for (int Y0 = 0; Y0 < p.oh; Y0 += 32) p.max_lr = std::max(p.max_lr, i1[std::min(Y0 + 32, p.oh) - 1] - i0[Y0] + 1);
   if (!(st = dev_upload(p, &p.y0, i0)).ok() || !(st = dev_upload(p, &p.y1, i1)).ok() || !(st = dev_upload(p, &p.ly0, l0)).ok() ||
       !(st = dev_upload(p, &p.ly1, l1)).ok())
     return st;
   build_bilinear_table(lw, p.ow, i0, i1, l0, l1);
+  if (!(st = dev_upload(p, &p.cell_xs, cell_starts(i0, lw))).ok()) return st;
   p.max_lc = 1;
   for (int X0 = 0; X0 < p.ow; X0 += 32) p.max_lc = std::max(p.max_lc, i1[std::min(X0 + 32, p.ow) - 1] - i0[X0] + 1);
   if (!(st = dev_upload(p, &p.x0, i0)).ok() || !(st = dev_upload(p, &p.x1, i1)).ok() || !(st = dev_upload(p, &p.lx0, l0)).ok() ||
@@ -817,6 +830,7 @@ static Status issue_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr,
   q.class_map = o.class_map; q.decoded = o.decoded; q.blended = o.blended; q.frame_rgba = o.frame_rgba; q.logits = o.logits;
   q.max_lr = p.max_lr; q.max_lc = p.max_lc; q.top_code = p.top_code;
   q.softmax = H->cfg.confidence == INFUR_CONF_SOFTMAX ? 1 : 0;
+  q.xs = p.cell_xs; q.ys = p.cell_ys;
   if (!q.decoded) q.decoded = p.d_decoded;
   if (o.aux_logits && p.aux_lowres) {
     // debug path: the aux head through the same post kernel first; only its logits are kept
@@ -824,10 +838,10 @@ static Status issue_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr,
     qa.lowres = p.aux_lowres; qa.logits = o.aux_logits; qa.class_map = nullptr; qa.blended = nullptr; qa.frame_rgba = nullptr;
     qa.decoded = p.d_decoded;
     CU_TRY(launch_post(qa, s));
-    launched++;
+    launched += post_launch_count(qa);
   }
   CU_TRY(launch_post(q, s));
-  launched += (q.top_code && q.k == 21 && !q.softmax) ? 2 : 1;
+  launched += post_launch_count(q);
   if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
   return Status();
 }

@@ -107,6 +107,7 @@ struct Plan {
   float *sblx0 = nullptr, *sblx1 = nullptr, *sbly0 = nullptr, *sbly1 = nullptr;
   int32_t *y0 = nullptr, *y1 = nullptr, *x0 = nullptr, *x1 = nullptr;
   float *ly0 = nullptr, *ly1 = nullptr, *lx0 = nullptr, *lx1 = nullptr;
+  int32_t *cell_xs = nullptr, *cell_ys = nullptr;   // first output column / row of every low-res cell (post_cell_kernel)
   __half* stem_in = nullptr;
   uint8_t* scaled = nullptr;     // Scale output when factor != 1
   float* lowres = nullptr;       // [n][lh][lw][ldk]

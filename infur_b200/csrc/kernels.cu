@@ -92,6 +92,38 @@ __global__ void __launch_bounds__(256) pre_unit_vec4_kernel(PreArgs a, int stem_
   dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// Unit-scale path for w % 128 == 0: a warp converts 128 pixels per step.  Lanes 0..23 fetch the 384 input bytes with one 128-bit
+// load each (fully coalesced), the bytes are staged in shared memory, and every lane then emits pixel pairs as 128-bit stores to
+// consecutive addresses (512 contiguous bytes per store instruction) -- both directions move whole 128-byte lines.
+__global__ void __launch_bounds__(128) pre_unit_warp128_kernel(PreArgs a, int stem_pitch, int stem_rows_) {
+  __shared__ __half lut[3 * 256];
+  __shared__ __align__(16) uint8_t stage[4][384];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = a.lut_h[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y = blockIdx.y, img = blockIdx.z;
+  const int chunks = a.w >> 7;
+  const uint8_t* row = a.src + ((size_t)img * a.h + y) * (size_t)a.w * 3;
+  uint4* drow = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(a.stem_in) + ((size_t)img * stem_rows_ + (y + kStemPadTop)) * stem_pitch + kStemPadLeft);
+  for (int ch = blockIdx.x * 4 + warp; ch < chunks; ch += gridDim.x * 4) {
+    if (lane < 24) *reinterpret_cast<uint4*>(&stage[warp][lane * 16]) = __ldg(reinterpret_cast<const uint4*>(row + (size_t)ch * 384) + lane);
+    __syncwarp();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const uint16_t* sp = reinterpret_cast<const uint16_t*>(&stage[warp][hh * 192 + lane * 6]);   // b0 g0 | r0 b1 | g1 r1
+      const uint32_t h0 = sp[0], h1 = sp[1], h2 = sp[2];
+      const uint8_t b0 = (uint8_t)h0, g0 = (uint8_t)(h0 >> 8), r0 = (uint8_t)h1, b1 = (uint8_t)(h1 >> 8), g1 = (uint8_t)h2, r1 = (uint8_t)(h2 >> 8);
+      const uint8_t p0c0 = a.bgr_order ? b0 : r0, p0c2 = a.bgr_order ? r0 : b0, p1c0 = a.bgr_order ? b1 : r1, p1c2 = a.bgr_order ? r1 : b1;
+      const __half zero = __ushort_as_half((unsigned short)0);
+      __half2 o0 = __halves2half2(lut[p0c0], lut[256 + g0]), o1 = __halves2half2(lut[512 + p0c2], zero);
+      __half2 o2 = __halves2half2(lut[p1c0], lut[256 + g1]), o3 = __halves2half2(lut[512 + p1c2], zero);
+      drow[(size_t)ch * 64 + hh * 32 + lane] = make_uint4(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1),
+                                                          *reinterpret_cast<uint32_t*>(&o2), *reinterpret_cast<uint32_t*>(&o3));
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(256) preprocess_f32_kernel(const uint8_t* __restrict__ bgr, int h, int w, const float* __restrict__ lut_f,
                                                               float* __restrict__ out) {
   __shared__ float lut[768];
@@ -487,6 +519,167 @@ __global__ void __launch_bounds__(128, 3) post_strip_kernel(PostArgs a) {
   }
 }
 
+
+// Cell-per-thread variant of K5 for K = 21 (the network path).  A "cell" is the block of output pixels that blend the same four
+// low-res logit vectors (8 x 8 pixels at the network's x8 upsample; 12 wide / tall along the top-left border, 4 along the
+// bottom-right one).  One thread owns one cell:
+//   1. candidate pruning: class k can win somewhere in the cell only if its largest corner value reaches L = max_k min_corner(k)
+//      (class argmax-of-min is >= L everywhere in the cell, every blend is a convex combination of the corners) and is not
+//      clearly negative (the scan starts from (0, 0.0)); the margin 1e-5 * (1 + |.|) is ~50x the rounding error of the three
+//      un-fused f32 operations of a blend.  Typically 1-4 of the 21 classes survive.  Non-finite corners: all classes stay.
+//   2. for each surviving class, in class order: the horizontal blends of the cell's columns once, then per pixel the vertical
+//      blend and ColorCode's strict '>' update -- the very same f32 operations in the same order as the strip / generic kernels
+//      and the oracle, so the same bits; pruned classes are strictly below the winner and cannot change the scan's result.
+// ~35 instructions per pixel instead of ~130.  Only class map + decoded RGBA are written here; frame RGBA / blend are a
+// separate streaming pass (frame_blend_kernel).
+template <int K>
+__global__ void __launch_bounds__(128) post_cell_kernel(PostArgs a) {
+  constexpr int KQ = (K + 3) / 4;
+  const int cells = a.lh * a.lw;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int img = blockIdx.y;
+  if (idx >= cells) return;
+  const int r = idx / a.lw, c = idx - r * a.lw;
+  const int X0 = __ldg(a.xs + c), X1 = __ldg(a.xs + c + 1), Y0 = __ldg(a.ys + r), Y1 = __ldg(a.ys + r + 1);
+  if (X0 >= X1 || Y0 >= Y1) return;
+  const int c1 = __ldg(a.x1 + X0), r1 = __ldg(a.y1 + Y0);
+  const float* p00 = a.lowres + (((size_t)img * a.lh + r) * a.lw + c) * a.ldk;
+  const float* p01 = a.lowres + (((size_t)img * a.lh + r) * a.lw + c1) * a.ldk;
+  const float* p10 = a.lowres + (((size_t)img * a.lh + r1) * a.lw + c) * a.ldk;
+  const float* p11 = a.lowres + (((size_t)img * a.lh + r1) * a.lw + c1) * a.ldk;
+  // ---- 1. candidate classes
+  float mx[KQ * 4];
+  float L = -INFINITY;
+  bool odd = false;
+#pragma unroll
+  for (int q = 0; q < KQ; ++q) {
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(p00) + q), u1 = __ldg(reinterpret_cast<const float4*>(p01) + q);
+    const float4 u2 = __ldg(reinterpret_cast<const float4*>(p10) + q), u3 = __ldg(reinterpret_cast<const float4*>(p11) + q);
+    const float v0[4] = {u0.x, u0.y, u0.z, u0.w}, v1[4] = {u1.x, u1.y, u1.z, u1.w}, v2[4] = {u2.x, u2.y, u2.z, u2.w}, v3[4] = {u3.x, u3.y, u3.z, u3.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 4 * q + j;
+      if (k < K) {
+        const float hi = fmaxf(fmaxf(v0[j], v1[j]), fmaxf(v2[j], v3[j])), lo = fminf(fminf(v0[j], v1[j]), fminf(v2[j], v3[j]));
+        odd |= !(fabsf(v0[j]) <= 3.0e38f) || !(fabsf(v1[j]) <= 3.0e38f) || !(fabsf(v2[j]) <= 3.0e38f) || !(fabsf(v3[j]) <= 3.0e38f);
+        mx[k] = hi;
+        L = fmaxf(L, lo);
+      } else {
+        mx[k] = -INFINITY;
+      }
+    }
+  }
+  uint32_t mask = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float eps = 1e-5f * (1.f + fabsf(L) + fabsf(mx[k]));
+    if (mx[k] >= L - eps && mx[k] >= -eps) mask |= 1u << k;
+  }
+  if (odd) mask = (1u << K) - 1u;
+  const size_t plane = (size_t)a.oh * a.ow;
+  // ---- 2. chunks of 4 rows x 8 columns
+  for (int ya = Y0; ya < Y1; ya += 4) {
+    float wy0[4], wy1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int y = min(ya + i, Y1 - 1); wy0[i] = __ldg(a.ly0 + y); wy1[i] = __ldg(a.ly1 + y); }
+    for (int xa = X0; xa < X1; xa += 8) {
+      float wx0[8], wx1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int x = min(xa + j, X1 - 1); wx0[j] = __ldg(a.lx0 + x); wx1[j] = __ldg(a.lx1 + x); }
+      float cm[4][8];
+      int km[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { cm[i][j] = 0.f; km[i][j] = 0; }
+      for (uint32_t m = mask; m != 0; m &= m - 1) {
+        const int k = __ffs((int)m) - 1;
+        const float a00 = __ldg(p00 + k), a01 = __ldg(p01 + k), a10 = __ldg(p10 + k), a11 = __ldg(p11 + k);
+        float top[8], bot[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          top[j] = __fadd_rn(__fmul_rn(wx0[j], a00), __fmul_rn(wx1[j], a01));
+          bot[j] = __fadd_rn(__fmul_rn(wx0[j], a10), __fmul_rn(wx1[j], a11));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float v = __fadd_rn(__fmul_rn(wy0[i], top[j]), __fmul_rn(wy1[i], bot[j]));
+            const bool gt = v > cm[i][j];
+            km[i][j] = gt ? k : km[i][j];
+            cm[i][j] = gt ? v : cm[i][j];
+          }
+      }
+      // emit: alpha = trunc(sat(c * 255)), colour from the premultiplied table
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int y = ya + i;
+        if (y >= Y1) break;
+        const size_t rowp = (size_t)img * plane + (size_t)y * a.ow;
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+          const int xg = xa + 4 * gq;
+          if (xg >= X1) break;
+          uint32_t col[4];
+          uint32_t cls = 0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int j = 4 * gq + t;
+            const float av = __fmul_rn(cm[i][j], 255.0f);
+            const int alpha = av >= 255.0f ? 255 : (int)av;
+            const int kk = km[i][j];
+            col[t] = __ldg(a.color_lut + (kk >= 20 ? kk - 20 : kk) * 256 + alpha);
+            cls |= (uint32_t)kk << (8 * t);
+          }
+          const size_t gp = rowp + (size_t)xg;
+          if (xg + 4 <= X1 && ((gp & 3) == 0)) {
+            *reinterpret_cast<uint4*>(a.decoded + gp) = make_uint4(col[0], col[1], col[2], col[3]);
+            if (a.class_map) *reinterpret_cast<uint32_t*>(a.class_map + gp) = cls;
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (xg + t < X1) {
+                a.decoded[gp + t] = col[t];
+                if (a.class_map) a.class_map[gp + t] = (uint8_t)(cls >> (8 * t));
+              }
+          }
+        }
+      }
+    }
+  }
+}
+
+// Display buffer (app.rs:132-144) and the optional "over" blend as one streaming pass: 4 pixels per thread.
+__global__ void __launch_bounds__(256) frame_blend_kernel(const uint8_t* __restrict__ bgr, const uint32_t* __restrict__ decoded, size_t npix,
+                                                           uint32_t* __restrict__ frame_rgba, uint32_t* __restrict__ blended) {
+  const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= npix) return;
+  auto one = [&](size_t i, uint32_t fb, uint32_t fg, uint32_t fr) {
+    if (frame_rgba) frame_rgba[i] = fr | (fg << 8) | (fb << 16) | 0xff000000u;
+    if (blended) {
+      const uint32_t col = decoded[i];
+      const uint32_t ia = 255u - (col >> 24);
+      const uint32_t r = min(255u, (col & 0xff) + (fr * ia + 127u) / 255u);
+      const uint32_t g = min(255u, ((col >> 8) & 0xff) + (fg * ia + 127u) / 255u);
+      const uint32_t b = min(255u, ((col >> 16) & 0xff) + (fb * ia + 127u) / 255u);
+      blended[i] = r | (g << 8) | (b << 16) | 0xff000000u;
+    }
+  };
+  if (i4 + 4 <= npix && !blended && (reinterpret_cast<uintptr_t>(bgr + i4 * 3) & 3) == 0) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(bgr + i4 * 3);   // 12 bytes, 4-byte aligned (i4 % 4 == 0)
+    const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    // bytes: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+    const uint32_t o0 = ((w0 >> 16) & 0xff) | (w0 & 0xff00) | ((w0 & 0xff) << 16) | 0xff000000u;
+    const uint32_t o1 = ((w1 >> 8) & 0xff) | ((w1 & 0xff) << 8) | ((w0 >> 24) << 16) | 0xff000000u;
+    const uint32_t o2 = (w2 & 0xff) | ((w1 >> 24) << 8) | (((w1 >> 16) & 0xff) << 16) | 0xff000000u;
+    const uint32_t o3 = (w2 >> 24) | (((w2 >> 16) & 0xff) << 8) | (((w2 >> 8) & 0xff) << 16) | 0xff000000u;
+    *reinterpret_cast<uint4*>(frame_rgba + i4) = make_uint4(o0, o1, o2, o3);
+    return;
+  }
+  for (size_t i = i4; i < npix && i < i4 + 4; ++i) { const uint8_t* f = bgr + i * 3; one(i, f[0], f[1], f[2]); }
+}
+
 __global__ void __launch_bounds__(256) color_code_kernel(const float* __restrict__ hm, int k, size_t npix, const uint32_t* __restrict__ lut,
                                                           uint32_t* __restrict__ rgba, uint8_t* __restrict__ class_map) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -546,7 +739,10 @@ cudaError_t launch_pre(const PreArgs& a, cudaStream_t s) {
   const int pitch = stem_pitch_px(a.ow), rows = stem_rows(a.oh);
   const bool unit = a.xmap == nullptr && a.ymap == nullptr && a.bx0 == nullptr && a.scaled_bgr == nullptr && a.stem_in != nullptr && (a.w % 4) == 0 &&
                     a.oh == a.h && a.ow == a.w;
-  if (unit) {
+  if (unit && (a.w % 128) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 15) == 0) {
+    dim3 grid(((a.w >> 7) + 3) / 4, a.h, a.n);
+    pre_unit_warp128_kernel<<<grid, 128, 0, s>>>(a, pitch, rows);
+  } else if (unit) {
     dim3 grid((a.w / 4 + 255) / 256, a.h, a.n);
     pre_unit_vec4_kernel<<<grid, 256, 0, s>>>(a, pitch, rows);
   } else {
@@ -582,12 +778,29 @@ cudaError_t launch_maxpool3s2_u8(const uint8_t* in, uint8_t* out, int n, int h, 
   return cudaGetLastError();
 }
 
+// which kernel(s) launch_post uses for these arguments
+static bool post_uses_cells(const PostArgs& a) { return a.k == 21 && a.ldk % 4 == 0 && a.ldk >= 24 && a.xs && a.ys && !a.softmax && !a.logits && a.n <= 65535; }
+int post_launch_count(const PostArgs& a) {
+  if (post_uses_cells(a)) return (a.frame_bgr && (a.frame_rgba || a.blended)) ? 2 : 1;
+  if (a.k == 21 && a.ldk % 4 == 0 && a.ldk >= 24) return (a.top_code && !a.softmax) ? 2 : 1;
+  return 1;
+}
+
 size_t post_smem_bytes(const PostArgs& a) {
   return ((size_t)a.max_lr * a.max_lc * post_pad(a.k) + (size_t)a.k * a.max_lr * kPostTile) * sizeof(float);
 }
 
 cudaError_t launch_post(const PostArgs& a, cudaStream_t s) {
   if (a.k == 21 && a.ldk % 4 == 0 && a.ldk >= 24) {   // the 21 VOC classes of fcn-resnet50; other K: generic kernel below
+    if (post_uses_cells(a)) {
+      dim3 cgrid((unsigned)((a.lh * a.lw + 127) / 128), (unsigned)a.n);
+      post_cell_kernel<21><<<cgrid, 128, 0, s>>>(a);
+      if (a.frame_bgr && (a.frame_rgba || a.blended)) {
+        const size_t npix = (size_t)a.n * a.oh * a.ow;
+        frame_blend_kernel<<<(unsigned)((npix / 4 + 256) / 256), 256, 0, s>>>(a.frame_bgr, a.decoded, npix, a.frame_rgba, a.blended);
+      }
+      return cudaGetLastError();
+    }
     dim3 grid((a.ow + 31) / 32, (a.oh + 4 * kPostStripRows - 1) / (4 * kPostStripRows), a.n);
     if (a.softmax) { post_strip_kernel<21, true><<<grid, 128, 0, s>>>(a); return cudaGetLastError(); }
     if (a.top_code) {

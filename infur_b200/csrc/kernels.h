@@ -55,10 +55,14 @@ struct PostArgs {
   uint32_t* frame_rgba;       // may be nullptr
   float* logits;              // [n][k][oh][ow] f32, may be nullptr (debug)
   int max_lr, max_lc;         // largest low-res patch (rows, cols) any 32x32 output tile touches
+  // cell tables of the cell-per-thread kernel (K = 21 path): low-res cell c covers output columns [xs[c], xs[c + 1]) -- the run of
+  // columns whose left tap x0[] is c -- and likewise rows; nullptr: strip kernel
+  const int32_t* xs; const int32_t* ys;
   int softmax;                // INFUR_CONF_SOFTMAX: confidence = softmax probability of the winning class (README.md:76), else the raw logit
   int32_t* top_code;          // scratch [n][lh][lw] (K = 21 path): winning class of a low-res pixel if it wins by a safe margin, else -1; may be nullptr
 };
 cudaError_t launch_post(const PostArgs& a, cudaStream_t s);
+int post_launch_count(const PostArgs& a);   // kernels launch_post enqueues for these arguments
 size_t post_smem_bytes(const PostArgs& a);
 
 // ColorCode::advance alone on a planar [k][h][w] f32 map
