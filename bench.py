@@ -682,6 +682,20 @@ def run_single_host(args):
     host_sets = [np.ascontiguousarray(np.roll(base, s, axis=0)) for s in range(nsets)]
     depth_total = args.ring_depth * N
     sink = np.zeros(2, dtype=np.int64)
+    # the frame source: --producers threads fill a slot's frames in parallel (a decoder pool); 1 = the reference's single "Proc" thread
+    pool = None
+    if args.producers > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=args.producers)
+
+    def fill(view, src):
+        if pool is None:
+            np.copyto(view, src)
+            return
+        parts = np.array_split(np.arange(B), args.producers)
+        futs = [pool.submit(np.copyto, view[p[0]:p[-1] + 1], src[p[0]:p[-1] + 1]) for p in parts if len(p)]   # numpy releases the GIL while copying
+        for f in futs:
+            f.result()
 
     def consume(r):
         sink[0] += int(r["class_map"][0, 0, 0]); sink[1] += int(r["decoded_rgba"][B - 1, -1, -1, 3])
@@ -692,7 +706,7 @@ def run_single_host(args):
             if len(inflight) == depth_total:
                 consume(h.ring_wait(inflight.pop(0)))      # submission order
             t, view = h.ring_acquire(B, W, H)              # ticket t -> GPU (t - 1) % N
-            np.copyto(view, host_sets[i % nsets])
+            fill(view, host_sets[i % nsets])
             h.ring_submit(t)
             inflight.append(t)
         for t in inflight:
@@ -732,11 +746,11 @@ def run_single_host(args):
         "ms_per_step": 1e3 * total_s / steps_done, "steps_timed": steps_done, "timed_seconds": total_s, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dtype, "data": "synthetic", "mode": "single-host",
         "config": {"workload": ("configs[3]: ONE synthetic stream sharded round-robin over the GPUs of one box behind ONE handle (cfg.num_devices = %d), "
-                                "weights ncclBroadcast inside infur_b200_model_load, ONE producer thread; " % N) + workload_name(args) + ", " + label,
+                                "weights ncclBroadcast inside infur_b200_model_load, %d producer thread(s) copying frames into the pinned slots; " % (N, args.producers)) + workload_name(args) + ", " + label,
                    "frames_per_step_per_gpu": B, "width": W, "height": H, "ring_depth": args.ring_depth, "sharding": "ring ticket t -> devices[(t - 1) % N]"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H * 3, "d2h_bytes_per_step": B * ow * oh * 9,
                 "api": "infur_b200_ring_acquire/submit/wait on a multi-device handle; host memcpy into the pinned slot inside the timed region",
-                "host_feed_GBps": fps * (W * H * 3 + ow * oh * 9) / 1e9},
+                "host_feed_GBps": fps * (W * H * 3 + ow * oh * 9) / 1e9, "producer_threads": args.producers},
         "gpu_launches": int(launches), "clocks": clocks, "model_load_s": load_s, "weight_checksums_equal": len(set(sums)) == 1,
         "same_result_on_two_gpus": {"equal": same, "devices": [grp_dev, other_dev]},
         "note": "value == e2e here: the only path through a multi-device handle is the host-buffer ring (no device-resident leg)",
@@ -753,6 +767,7 @@ def main():
                     help="both (default): the fp16 network of BASELINE configs[1..4] as the headline and the QOperator-quantised network as `int8` in the same line")
     ap.add_argument("--config", default="1080p", choices=["1080p", "4k"])
     ap.add_argument("--single-host", action="store_true", help="one process, one handle over --gpus GPUs, one producer thread (configs[3])")
+    ap.add_argument("--producers", type=int, default=1, help="--single-host: threads that copy frames into the pinned slots (1 = one Proc thread)")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--ring-depth", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=3)

@@ -360,6 +360,13 @@ int32_t infur_b200_profile_collect(infur_b200_handle* h, float* ms, int32_t cap,
  * convolutions it autotuned (0 when every layer-shape class was known). */
 int32_t infur_b200_plan_build_stats(const infur_b200_handle* h, float* ms, int32_t* tuned_convs);
 
+/* Autotune decisions as text, so that a host can persist them next to the model file and skip the measurements in the next process
+ * (one line per layer-shape class: "cin cout k stride dilation mode has_res cin2 bucket block_n variant").  export: every decision of
+ * the handle (device 0 of a multi-device handle); import: adds decisions (all devices); unknown / malformed lines are INFUR_E_INVALID_ARG.
+ * Results never depend on these choices (every variant is bit-identical), only plan-build time does. */
+int32_t infur_b200_tune_export(infur_b200_handle* h, char* buf, size_t cap, size_t* required);
+int32_t infur_b200_tune_import(infur_b200_handle* h, const char* text);
+
 /* Parses an .onnx file on the CPU only (no device needed) and writes the fused op list as text;
  * lets the loader be tested without a GPU. */
 int32_t infur_b200_onnx_describe(const char* utf8_path, char* buf, size_t cap, size_t* required);

@@ -17,6 +17,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <cstring>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -120,6 +121,20 @@ class Handle {
     if (rc != INFUR_OK) throw Error(rc, infur_b200_last_error(nullptr));
     compute_aux_ = compute_aux;
   }
+  // Several GPUs of the box behind ONE handle (one owner thread, like the reference's "Proc" thread, main.rs:36-40,105-112):
+  // weights are ncclBroadcast inside model_load, frame id goes to devices[(id - 1) % n], results come back in submission order.
+  explicit Handle(const std::vector<int>& devices, int max_batch = 8, bool compute_aux = false, bool blend = false) {
+    infur_b200_config cfg;
+    infur_b200_default_config(&cfg);
+    if (devices.empty() || devices.size() > INFUR_B200_MAX_DEVICES) throw Error(INFUR_E_INVALID_ARG, "1..8 devices");
+    cfg.device = devices[0]; cfg.num_devices = (int32_t)devices.size();
+    for (size_t i = 0; i < devices.size(); ++i) cfg.devices[i] = devices[i];
+    cfg.max_batch = max_batch; cfg.compute_aux = compute_aux; cfg.blend = blend;
+    const int rc = infur_b200_create(&cfg, &h_);
+    if (rc != INFUR_OK) throw Error(rc, infur_b200_last_error(nullptr));
+    compute_aux_ = compute_aux;
+  }
+  int num_devices() const { return infur_b200_num_devices(h_); }
   bool compute_aux() const { return compute_aux_; }
   ~Handle() { infur_b200_destroy(h_); }
   Handle(const Handle&) = delete;
@@ -296,6 +311,35 @@ class GpuPipeline : public Processor<AppCmd, std::optional<Frame>, std::optional
     }
     if (o.has_decoded) g.decoded_buffer = std::move(dec);
     out = std::move(g);
+  }
+
+  // Streaming use (configs 3-5): submit() copies the frame into the pinned ring slot of GPU (id - 1) % n and returns a ticket;
+  // wait() hands back that frame's GUIFrame (copied out of the library's pinned memory).  Tickets complete in submission order.
+  uint64_t submit(const Frame& f) {
+    uint64_t t = 0;
+    const int rc = infur_b200_submit(h_.get(), f.img.data.data(), f.img.width, f.img.height, f.id, &t);
+    if (rc != INFUR_OK) detail::raise(h_, rc);
+    return t;
+  }
+  void flush() { const int rc = infur_b200_flush(h_.get()); if (rc != INFUR_OK) detail::raise(h_, rc); }
+  GUIFrame wait(uint64_t ticket) {
+    infur_b200_result r{};
+    const int rc = infur_b200_wait(h_.get(), ticket, &r);
+    if (rc != INFUR_OK) detail::raise(h_, rc);
+    GUIFrame g;
+    g.id = r.id;
+    const size_t px = (size_t)r.out_w * r.out_h;
+    g.buffer.size = {r.out_w, r.out_h};
+    if (r.frame_rgba) { g.buffer.pixels.resize(px); std::memcpy(g.buffer.pixels.data(), r.frame_rgba, px * 4); }
+    if (r.has_decoded && r.decoded_rgba) {
+      ColorImage dec;
+      dec.size = {r.out_w, r.out_h};
+      dec.pixels.resize(px);
+      std::memcpy(dec.pixels.data(), r.decoded_rgba, px * 4);
+      g.decoded_buffer = std::move(dec);
+      g.class_map.assign(r.class_map, r.class_map + px);
+    }
+    return g;
   }
 
   Scale scale;

@@ -135,6 +135,8 @@ SYMBOLS = {
     "infur_b200_class_legend": (C.c_int32, [_H, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "infur_b200_profile_step": (C.c_int32, [_H, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "infur_b200_profile_collect": (C.c_int32, [_H, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "infur_b200_tune_export": (C.c_int32, [_H, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "infur_b200_tune_import": (C.c_int32, [_H, C.c_char_p]),
     "infur_b200_plan_build_stats": (C.c_int32, [_H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "infur_b200_compute_stream": (C.c_void_p, [_H]),
     "infur_b200_launch_count": (C.c_uint64, [_H]),

@@ -1292,6 +1292,43 @@ int32_t infur_b200_profile_collect(infur_b200_handle* h, float* ms, int32_t cap,
   if (!h) return INFUR_E_INVALID_ARG;
   return run_on(h, 0, [&](infur_b200_handle* c) { return profile_collect_impl(c, ms, cap, count, steps); });
 }
+int32_t infur_b200_tune_export(infur_b200_handle* h, char* buf, size_t cap, size_t* required) {
+  if (!h) return INFUR_E_INVALID_ARG;
+  std::string text;
+  const int32_t rc = run_on(h, 0, [&](infur_b200_handle* c) -> int32_t {
+    std::ostringstream os;
+    for (auto& kv : c->tune_cache) {
+      const TuneKey& k = kv.first;
+      os << k.cin << ' ' << k.cout << ' ' << k.kh << ' ' << k.stride << ' ' << k.dil << ' ' << k.mode << ' ' << k.has_res << ' ' << k.cin2 << ' ' << k.bucket << ' '
+         << kv.second.block_n << ' ' << kv.second.variant << '\n';
+    }
+    text = os.str();
+    return INFUR_OK;
+  });
+  if (rc != INFUR_OK) return rc;
+  return copy_text(text, buf, cap, required);
+}
+
+int32_t infur_b200_tune_import(infur_b200_handle* h, const char* text) {
+  if (!h || !text) return fail(h, INFUR_E_INVALID_ARG, "tune_import: NULL argument");
+  std::vector<std::pair<TuneKey, TuneChoice>> items;
+  std::istringstream is(text);
+  std::string line;
+  while (std::getline(is, line)) {
+    if (line.find_first_not_of(" \t\r") == std::string::npos) continue;
+    std::istringstream ls(line);
+    TuneKey k; TuneChoice c;
+    if (!(ls >> k.cin >> k.cout >> k.kh >> k.stride >> k.dil >> k.mode >> k.has_res >> k.cin2 >> k.bucket >> c.block_n >> c.variant) ||
+        (c.block_n != 32 && c.block_n != 64 && c.block_n != 128 && c.block_n != 256) || c.variant < 0 || c.variant > 2 || k.cout <= 0 || k.cout % c.block_n != 0)
+      return fail(h, INFUR_E_INVALID_ARG, "tune_import: malformed line '" + line + "'");
+    items.emplace_back(k, c);
+  }
+  return run_all(h, [&](infur_b200_handle* c, int) -> int32_t {
+    for (auto& it : items) c->tune_cache[it.first] = it.second;
+    return INFUR_OK;
+  });
+}
+
 int32_t infur_b200_plan_build_stats(const infur_b200_handle* h, float* ms, int32_t* tuned_convs) {
   if (!h) return INFUR_E_INVALID_ARG;
   float m = 0.f; int t = 0;

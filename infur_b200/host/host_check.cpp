@@ -171,6 +171,22 @@ int main(int argc, char** argv) {
     const Frame src = synthetic_frame(9, 64, 48);
     CHECK(f->buffer.pixels[5].r == src.img.data[5 * 3 + 2] && f->buffer.pixels[5].b == src.img.data[5 * 3] && f->buffer.pixels[5].a == 255);
   });
+  run("stream_submit_wait_in_order", [&] {   // new surface (configs 3-5): per-frame submit / wait, results in submission order
+    GpuPipeline app(h);
+    app.control(AppCmdModel{model_path});
+    app.control(AppCmdScale{1.0f});
+    std::vector<uint64_t> tickets;
+    for (uint64_t id = 1; id <= 5; ++id) tickets.push_back(app.submit(synthetic_frame(id, 96, 64)));
+    for (uint64_t id = 1; id <= 5; ++id) {
+      GUIFrame g = app.wait(tickets[id - 1]);
+      std::optional<GUIFrame> ref;
+      app.advance(synthetic_frame(id, 96, 64), ref);
+      CHECK(g.id == id && g.buffer.size == (std::array<size_t, 2>{96, 64}) && g.decoded_buffer && ref && ref->decoded_buffer);
+      CHECK(std::memcmp(g.decoded_buffer->pixels.data(), ref->decoded_buffer->pixels.data(), 96 * 64 * 4) == 0);
+      CHECK(std::memcmp(g.buffer.pixels.data(), ref->buffer.pixels.data(), 96 * 64 * 4) == 0 && g.class_map == ref->class_map);
+    }
+    app.flush(); app.flush();
+  });
   std::printf("%s (%d failed)\n", g_failed ? "FAILED" : "all reference tests passed", g_failed);
   return g_failed ? 1 : 0;
 }

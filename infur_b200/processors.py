@@ -421,6 +421,16 @@ class Handle:
         self._check(self.lib.infur_b200_plan_build_stats(self._h, C.byref(ms), C.byref(tuned)))
         return ms.value, tuned.value
 
+    def tune_export(self) -> str:
+        need = C.c_size_t()
+        self.lib.infur_b200_tune_export(self._h, None, 0, C.byref(need))
+        buf = C.create_string_buffer(max(need.value, 1))
+        self._check(self.lib.infur_b200_tune_export(self._h, buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
+    def tune_import(self, text: str):
+        self._check(self.lib.infur_b200_tune_import(self._h, text.encode()))
+
     def num_devices(self) -> int:
         return int(self.lib.infur_b200_num_devices(self._h))
 

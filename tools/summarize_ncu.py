@@ -34,7 +34,7 @@ def main():
         h = src[1]
         ix = {n: i for i, n in enumerate(h)}
         stalls = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
-        data = [r for r in src[2:] if len(r) == len(h)]
+        data = [r for r in src[2:] if len(r) == len(h) and r[ix["# Samples"]].strip().isdigit()]   # several kernels: repeated header rows
         tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
         print(f"== hottest SASS lines (warp-state samples, total {tot}; idle warps parked on barriers included)")
         for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]] or 0))[:25]:
