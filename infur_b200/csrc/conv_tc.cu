@@ -953,6 +953,344 @@ conv_halo_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Back-to-back fusion of a bottleneck's tail:  y = relu(W3 . relu(W2 (*) x + b2) + b3 + residual)
+// with W2 a 3x3 / stride 1 convolution over CMID channels (64 or 128) and W3 the 1x1 expansion that follows it.  Run as two
+// kernels, the CMID-channel intermediate makes a round trip through HBM and the 1x1 layer is purely HBM-bound (it streams
+// the residual and the output, 4 x CMID channels each) while the 3x3 layer is operand-load-bound -- fused, the 3x3's MMAs
+// run in the shadow of the 1x1's HBM streams, and the intermediate lives only in shared memory:
+//   GEMM1  acc1[128 px][CMID]  = sum over (64-channel chunk, tap) of A1(TMA, tap-shifted box) . B1          (as conv_tc_kernel)
+//   epi1   acc1 + b2 -> ReLU -> fp16 -> A2 in smem, written in the 128B-swizzled K-major layout TMA would have produced
+//          (the same bits the unfused 3x3 layer stores to HBM)
+//   GEMM2  acc2[128 px][128]   = A2 . B2(n-tile)                        for each 128-channel tile of the 4 x CMID outputs
+//   epi2   acc2 + b3 + residual (TMA-prefetched) -> fp16 -> ReLU -> TMA store                                (as epilogue_tma)
+// K orders equal the unfused kernels', so the result is bit-identical to running the two layers separately.
+// Warps: 0 TMA producer of the GEMM1 ring, 2 (after allocating TMEM) TMA producer of the B2 ring, 1 MMA issuer, 3 epilogue
+// DMA (residual prefetch + stores), 4-11 epilogue (epi1 and epi2 of a tile in turn).  TMEM: acc1 double-buffered at columns
+// [0, 2 CMID), acc2 double-buffered at [2 CMID, 2 CMID + 256).
+template <int CMID>
+struct B2BCfg {
+  static constexpr int kCC = CMID / 64;                         // 64-channel chunks of the intermediate = K blocks of GEMM2
+  static constexpr int kStage1 = kABytes + CMID * kBlockK * 2;  // A1 tile + B1 tile
+  static constexpr int kN2 = 128;
+  static constexpr int kStage2 = kN2 * kBlockK * 2;             // one B2 tile (128 output channels x 64)
+  static constexpr int kS2 = 2;
+  static constexpr int kA2 = kCC * kABytes;
+  static constexpr int kEB = 4;
+  static constexpr int kS1 = (kSmemLimit - 1024 - kBarBytes - kEB * kEpiBufBytes - kA2 - kS2 * kStage2) / kStage1;
+  static constexpr int kSmem = kS1 * kStage1 + kS2 * kStage2 + kA2 + kEB * kEpiBufBytes + 1024 + kBarBytes;
+  static constexpr int kAcc2Col0 = 2 * CMID;
+  static_assert(kS1 >= 3 && kS1 <= kMaxStages, "GEMM1 ring depth");
+};
+
+struct SchedB {   // virtual tiles of the 1x1 stage: (M tile of this CTA, 128-channel N tile), N fastest
+  int first, step, m_tiles, nt2;
+  __device__ __forceinline__ int tile(int v) const { const int m = first + (v / nt2) * step; return m < m_tiles ? m * nt2 + v % nt2 : -1; }
+  __device__ __forceinline__ int count() const { return first < m_tiles ? ((m_tiles - first + step - 1) / step) * nt2 : 0; }
+};
+
+template <int CMID>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_b2b_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
+  using C = B2BCfg<CMID>;
+  constexpr int S1 = C::kS1, S2 = C::kS2, CC = C::kCC, N2 = C::kN2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring2_base = smem_base + S1 * C::kStage1;
+  const uint32_t a2_base = ring2_base + S2 * C::kStage2;
+  const uint32_t epi_base = a2_base + C::kA2;
+  const uint32_t bar_base = epi_base + C::kEB * kEpiBufBytes;
+  auto full1 = [&](int s) { return bar_base + 8u * s; };
+  auto empty1 = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto full2 = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto empty2 = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto tfull1 = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + s); };
+  auto tempty1 = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 6 + s); };
+  auto tfull2 = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 8 + s); };
+  auto tempty2 = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 10 + s); };
+  const uint32_t a2_ready = bar_base + 8u * (2 * kMaxStages + 12);
+  const uint32_t a2_free = bar_base + 8u * (2 * kMaxStages + 13);
+  EpiBars eb;
+  eb.res = bar_base + 8u * (2 * kMaxStages + 14);
+  eb.ready = eb.res + 8u * 4;
+  eb.free_ = eb.ready + 8u * 4;
+  const uint32_t tmem_ptr_addr = eb.free_ + 8u * 4;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nt2 = g.tiles_n;                       // 128-channel tiles of the 1x1 stage
+  const int m_tiles = g.num_tiles / nt2;
+  const int my_first = (int)blockIdx.x, my_step = (int)gridDim.x;
+  const SchedB sched{my_first, my_step, m_tiles, nt2};
+
+  if (warp == 0 && ptx::elect_one()) {
+    for (int v = 0; v < kMaxViews; ++v) ptx::prefetch_tmap(&maps.a[v]);
+    ptx::prefetch_tmap(&maps.b); ptx::prefetch_tmap(&maps.b2); ptx::prefetch_tmap(&maps.c); ptx::prefetch_tmap(&maps.r);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < S1; ++s) { ptx::mbar_init(full1(s), 1); ptx::mbar_init(empty1(s), 1); }
+    for (int s = 0; s < S2; ++s) { ptx::mbar_init(full2(s), 1); ptx::mbar_init(empty2(s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull1(s), 1); ptx::mbar_init(tempty1(s), kEpiWarps);
+      ptx::mbar_init(tfull2(s), 1); ptx::mbar_init(tempty2(s), kEpiWarps);
+    }
+    ptx::mbar_init(a2_ready, kEpiWarps);
+    ptx::mbar_init(a2_free, 1);
+    for (int s = 0; s < 4; ++s) {
+      ptx::mbar_init(eb.res + 8u * s, 1);
+      ptx::mbar_init(eb.ready + 8u * s, kEpiWarps);
+      ptx::mbar_init(eb.free_ + 8u * s, 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_addr, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    // ===================== TMA producer: GEMM1 operands =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m = my_first; m < m_tiles; m += my_step) {
+        const TileCoord tc = decode_tile(g, m * nt2);
+        for (int cc = 0; cc < g.cchunks; ++cc)          // chunk-major K order, as in conv_tc_kernel
+          for (int tap = 0; tap < g.main_taps; ++tap) {
+            ptx::mbar_wait(empty1(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + stage * C::kStage1;
+            ptx::mbar_expect_tx(full1(stage), (uint32_t)C::kStage1);
+            ptx::tma_load_4d(a_dst, &maps.a[g.tap_view[tap]], full1(stage), cc * kBlockK, tc.ox0 + g.tap_dx[tap], tc.oy0 + g.tap_dy[tap], tc.img);
+            ptx::tma_load_2d(a_dst + kABytes, &maps.b, full1(stage), (tap * g.cchunks + cc) * kBlockK, 0);
+            if (++stage == S1) { stage = 0; phase ^= 1u; }
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== TMA producer: weights of the 1x1 stage =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m = my_first; m < m_tiles; m += my_step)
+        for (int j = 0; j < nt2; ++j)
+          for (int k2 = 0; k2 < CC; ++k2) {
+            ptx::mbar_wait(empty2(stage), phase ^ 1u);
+            ptx::mbar_expect_tx(full2(stage), (uint32_t)C::kStage2);
+            ptx::tma_load_2d(ring2_base + stage * C::kStage2, &maps.b2, full2(stage), k2 * kBlockK, j * N2);
+            if (++stage == S2) { stage = 0; phase ^= 1u; }
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc1 = ptx::make_idesc_f16(kBlockM, CMID);
+      constexpr uint32_t idesc2 = ptx::make_idesc_f16(kBlockM, N2);
+      const int num_kb = g.num_kb;
+      const int n_my = sched.count() / nt2;          // M tiles of this CTA
+      // Two work streams share the tensor pipe: GEMM2 of tile t2 (short MMAs that unblock the HBM-bound epilogue) and GEMM1 of
+      // tile t1 in {t2, t2 + 1} (the long K loop).  The issuer never blocks on one while the other could run: it polls the
+      // barriers (try_wait) and issues whatever is ready, GEMM2 first -- so the 3x3's MMAs of the NEXT tile fill the time the
+      // epilogue warps spend streaming this tile's residual and output.
+      int stage1 = 0, stage2 = 0;
+      uint32_t phase1 = 0, phase2 = 0;
+      int t1 = 0, kb = 0;             // GEMM1 cursor
+      int t2 = 0, jn = 0, k2 = 0;     // GEMM2 cursor
+      int v = 0;                      // virtual tile counter of the 1x1 stage (accumulator stage / phase)
+      bool g1_acc_ok = false, g2_ready = false, g2_acc_ok = false;
+      long long t_idle = 0;
+      while (t2 < n_my) {
+        bool progressed = false;
+        // ---- GEMM2(t2, jn, k2)
+        if (t1 > t2) {
+          if (!g2_ready && ptx::mbar_try_wait(a2_ready, (uint32_t)t2 & 1u)) g2_ready = true;
+          if (g2_ready) {
+            const int as2 = v & 1;
+            if (!g2_acc_ok && ptx::mbar_try_wait(tempty2(as2), (((uint32_t)(v >> 1)) & 1u) ^ 1u)) g2_acc_ok = true;
+            if (g2_acc_ok && ptx::mbar_try_wait(full2(stage2), phase2)) {
+              ptx::tc_fence_after();
+              const uint32_t d2 = tmem_base + (uint32_t)(C::kAcc2Col0 + as2 * N2);
+              const uint64_t a_desc = ptx::make_smem_desc(a2_base + k2 * kABytes, 128);
+              const uint64_t b_desc = ptx::make_smem_desc(ring2_base + stage2 * C::kStage2, 128);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) ptx::umma_f16(d2, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc2, (k2 | k) != 0);
+              ptx::umma_commit(empty2(stage2));
+              if (++stage2 == S2) { stage2 = 0; phase2 ^= 1u; }
+              if (++k2 == CC) {
+                k2 = 0;
+                ptx::umma_commit(tfull2(as2));
+                ++v; g2_acc_ok = false;
+                if (++jn == nt2) {
+                  jn = 0;
+                  ptx::umma_commit(a2_free);      // every read of the intermediate has retired: epi1 of the next tile may overwrite it
+                  ++t2; g2_ready = false;
+                }
+              }
+              progressed = true;
+            }
+          }
+        }
+        // ---- GEMM1(t1, kb)
+        if (!progressed && t1 < n_my && t1 <= t2 + 1) {
+          const int as1 = t1 & 1;
+          if (!g1_acc_ok && ptx::mbar_try_wait(tempty1(as1), (((uint32_t)(t1 >> 1)) & 1u) ^ 1u)) g1_acc_ok = true;
+          if (g1_acc_ok && ptx::mbar_try_wait(full1(stage1), phase1)) {
+            ptx::tc_fence_after();
+            const uint32_t d1 = tmem_base + (uint32_t)(as1 * CMID);
+            const uint32_t a_addr = smem_base + stage1 * C::kStage1;
+            const uint64_t a_desc = ptx::make_smem_desc(a_addr, 128);
+            const uint64_t b_desc = ptx::make_smem_desc(a_addr + kABytes, 128);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) ptx::umma_f16(d1, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc1, (kb | k) != 0);
+            ptx::umma_commit(empty1(stage1));
+            if (++stage1 == S1) { stage1 = 0; phase1 ^= 1u; }
+            if (++kb == num_kb) {
+              kb = 0;
+              ptx::umma_commit(tfull1(as1));
+              ++t1; g1_acc_ok = false;
+            }
+            progressed = true;
+          }
+        }
+        if (progressed) t_idle = 0;
+        else {   // a protocol bug must trap, never hang the device
+          if (t_idle == 0) t_idle = clock64();
+          else if (clock64() - t_idle > 4000000000LL) __trap();
+        }
+      }
+    }
+  } else if (warp == kDmaWarp) {
+    if (ptx::elect_one()) epilogue_dma<N2, true, SchedB, 4, kEpiBufBytes, 64>(maps, g, sched, eb, epi_base);
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue warps: epi1 then epi2 of every tile =====================
+    const int ew = warp - kEpiWarp0;
+    const int quad = ew & 3, half = ew >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int it = 0, v = 0, q = 0;
+    for (int m = my_first; m < m_tiles; m += my_step, ++it) {
+      // ---- epi1: acc1 + b2 -> ReLU -> fp16 -> A2 (128B-swizzled K-major: 16-byte group gidx of row r sits at group gidx ^ (r & 7))
+      const int as1 = it & 1;
+      ptx::mbar_wait(tfull1(as1), ((uint32_t)(it >> 1)) & 1u);
+      ptx::tc_fence_after();
+      if (it >= 1) ptx::mbar_wait(a2_free, (uint32_t)(it - 1) & 1u);     // GEMM2 of the previous tile has read A2
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        float4 bias[8];
+        const float4* b4 = reinterpret_cast<const float4*>(g.bias + c * 64 + half * 32);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) bias[jj] = __ldg(b4 + jj);
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32b_x32(lane_base + (uint32_t)(as1 * CMID + c * 64 + half * 32), acc);
+        ptx::tmem_ld_wait();
+        if (c == CC - 1) {   // accumulator stage fully read
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tempty1(as1));
+        }
+        const uint32_t rowp = a2_base + (uint32_t)c * kABytes + (uint32_t)row * 128u;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint32_t addr = rowp + (((uint32_t)(half * 4 + jj) ^ sw) << 4);
+          const float4 bl = bias[2 * jj], bh = bias[2 * jj + 1];
+          float x[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) x[t] = __uint_as_float(acc[8 * jj + t]);
+          ptx::add_f32x2(x[0], x[1], bl.x, bl.y); ptx::add_f32x2(x[2], x[3], bl.z, bl.w);
+          ptx::add_f32x2(x[4], x[5], bh.x, bh.y); ptx::add_f32x2(x[6], x[7], bh.z, bh.w);
+          uint4 o;
+          __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(x[2 * t], x[2 * t + 1]);
+          const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h[t] = __hmax2(h[t], z);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+      }
+      ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a2_ready);
+      // ---- epi2: every 128-channel tile of the 1x1 stage, two 64-channel chunks each (as epilogue_tma with a residual)
+      for (int j = 0; j < nt2; ++j, ++v) {
+        const int as2 = v & 1;
+        ptx::mbar_wait(tfull2(as2), ((uint32_t)(v >> 1)) & 1u);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c, ++q) {
+          const int b = q & 3;
+          const uint32_t use = (uint32_t)(q >> 2);
+          const uint32_t rowp = epi_base + b * kEpiBufBytes + (uint32_t)row * 128u;
+          float4 bias[8];
+          const float4* b4 = reinterpret_cast<const float4*>(g.bias2 + j * N2 + c * 64 + half * 32);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) bias[jj] = __ldg(b4 + jj);
+          uint32_t acc[32];
+          ptx::tmem_ld_32x32b_x32(lane_base + (uint32_t)(C::kAcc2Col0 + as2 * N2 + c * 64 + half * 32), acc);
+          ptx::tmem_ld_wait();
+          if (c == 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty2(as2));
+          }
+          uint4 res[4];
+          ptx::mbar_wait(eb.res + 8u * b, use & 1u);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t addr = rowp + (((uint32_t)(half * 4 + jj) ^ sw) << 4);
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(res[jj].x), "=r"(res[jj].y), "=r"(res[jj].z), "=r"(res[jj].w) : "r"(addr));
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t addr = rowp + (((uint32_t)(half * 4 + jj) ^ sw) << 4);
+            const float4 bl = bias[2 * jj], bh = bias[2 * jj + 1];
+            float x[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) x[t] = __uint_as_float(acc[8 * jj + t]);
+            ptx::add_f32x2(x[0], x[1], bl.x, bl.y); ptx::add_f32x2(x[2], x[3], bl.z, bl.w);
+            ptx::add_f32x2(x[4], x[5], bh.x, bh.y); ptx::add_f32x2(x[6], x[7], bh.z, bh.w);
+            const uint32_t rw[4] = {res[jj].x, res[jj].y, res[jj].z, res[jj].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              x[2 * t] = ptx::add_f32_f16(x[2 * t], (unsigned short)(rw[t] & 0xffffu));
+              x[2 * t + 1] = ptx::add_f32_f16(x[2 * t + 1], (unsigned short)(rw[t] >> 16));
+            }
+            uint4 o;
+            __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(x[2 * t], x[2 * t + 1]);
+            if (g.relu) {
+              const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) h[t] = __hmax2(h[t], z);
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(eb.ready + 8u * b);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 7x7 / stride 2 / pad 3 stem on 3 input channels (ORT Conv of `conv1`, inside session.run predict_onnx.rs:138).
 // Input: padded NHWC4 fp16 (kernels.h).  Output tile = 128 consecutive pixels of one output row.  For filter row
@@ -1134,10 +1472,22 @@ cudaError_t conv_tc_init() {
   opt_in(conv_halo_kernel<128, 0>, kSmemLimit); opt_in(conv_halo_kernel<128, 1>, kSmemLimit);
   opt_in(conv_halo_kernel<256, 0>, kSmemLimit); opt_in(conv_halo_kernel<256, 1>, kSmemLimit);
   opt_in(conv_tc_pair_kernel<0>, kSmemLimit); opt_in(conv_tc_pair_kernel<1>, kSmemLimit); opt_in(conv_tc_pair_kernel<3>, kSmemLimit);
+  opt_in(conv_b2b_kernel<64>, B2BCfg<64>::kSmem); opt_in(conv_b2b_kernel<128>, B2BCfg<128>::kSmem);
   return e;
 }
 
+bool conv_b2b_supported(int cmid) { return cmid == 64 || cmid == 128; }
+
 cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom& g, int num_sms, cudaStream_t stream) {
+  if (g.b2b) {
+    const int m_tiles = g.tiles_n > 0 ? g.num_tiles / g.tiles_n : 0;
+    const int grid = m_tiles < num_sms ? m_tiles : num_sms;
+    if (grid <= 0) return cudaSuccess;
+    if (g.store_mode != 2 || g.mode != 0 || g.main_taps != g.num_taps || g.num_kb != g.main_taps * g.cchunks) return cudaErrorInvalidValue;
+    if (g.b2b_cmid == 64 && g.cchunks == 1) return launch_conv(conv_b2b_kernel<64>, grid, B2BCfg<64>::kSmem, stream, maps, g);
+    if (g.b2b_cmid == 128 && g.cchunks == 2) return launch_conv(conv_b2b_kernel<128>, grid, B2BCfg<128>::kSmem, stream, maps, g);
+    return cudaErrorInvalidValue;
+  }
   if (g.stem) {
     const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
     if (grid <= 0) return cudaSuccess;

@@ -33,6 +33,11 @@ struct ConvTcGeom {
   int32_t stages, epi_bufs;   // smem pipeline depth and epilogue chunk buffers (0 / 2 / 4), see conv_tc_stages
   int32_t pair, num_work;     // 1: conv_tc_pair_kernel (cta_group::2); work items = ceil(M tiles / 2) * tiles_n
   int32_t halo, halo_dil;     // 1: conv_halo_kernel (3x3 / stride 1 / pad = dilation = halo_dil): maps.a[0] has a halo-patch box
+  // 1: conv_b2b_kernel -- a 3x3 / stride 1 convolution (cmid -> cmid, ReLU) fused with the 1x1 convolution that follows it
+  // (cmid -> tiles_n * 128 channels, + residual, ReLU): the cmid-channel intermediate never leaves shared memory.  The fields
+  // above describe the 3x3 (maps.a / maps.b, bias, taps); maps.b2 / bias2 / residual / out / maps.c / maps.r the 1x1.
+  int32_t b2b, b2b_cmid;
+  const float* bias2;
   int32_t stem;               // 1: 7x7/s2 RGB stem through stem_tc_kernel (maps.a[0] = row-group view of the padded NHWC4 input)
   const __half* stem_w;       // stem weights in smem order [7 ky][4 k-cores][64 cout][8], kStemWBytes
   const float* bias;          // [tiles_n * BLOCK_N]
@@ -62,6 +67,7 @@ struct alignas(64) ConvTcMaps {
   CUtensorMap b;             // weights [cout][K]
   CUtensorMap c;             // output (store_mode 1, 2): 4-D NHWC, box 64 channels x tile
   CUtensorMap r;             // residual (store_mode 2), same geometry as c
+  CUtensorMap b2;            // conv_b2b_kernel: weights of the fused 1x1 convolution [cout][cmid], box 64 x 128
 };
 
 // block_n in {32, 64, 128, 256}.  Returns cudaSuccess or the launch error.
@@ -70,5 +76,6 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
 cudaError_t conv_tc_init();
 int conv_tc_stages(int block_n, int epi_bufs, bool i8 = false);
 int conv_tc_pair_stages(int epi_bufs, bool i8 = false);
+bool conv_b2b_supported(int cmid);   // 64 or 128
 
 }  // namespace infur

@@ -464,6 +464,118 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
   return st;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Bottleneck-tail fusion (conv_b2b_kernel): a 3x3 / stride 1 convolution (cmid -> cmid, ReLU) whose only consumer is a 1x1
+// convolution with a residual (cmid -> 4 cmid, + identity, ReLU) becomes ONE launch; the cmid-channel tensor between them never
+// reaches HBM.  Results are bit-identical to the two launches (same K order, same rounding points), so -- like the tile shapes --
+// the choice is made by measurement per layer-shape class and cached.
+static bool b2b_disabled_env() { const char* e = getenv("INFUR_B200_NO_B2B"); return e && e[0] == '1'; }
+static bool b2b_forced_env() { const char* e = getenv("INFUR_B200_B2B"); return e && e[0] == 'f'; }   // INFUR_B200_B2B=force: skip the measurement
+
+static Status setup_b2b(const DevConv& da, const ConvIO& ioa, const DevConv& db, const ConvIO& iob, PlanOp& pf) {
+  Status st = setup_conv_tc(da, ioa, pf, da.cout, kVarPlain);
+  if (!st.ok()) return st;
+  ConvTcGeom& g = pf.geom;
+  const int m_tiles = ioa.n * g.tiles_x * g.tiles_y;
+  g.b2b = 1; g.b2b_cmid = da.cout;
+  g.tiles_n = db.cout / 128;
+  g.num_tiles = m_tiles * g.tiles_n;
+  g.bias2 = iob.bias; g.residual = iob.residual; g.out = iob.y; g.out_f32 = nullptr; g.out_ld = iob.out_ld; g.relu = db.relu ? 1 : 0;
+  g.store_mode = 2; g.epi_bufs = 4; g.pair = 0; g.halo = 0;
+  pf.b2b = true; pf.pair = false; pf.variant = kVarPlain; pf.block_n = da.cout;
+  const int bw = 1 << g.bw_log2, bh = 128 >> g.bw_log2;
+  {
+    const uint64_t dims[2] = {(uint64_t)db.kdim, (uint64_t)db.cout_pad};
+    const uint64_t strides[1] = {(uint64_t)db.kdim * 2};
+    const uint32_t bbox[2] = {64, 128};
+    if (!(st = make_tmap(&pf.maps.b2, iob.wgt, 2, dims, strides, bbox, 128, 2)).ok()) return st;
+  }
+  const uint64_t dims[4] = {(uint64_t)db.cout, (uint64_t)iob.ow, (uint64_t)iob.oh, (uint64_t)iob.n};
+  const uint64_t strides[3] = {(uint64_t)iob.out_ld * 2, (uint64_t)iob.ow * iob.out_ld * 2, (uint64_t)iob.oh * iob.ow * iob.out_ld * 2};
+  const uint32_t cbox[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  if (!(st = make_tmap(&pf.maps.c, iob.y, 4, dims, strides, cbox, 128, 2)).ok()) return st;
+  return make_tmap(&pf.maps.r, iob.residual, 4, dims, strides, cbox, 128, 2);
+}
+
+static Status fuse_b2b_pairs(infur_b200_handle* H, const DeviceModel& M, Plan& p, const std::vector<ConvIO>& ios, const std::vector<int>& last_use) {
+  const LoweredModel& m = M.lm;
+  std::vector<int> uses(m.num_tensors, 0);
+  for (size_t i = 0; i < m.ops.size(); ++i) {
+    if (!M.needed[i]) continue;
+    const LoweredOp& op = m.ops[i];
+    if (op.in >= 0) uses[op.in]++;
+    if (op.kind == OpKind::Conv) { if (op.conv.residual >= 0) uses[op.conv.residual]++; if (op.conv.in2 >= 0) uses[op.conv.in2]++; }
+  }
+  for (auto& hd : m.heads) uses[hd.tensor]++;
+  (void)last_use;
+  for (size_t k = 0; k + 1 < p.ops.size(); ++k) {
+    PlanOp &a = p.ops[k], &b = p.ops[k + 1];
+    if (!a.is_conv || !b.is_conv || a.skip || b.skip) continue;
+    const LoweredOp &opa = m.ops[a.op], &opb = m.ops[b.op];
+    const DevConv &da = M.convs[a.op], &db = M.convs[b.op];
+    const ConvIO &ioa = ios[k], &iob = ios[k + 1];
+    if (!(da.tc_ok && db.tc_ok && !da.stem && da.kh == 3 && da.kw == 3 && da.stride == 1 && da.pad == da.dil && da.relu && da.cin2 == 0 && !da.quant && da.mode == 0 &&
+          da.cin == da.cout && conv_b2b_supported(da.cout) && opa.conv.residual < 0 && !ioa.y_f32))
+      continue;
+    if (!(db.kh == 1 && db.kw == 1 && db.stride == 1 && db.pad == 0 && db.cin == da.cout && db.cin2 == 0 && !db.quant && db.mode == 0 && db.cout % 128 == 0 &&
+          db.cout_pad == db.cout && opb.conv.residual >= 0 && iob.residual && !iob.y_f32 && opb.in == opa.out && uses[opa.out] == 1))
+      continue;
+    PlanOp pf = a;
+    Status st = setup_b2b(da, ioa, db, iob, pf);
+    if (!st.ok()) return st;
+    const double mtiles = (double)ioa.n * ((ioa.ow + 15) / 16) * ((ioa.oh + 7) / 8);
+    const TuneKey key{da.cin, db.cout, 3, 1, da.dil, 100, 1, 0, (int)lround(2.0 * log2(std::max(1.0, mtiles)))};
+    bool fuse = true;
+    if (H->cfg.autotune && !b2b_forced_env()) {
+      auto it = H->tune_cache.find(key);
+      for (int delta = 1; delta <= 2 && it == H->tune_cache.end(); ++delta)
+        for (int sgn = -1; sgn <= 1 && it == H->tune_cache.end(); sgn += 2) { TuneKey k2 = key; k2.bucket += sgn * delta; it = H->tune_cache.find(k2); }
+      if (it != H->tune_cache.end()) fuse = it->second.variant == 1;
+      else {
+        H->last_build_tuned++;
+        cudaEvent_t e0, e1, e2;
+        CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1)); CU_TRY(cudaEventCreate(&e2));
+        float best_f = 1e30f, best_s = 1e30f;
+        cudaError_t e = cudaSuccess;
+        for (int round = 0; round < 3 && e == cudaSuccess; ++round) {
+          e = conv_tc_launch(pf.block_n, pf.maps, pf.geom, H->num_sms, H->stream);   // warm-up
+          cudaEventRecord(e0, H->stream);
+          for (int r = 0; r < 3 && e == cudaSuccess; ++r) e = conv_tc_launch(pf.block_n, pf.maps, pf.geom, H->num_sms, H->stream);
+          cudaEventRecord(e1, H->stream);
+          for (int r = 0; r < 3 && e == cudaSuccess; ++r) {
+            e = conv_tc_launch(a.block_n, a.maps, a.geom, H->num_sms, H->stream);
+            if (e == cudaSuccess) e = conv_tc_launch(b.block_n, b.maps, b.geom, H->num_sms, H->stream);
+          }
+          cudaEventRecord(e2, H->stream);
+          if (e == cudaSuccess) e = cudaEventSynchronize(e2);
+          H->launches += 10;
+          float tf = 0.f, ts = 0.f;
+          if (e == cudaSuccess) { cudaEventElapsedTime(&tf, e0, e1); cudaEventElapsedTime(&ts, e1, e2); best_f = std::min(best_f, tf); best_s = std::min(best_s, ts); }
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        if (e != cudaSuccess) return Status::error(INFUR_E_RUNTIME, std::string("autotune (b2b): ") + cudaGetErrorString(e));
+        fuse = best_f < best_s * 0.98f;
+        H->tune_cache[key] = TuneChoice{da.cout, fuse ? 1 : 0};
+        if (const char* dbg = getenv("INFUR_B200_DEBUG_TUNE"))
+          if (dbg[0] == '1') fprintf(stderr, "[infur_b200] b2b %d -> %d d%d, n %d out %dx%d: fused %.3f ms vs separate %.3f ms -> %s\n", da.cin, db.cout, da.dil, ioa.n,
+                                     ioa.ow, ioa.oh, best_f / 3, best_s / 3, fuse ? "fused" : "separate");
+      }
+    }
+    if (!fuse) continue;
+    const double inter = (double)ioa.n * ioa.oh * ioa.ow * da.cout * 2.0;   // the intermediate: written once and read once when unfused
+    pf.flops = a.flops + b.flops;
+    pf.bytes = a.bytes + b.bytes - 2.0 * inter;
+    pf.text = a.text.substr(0, a.text.find(" | ")) + " ++ " + opb.name + " 1x1 -> " + std::to_string(db.cout) + " +res relu | tcgen05 fused 3x3 -> 1x1 (conv_b2b_kernel, cmid " +
+              std::to_string(da.cout) + ") tiles " + std::to_string(pf.geom.num_tiles / pf.geom.tiles_n) + " | GFLOP " + std::to_string(pf.flops * 1e-9) + " MB " + std::to_string(pf.bytes * 1e-6);
+    b.skip = true;
+    b.text = b.text.substr(0, b.text.find(" | ")) + " | (fused into previous) | GFLOP 0 MB 0";
+    b.flops = 0; b.bytes = 0;
+    p.ops[k] = pf;
+  }
+  return Status();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Plan
 constexpr size_t kMaxPlans = 6;
@@ -626,6 +738,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
     if (op.kind == OpKind::Conv) { release(op.conv.residual); release(op.conv.in2); }
   }
   // ---- ops
+  std::vector<ConvIO> ios;   // parallel to p.ops (default-constructed for pools)
   for (size_t i = 0; i < m.ops.size(); ++i) {
     if (!M->needed[i]) continue;
     const LoweredOp& op = m.ops[i];
@@ -633,6 +746,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
     const TensorInfo& to = p.tensors[op.out];
     PlanOp po;
     po.op = (int)i;
+    ios.emplace_back();
     std::ostringstream os;
     if (op.kind == OpKind::Conv) {
       const DevConv& d = M->convs[i];
@@ -650,6 +764,7 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       }
       if (to.f32) io.y_f32 = reinterpret_cast<float*>(to.ptr); else io.y = reinterpret_cast<__half*>(to.ptr);
       io.out_ld = to.ld;
+      ios.back() = io;
       if (d.tc_ok) { if (!(st = setup_conv_tc(d, io, po, d.block_n)).ok()) return st; }
       if (d.tc_ok && !to.f32 && H->cfg.autotune && H->cfg.conv_impl == INFUR_CONV_TCGEN05) {
         if (!(st = tune_block_n(H, d, io, po)).ok()) return st;
@@ -674,6 +789,9 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
     }
     po.text = os.str();
     p.ops.push_back(po);
+  }
+  if (H->cfg.conv_impl == INFUR_CONV_TCGEN05 && !M->i8 && !m.quant && !b2b_disabled_env()) {
+    if (!(st = fuse_b2b_pairs(H, *M, p, ios, last_use)).ok()) return st;
   }
   // ---- head / post
   const LoweredHead& hd = m.heads[M->out_head];
@@ -806,6 +924,10 @@ static Status issue_forward(infur_b200_handle* H, Plan& p, const uint8_t* d_bgr,
   if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
   for (PlanOp& po : p.ops) {
     const LoweredOp& op = M.lm.ops[po.op];
+    if (po.skip) {   // runs inside the previous op's fused kernel; keep the event list aligned with the op list
+      if (evs) CU_TRY(cudaEventRecord(evs[ei++], s));
+      continue;
+    }
     if (po.is_conv) {
       const DevConv& d = M.convs[po.op];
       if (H->cfg.conv_impl == INFUR_CONV_TCGEN05) CU_TRY(conv_tc_launch(po.block_n, po.maps, po.geom, H->num_sms, s));

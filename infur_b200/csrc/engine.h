@@ -78,6 +78,8 @@ struct PlanOp {
   bool pair = false;           // CTA-pair (cta_group::2) variant
   int variant = 0;             // 0 plain, 1 CTA pair, 2 halo patch (3x3)
   bool is_conv = false;
+  bool skip = false;           // this convolution runs inside the previous op's fused kernel (conv_b2b_kernel)
+  bool b2b = false;            // this op is a fused 3x3 -> 1x1 (+residual) pair
   ConvTcMaps maps;
   ConvTcGeom geom;
   DirectConvArgs direct;       // validation path
