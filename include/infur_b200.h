@@ -58,7 +58,9 @@ enum { INFUR_CONV_TCGEN05 = 0, INFUR_CONV_VALIDATE = 1 /* slow CUDA-core kernel,
        INFUR_CONV_TCGEN05_PAIR = 2 /* conv_test only: force the CTA-pair (cta_group::2) variant of the tcgen05 kernel */,
        INFUR_CONV_TCGEN05_HALO = 3, /* conv_test only: force the halo-patch variant (3x3 / stride 1 convolutions) */
        INFUR_CONV_TCGEN05_I8 = 4, /* conv_test only: the layer as an int8 plan runs it (u8 tensors, tcgen05.mma.kind::i8) */
-       INFUR_CONV_TCGEN05_I8_PAIR = 5 /* conv_test only: the same through the CTA-pair kernel */ };
+       INFUR_CONV_TCGEN05_I8_PAIR = 5 /* conv_test only: the same through the CTA-pair kernel */,
+       INFUR_CONV_TCGEN05_PAIR_DEEP = 6 /* conv_test only: CTA pair with eight epilogue chunk buffers (layers with a residual) */,
+       INFUR_CONV_TCGEN05_I8_PAIR_DEEP = 7 };
 
 typedef struct infur_b200_config {
   uint32_t struct_size;  /* sizeof(infur_b200_config) */

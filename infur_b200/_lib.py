@@ -35,6 +35,8 @@ CONV_TCGEN05_PAIR = 2   # conv_test only
 CONV_TCGEN05_HALO = 3   # conv_test only
 CONV_TCGEN05_I8 = 4     # conv_test only: int8 plan form of a quantised layer
 CONV_TCGEN05_I8_PAIR = 5
+CONV_TCGEN05_PAIR_DEEP = 6   # conv_test only: CTA pair, eight epilogue chunk buffers (needs a residual)
+CONV_TCGEN05_I8_PAIR_DEEP = 7
 LOAD_DEFAULT = 0
 LOAD_SKIP_WEIGHTS = 1
 CONF_RAW = 0

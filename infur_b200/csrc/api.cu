@@ -1319,7 +1319,7 @@ int32_t infur_b200_tune_import(infur_b200_handle* h, const char* text) {
     std::istringstream ls(line);
     TuneKey k; TuneChoice c;
     if (!(ls >> k.cin >> k.cout >> k.kh >> k.stride >> k.dil >> k.mode >> k.has_res >> k.cin2 >> k.bucket >> c.block_n >> c.variant) ||
-        (c.block_n != 32 && c.block_n != 64 && c.block_n != 128 && c.block_n != 256) || c.variant < 0 || c.variant > 2 || k.cout <= 0 || k.cout % c.block_n != 0)
+        (c.block_n != 32 && c.block_n != 64 && c.block_n != 128 && c.block_n != 256) || c.variant < 0 || c.variant > 3 || k.cout <= 0 || k.cout % c.block_n != 0)
       return fail(h, INFUR_E_INVALID_ARG, "tune_import: malformed line '" + line + "'");
     items.emplace_back(k, c);
   }

@@ -303,8 +303,15 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
             float t[4];
             if (MODE == 3) {
               const int4 bi = __ldg(reinterpret_cast<const int4*>(g.bias_i32 + cofs) + j);
-              t[0] = __int2float_rn((int)acc[4 * j + 0] + bi.x); t[1] = __int2float_rn((int)acc[4 * j + 1] + bi.y);
-              t[2] = __int2float_rn((int)acc[4 * j + 2] + bi.z); t[3] = __int2float_rn((int)acc[4 * j + 3] + bi.w);
+              if (g.q_small_acc) {   // |acc + bias| < 2^22 (ConvTcGeom::q_small_acc): f32(x) = as_float(x + bits(1.5 * 2^23)) - 1.5 * 2^23, exactly
+                constexpr int kMagicBits = 0x4B400000;
+                t[0] = __int_as_float((int)acc[4 * j + 0] + bi.x + kMagicBits); t[1] = __int_as_float((int)acc[4 * j + 1] + bi.y + kMagicBits);
+                t[2] = __int_as_float((int)acc[4 * j + 2] + bi.z + kMagicBits); t[3] = __int_as_float((int)acc[4 * j + 3] + bi.w + kMagicBits);
+                ptx::add_f32x2(t[0], t[1], -kRneMagic, -kRneMagic); ptx::add_f32x2(t[2], t[3], -kRneMagic, -kRneMagic);
+              } else {
+                t[0] = __int2float_rn((int)acc[4 * j + 0] + bi.x); t[1] = __int2float_rn((int)acc[4 * j + 1] + bi.y);
+                t[2] = __int2float_rn((int)acc[4 * j + 2] + bi.z); t[3] = __int2float_rn((int)acc[4 * j + 3] + bi.w);
+              }
             } else {
               const float4 bf = __ldg(reinterpret_cast<const float4*>(g.bias + cofs) + j);
               t[0] = __uint_as_float(acc[4 * j + 0]); t[1] = __uint_as_float(acc[4 * j + 1]);
@@ -767,11 +774,13 @@ conv_tc_pair_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_consta
   } else if (warp == kDmaWarp) {
     if (ptx::elect_one()) {
       if (g.store_mode == 1) epilogue_dma<BLOCK_N, false, Sched2, 4, kEpiBufBytes, (MODE >= 2 ? 128 : 64)>(maps, g, sched, eb, epi_base);
+      else if (g.epi_bufs == 8) epilogue_dma<BLOCK_N, true, Sched2, 8, kEpiBufBytes, (MODE >= 2 ? 128 : 64)>(maps, g, sched, eb, epi_base);
       else epilogue_dma<BLOCK_N, true, Sched2, 4, kEpiBufBytes, (MODE >= 2 ? 128 : 64)>(maps, g, sched, eb, epi_base);
     }
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;
     if (g.store_mode == 1) epilogue_tma<BLOCK_N, ACC, false, MODE, Sched2, true, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
+    else if (g.epi_bufs == 8) epilogue_tma<BLOCK_N, ACC, true, MODE, Sched2, true, 8>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
     else epilogue_tma<BLOCK_N, ACC, true, MODE, Sched2, true, 4>(g, sched, tmem_base, tfull_bar(0), tempty_bar(0), eb, epi_base, ew, lane);
   }
 

@@ -56,6 +56,10 @@ struct ConvTcGeom {
   int32_t mode;
   const int32_t* bias_i32;    // mode 3: [tiles_n * BLOCK_N]
   float q_zres, q_zmagic;
+  // mode 3: 1 when |accumulator + bias| < 2^22 for every output channel whatever the u8 input (proven from the weights at load:
+  // 255 * sum|w| + |b| per channel): int -> float is then an integer add of the bit pattern of 1.5 * 2^23 and one float subtract
+  // (both exact) instead of I2F, which issues at a quarter of the f32 rate and paced the HBM-bound +residual layers
+  int32_t q_small_acc;
   int8_t tap_view[kMaxTaps + 3];
   uint8_t tap_cc[kMaxTaps + 3];  // 64-channel chunks of each tap (a fused shortcut tap may differ from the main taps)
   int16_t tap_dx[kMaxTaps + 1];

@@ -90,6 +90,18 @@ static bool halo_disabled_env() { const char* e = getenv("INFUR_B200_NO_HALO"); 
 static bool i8_enabled_env() { const char* e = getenv("INFUR_B200_I8"); return !(e && e[0] == '0'); }   // INFUR_B200_I8=0: keep quantised models on fp16-carried tensors
 static bool pair_disabled_env() { const char* e = getenv("INFUR_B200_NO_CTA_PAIR"); return e && e[0] == '1'; }
 
+// 255 * sum|w| + |b| < 2^22 for every output channel: the s32 accumulator + bias of a u8 x s8 convolution then converts to f32 with
+// the magic-number add (ConvTcGeom::q_small_acc) whatever the input
+static bool small_acc_bound(const float* w, size_t k_per_out, int cout, const float* bias) {
+  if (!w || k_per_out == 0) return false;
+  for (int co = 0; co < cout; ++co) {
+    double s = 0.0;
+    for (size_t j = 0; j < k_per_out; ++j) s += fabs((double)w[(size_t)co * k_per_out + j]);
+    if (255.0 * s + fabs((double)bias[co]) >= 4194304.0) return false;
+  }
+  return true;
+}
+
 static void classify_conv(const ConvOp& c, bool reads_input, bool is_head, DevConv& d) {
   d.cin = c.cin; d.cout = c.cout; d.kh = c.kh; d.kw = c.kw; d.stride = c.stride; d.pad = c.pad; d.dil = c.dil; d.relu = c.relu;
   d.quant = c.quant; d.q_lo = c.q_lo; d.q_hi = c.q_hi; d.q_ra = c.q_ra; d.q_rb = c.q_rb; d.q_lo2 = c.q_lo2; d.q_hi2 = c.q_hi2; d.q_deq = c.deq_scale;
@@ -152,6 +164,7 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
     DevConv& d = dm->convs[i];
     classify_conv(c, m.ops[i].in == m.input_tensor, is_head_tensor[m.ops[i].out] != 0, d);
     if (i8) { d.mode = d.stem ? 2 : 3; d.res_zp = c.res_zp; d.out_zp = c.out_zp; }
+    if (d.mode == 3) d.small_acc = small_acc_bound(c.weight.data(), c.weight.size() / (size_t)std::max(c.cout, 1), c.cout, c.bias.data());
     if (!d.tc_ok && cfg.conv_impl == INFUR_CONV_TCGEN05)
       return Status::error(INFUR_E_MODEL_LOAD, "convolution '" + m.ops[i].name + "' cannot run on the tcgen05 path: " + d.why_not);
     d.w_off = off; off = align_up(off + (size_t)d.cout_pad * d.kdim * 2, 256);
@@ -246,11 +259,11 @@ struct ConvIO {
   const int32_t* bias_i32 = nullptr;   // mode 3
 };
 
-enum { kVarPlain = 0, kVarPair = 1, kVarHalo = 2 };
+enum { kVarPlain = 0, kVarPair = 1, kVarHalo = 2, kVarPairDeep = 3 /* CTA pair with 8 epilogue chunk buffers (layers with a residual) */ };
 static bool halo_ok(const DevConv& d) { return !d.stem && d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad == d.dil && (d.dil == 1 || d.dil == 2 || d.dil == 4) && d.cin2 == 0; }
 
 static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int block_n, int variant = kVarPlain) {
-  const bool pair = variant == kVarPair, halo = variant == kVarHalo;
+  const bool pair = variant == kVarPair || variant == kVarPairDeep, halo = variant == kVarHalo;
   po.block_n = block_n; po.pair = pair; po.variant = variant;
   ConvTcGeom& g = po.geom;
   memset(&g, 0, sizeof(g));
@@ -282,6 +295,12 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
   const int osz = d.mode >= 2 ? 1 : 2;      // output / residual element size
   if ((d.mode >= 2 && halo) || (d.mode == 2 && pair)) return Status::error(INFUR_E_UNSUPPORTED, "int8 plans use the plain, CTA-pair and stem kernels only");
   if (d.mode == 3) g.epi_bufs = g.store_mode == 0 ? 0 : 4;
+  if (variant == kVarPairDeep) {
+    // four stores in flight + four residual chunks prefetched instead of two + two: the +residual 1x1 layers stream 2 x 64 KB per
+    // tile through these buffers, and with two stores in flight the chunk rate is bound by the TMA store's ~2 us read-out latency
+    if (g.store_mode != 2) return Status::error(INFUR_E_UNSUPPORTED, "the deep-epilogue pair variant is for layers with a residual");
+    g.epi_bufs = 8;
+  }
   g.stages = pair ? conv_tc_pair_stages(g.epi_bufs, d.mode == 3) : conv_tc_stages(block_n, g.epi_bufs, d.mode == 3);
   g.pair = pair ? 1 : 0;
   g.halo = halo ? 1 : 0; g.halo_dil = d.dil;
@@ -293,6 +312,7 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
     g.q_lo = d.q_lo; g.q_hi = d.q_hi; g.q_ra = d.q_ra; g.q_rb = d.q_rb; g.q_lo2 = d.q_lo2; g.q_hi2 = d.q_hi2; g.q_deq = d.q_deq;
     g.mode = d.mode ? d.mode : 1;
     g.bias_i32 = io.bias_i32; g.q_zres = (float)d.res_zp; g.q_zmagic = (float)d.out_zp + 12582912.f;
+    g.q_small_acc = d.small_acc ? 1 : 0;
   }
   Status st;
   const uint32_t box[4] = {64, (uint32_t)(d.stem ? 128 : bw), (uint32_t)(d.stem ? 1 : bh), 1};
@@ -403,7 +423,7 @@ static void setup_direct(const DevConv& d, const ConvIO& io, const __half* wv, D
 // stages (more HBM bytes in flight for the memory-bound 1x1 convs), a wider one halves the activation re-reads.
 static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO& io, PlanOp& po) {
   struct Cand { int bn; int var; };
-  static const Cand cands[7] = {{256, kVarPair}, {256, kVarPlain}, {128, kVarPlain}, {64, kVarPlain}, {256, kVarHalo}, {128, kVarHalo}, {64, kVarHalo}};
+  static const Cand cands[8] = {{256, kVarPair}, {256, kVarPlain}, {128, kVarPlain}, {64, kVarPlain}, {256, kVarHalo}, {128, kVarHalo}, {64, kVarHalo}, {256, kVarPairDeep}};
   if (d.stem) return Status();
   // Decisions are kept per layer-shape class: layer parameters + the number of 128-pixel M tiles of the whole batch in
   // half-octave buckets (what decides waves per SM and hence which variant wins).  The 91 positions of the reference's scale
@@ -426,7 +446,7 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
   }
   H->last_build_tuned++;
   if (const char* dbg = getenv("INFUR_B200_DEBUG_TUNE"))
-    if (dbg[0] == '1') fprintf(stderr, "[infur_b200] autotune: %dx%d conv %d->%d s%d d%d mode %d res %d cin2 %d, n %d out %dx%d, bucket %d\n", d.kh, d.kw, d.cin, d.cout,
+    if (dbg[0] == '1' || dbg[0] == '2') fprintf(stderr, "[infur_b200] autotune: %dx%d conv %d->%d s%d d%d mode %d res %d cin2 %d, n %d out %dx%d, bucket %d\n", d.kh, d.kw, d.cin, d.cout,
                                d.stride, d.dil, d.mode, io.residual ? 1 : 0, d.cin2, io.n, io.ow, io.oh, key.bucket);
   const bool allow_pair = !pair_disabled_env();
   cudaEvent_t e0, e1;
@@ -440,6 +460,7 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
   for (int round = 0; round < 3 && st.ok(); ++round) {
     for (const Cand& c : cands) {
       if (c.bn > d.block_n || d.cout_pad % c.bn != 0 || (c.var == kVarPair && !allow_pair) || (c.var == kVarHalo && !allow_halo)) continue;
+      if (c.var == kVarPairDeep && (!allow_pair || !io.residual || d.mode == 2)) continue;
       if (d.mode >= 2 && c.var == kVarHalo) continue;   // int8 plans: plain and CTA-pair kernels
       PlanOp trial;
       if (!(st = setup_conv_tc(d, io, trial, c.bn, c.var)).ok()) break;
@@ -453,6 +474,8 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
       const bool same = c.bn == best.bn && c.var == best.var;
+      if (const char* dbg = getenv("INFUR_B200_DEBUG_TUNE"))
+        if (dbg[0] == '2') fprintf(stderr, "[infur_b200]   round %d: N%d variant %d: %.4f ms\n", round, c.bn, c.var, ms / 3);
       if (ms < best_ms * 0.97f || (same && ms < best_ms)) { best_ms = ms < best_ms ? ms : best_ms; best = c; }
     }
   }
@@ -776,9 +799,9 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
                  (double)d.cout * (d.kh * d.kw * d.cin + d.cin2) * xsz + (io.x2 ? (double)n * io.h2 * io.w2 * d.cin2 * 2 : 0.0);
       os << "conv " << op.name << " [" << n << "x" << ti.h << "x" << ti.w << "x" << d.cin << "] -> [" << to.h << "x" << to.w << "x" << d.cout
          << "] k" << d.kh << " s" << d.stride << " p" << d.pad << " d" << d.dil << (io.residual ? " +res" : "") << (d.cin2 ? " +shortcut1x1" : "") << (d.relu ? " relu" : "");
-      if (d.mode == 3) os << " int8";
+      if (d.mode == 3) os << (d.small_acc ? " int8 (acc < 2^22)" : " int8");
       if (d.tc_ok)
-        os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << po.block_n << (po.variant == kVarPair ? " pair" : (po.variant == kVarHalo ? " halo" : "")) << " tiles "
+        os << " | tcgen05 tile " << (1 << po.geom.bw_log2) << "x" << (128 >> po.geom.bw_log2) << "px x N" << po.block_n << (po.variant == kVarPair ? " pair" : (po.variant == kVarHalo ? " halo" : (po.variant == kVarPairDeep ? " pair deep-epilogue" : ""))) << " tiles "
            << po.geom.num_tiles << " kblocks " << po.geom.num_kb;
       os << " | GFLOP " << po.flops * 1e-9 << " MB " << po.bytes * 1e-6;
     } else {
@@ -989,14 +1012,20 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   const bool f32out = y_f32 != nullptr;
   DevConv d;
   classify_conv(c, c.cin == 3, f32out, d);
-  const bool pair = cd->impl == INFUR_CONV_TCGEN05_PAIR || cd->impl == INFUR_CONV_TCGEN05_I8_PAIR;
+  const bool deep = cd->impl == INFUR_CONV_TCGEN05_PAIR_DEEP || cd->impl == INFUR_CONV_TCGEN05_I8_PAIR_DEEP;
+  const bool pair = cd->impl == INFUR_CONV_TCGEN05_PAIR || cd->impl == INFUR_CONV_TCGEN05_I8_PAIR || deep;
   const bool halo = cd->impl == INFUR_CONV_TCGEN05_HALO;
-  const bool i8 = cd->impl == INFUR_CONV_TCGEN05_I8 || cd->impl == INFUR_CONV_TCGEN05_I8_PAIR;
+  const bool i8 = cd->impl == INFUR_CONV_TCGEN05_I8 || cd->impl == INFUR_CONV_TCGEN05_I8_PAIR || cd->impl == INFUR_CONV_TCGEN05_I8_PAIR_DEEP;
   const bool tc = cd->impl == INFUR_CONV_TCGEN05 || pair || halo || i8;
   if (i8) {
     // int8 plan form of the layer: the RGB stem keeps fp16-carried operands and writes u8 (mode 2), everything else is native int8
     if (!c.quant) return Status::error(INFUR_E_INVALID_ARG, "conv_test: INFUR_CONV_TCGEN05_I8 needs the quantisation parameters (qmul)");
     d.mode = d.stem ? 2 : 3; d.res_zp = cd->q_zres; d.out_zp = cd->q_zout;
+    if (d.mode == 3) {
+      std::vector<float> wf((size_t)c.cout * c.kh * c.kw * c.cin);
+      for (size_t j = 0; j < wf.size(); ++j) wf[j] = __half2float(reinterpret_cast<const __half*>(wgt)[j]);
+      d.small_acc = small_acc_bound(wf.data(), wf.size() / (size_t)c.cout, c.cout, bias);
+    }
   }
   if (c.quant && !tc) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: quantised layers run on the tcgen05 implementations only");
   if (tc && !d.tc_ok) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: shape not supported by the tcgen05 kernel: " + d.why_not);
@@ -1090,7 +1119,8 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
   PlanOp po;
   if (pair && (d.block_n != 256 || d.stem || f32out)) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the CTA-pair variant needs cout % 256 == 0 and an fp16 output");
   if (halo && !halo_ok(d)) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the halo variant needs a 3x3 / stride 1 / pad = dilation convolution");
-  if (tc) { if (!(st = setup_conv_tc(d, io, po, d.block_n, pair ? kVarPair : (halo ? kVarHalo : kVarPlain))).ok()) return st; }
+  if (deep && !residual) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: the deep-epilogue pair variant needs a residual");
+  if (tc) { if (!(st = setup_conv_tc(d, io, po, d.block_n, deep ? kVarPairDeep : (pair ? kVarPair : (halo ? kVarHalo : kVarPlain)))).ok()) return st; }
   else setup_direct(d, io, d_wv, po.direct);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);

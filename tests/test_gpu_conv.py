@@ -90,6 +90,9 @@ def test_conv_pair_bit_identical_to_single_cta(handle, case):
     y2 = handle.conv_test(x, wt, b, r, stride, pad, dil, relu, impl=L.CONV_TCGEN05_PAIR)
     assert (y1.view(np.uint16) == y2.view(np.uint16)).all()
     assert (np.abs(y2.astype(np.float32) - ref) <= 2e-3 + 4e-3 * np.abs(ref)).all()
+    if res:   # the deep-epilogue pair variant (eight chunk buffers: four stores + four residual chunks in flight)
+        y3 = handle.conv_test(x, wt, b, r, stride, pad, dil, relu, impl=L.CONV_TCGEN05_PAIR_DEEP)
+        assert (y1.view(np.uint16) == y3.view(np.uint16)).all()
 
 
 HALO_CASES = [

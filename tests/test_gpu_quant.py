@@ -53,6 +53,8 @@ I8CASES = [c[:10] + (L.CONV_TCGEN05_I8, c[11]) for c in QCASES if c[10] == L.CON
     (1, 30, 40, 512, 256, 1, 1, 0, 1, False, L.CONV_TCGEN05_I8_PAIR, False),
     (1, 33, 47, 256, 256, 3, 1, 2, 2, False, L.CONV_TCGEN05_I8_PAIR, False),
     (2, 31, 45, 512, 512, 3, 1, 4, 4, False, L.CONV_TCGEN05_I8_PAIR, False),
+    (1, 30, 40, 256, 512, 1, 1, 0, 1, True, L.CONV_TCGEN05_I8_PAIR_DEEP, False),    # eight epilogue chunk buffers (round 2)
+    (3, 17, 23, 64, 256, 1, 1, 0, 1, True, L.CONV_TCGEN05_I8_PAIR_DEEP, False),     # small K: |acc| < 2^22, the I2F-free conversion
 ]
 
 
@@ -64,7 +66,7 @@ def test_qlinear_conv_native_int8_bit_exact(handle, case):
 def _run_qcase(handle, case, x_zp):
     n, h, w, cin, cout, k, stride, pad, dil, res, impl, f32 = case
     rng = np.random.default_rng(abs(hash(case[:10])) % 2**31)
-    i8 = impl in (L.CONV_TCGEN05_I8, L.CONV_TCGEN05_I8_PAIR)
+    i8 = impl in (L.CONV_TCGEN05_I8, L.CONV_TCGEN05_I8_PAIR, L.CONV_TCGEN05_I8_PAIR_DEEP)
     y_zp, r_zp, c_zp = 128 if (res or f32) else 0, 37 if i8 else 0, 0
     xq = rng.integers(0, 256, size=(n, cin, h, w), dtype=np.uint8)
     wq = rng.integers(-127, 128, size=(cout, cin, k, k), dtype=np.int8)
