@@ -1425,6 +1425,283 @@ stem_tc_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Stem + max-pool in one kernel (ORT Conv + Relu + MaxPool of the network's first three nodes).  Run separately the stem writes
+// 531 MB per 8 x 1080p frames (it is HBM-write-bound) only for the pool to read them back; fused, the convolution's output never
+// leaves the SM.  A CTA walks DOWN a column strip: per convolution row the same 14 Toeplitz MMAs as stem_tc_kernel (one TMA box of
+// 7 input rows, weights resident in smem) fill a TMEM stage; the epilogue warps turn the row into fp16 (+ bias, ReLU), exchange
+// it through shared memory to take the horizontal 3-max, and combine rows vertically in registers -- pooled row p is
+// max(H[2p-1], H[2p], H[2p+1]) and H[2p+1] is carried into row p+1, so every convolution row is computed once.
+// Strip geometry: TMA boxes start on 16-input-pixel (= 8 convolution pixel) boundaries, so a strip's 128 convolution columns start at
+// c0 = 120 t - 8 and yield the 60 pooled columns q = 60 t + u, u < 60, from local columns 2u + 7 .. 2u + 9.  Columns / rows outside the
+// convolution's output count as 0: the pool pads with -inf, and every real value is >= 0 after the ReLU, so 0 never wins wrongly.
+// fp16 values are maxed exactly as maxpool3s2_kernel does: same bits as the two separate kernels.
+constexpr int kSpStrip = 60;
+constexpr int kSpXchBytes = kBlockM * 128;          // one convolution row: 128 pixels x 64 channels fp16
+constexpr int kSpSmemBytes = kStemStages * kStemStageBytes + 2 * kSpXchBytes + kStemWBytes + 1024 + kBarBytes;
+
+template <int MODE>   // 0: fp16 model; 2: the stem of an int8 plan (fp16-carried integer operands, requantised u8 output, pooled as bytes)
+__global__ void __launch_bounds__(kThreads, 1)
+stem_pool_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__ ConvTcGeom g) {
+  constexpr int BLOCK_N = 64;
+  constexpr int ACC = 4;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t xch_base = smem_base + kStemStages * kStemStageBytes;
+  const uint32_t w_base = xch_base + 2 * kSpXchBytes;
+  const uint32_t bar_base = w_base + kStemWBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + kMaxAcc + s); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kMaxStages + 2 * kMaxAcc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && ptx::elect_one()) ptx::prefetch_tmap(&maps.a[0]);
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < kStemStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < ACC; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), kEpiWarps); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_addr, ACC * BLOCK_N);
+    ptx::tmem_relinquish();
+  }
+  {  // weights: global (already in smem order) -> smem, once per CTA
+    const uint4* src = reinterpret_cast<const uint4*>(g.stem_w);
+    for (int i = threadIdx.x; i < kStemWBytes / 16; i += kThreads) {
+      const uint4 v = __ldg(src + i);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_base + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    ptx::fence_proxy_async_smem();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  // unit -> (image, chunk of pooled rows, strip of pooled columns); strips fastest: neighbours share input rows in L2
+  auto unit_geom = [&](int unit, int& img, int& pr0, int& pr1, int& strip) {
+    strip = unit % g.sp_strips;
+    const int rest = unit / g.sp_strips;
+    const int chunk = rest % g.sp_chunks;
+    img = rest / g.sp_chunks;
+    pr0 = chunk * g.sp_rc;
+    pr1 = min(pr0 + g.sp_rc, g.sp_oh);
+  };
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < g.num_tiles; unit += gridDim.x) {
+        int img, pr0, pr1, strip;
+        unit_geom(unit, img, pr0, pr1, strip);
+        for (int r = 2 * pr0 - 1; r <= 2 * pr1 - 1; ++r) {          // convolution rows of this unit, top to bottom
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_expect_tx(full_bar(stage), (uint32_t)kStemTxBytes);
+          // column c0 = 120 strip - 8 starts at input pixel 2 c0 = 16-pixel group 15 strip - 1; row r reads input rows 2r .. 2r + 6
+          // of the padded buffer; groups / rows outside it are zero-filled by TMA and their outputs masked in the epilogue
+          ptx::tma_load_4d(smem_base + stage * kStemStageBytes, &maps.a[0], full_bar(stage), 0, 15 * strip - 1, 2 * r, img);
+          if (++stage == kStemStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < g.num_tiles; unit += gridDim.x) {
+        int img, pr0, pr1, strip;
+        unit_geom(unit, img, pr0, pr1, strip);
+        for (int r = 2 * pr0 - 1; r <= 2 * pr1 - 1; ++r, ++it) {
+          const int as = it % ACC;
+          ptx::mbar_wait(tempty_bar(as), (((uint32_t)(it / ACC)) & 1u) ^ 1u);
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+          const uint32_t a_addr = smem_base + stage * kStemStageBytes;
+#pragma unroll
+          for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t a_desc = ptx::make_smem_desc_noswz(a_addr + ky * kStemRowBytes + kk * 32, 16, 128);
+              const uint64_t b_desc = ptx::make_smem_desc_noswz(w_base + ky * 4096 + kk * 2048, 1024, 128);
+              ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, (ky | kk) != 0);
+            }
+          }
+          ptx::umma_commit(empty_bar(stage));
+          ptx::umma_commit(tfull_bar(as));
+          if (++stage == kStemStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    const int ew = warp - kEpiWarp0;
+    const int quad = ew & 3, half = ew >> 2;
+    const int m = quad * 32 + lane;                       // convolution column of this thread inside the strip (TMEM lane)
+    const uint32_t msw = (uint32_t)(m & 7);
+    const int tid2 = ew * 32 + lane;                      // reader role: pooled column u, 16-channel group cg
+    const int u = tid2 >> 2, cg = tid2 & 3;
+    float4 bias[8];
+    {
+      const float4* b4 = reinterpret_cast<const float4*>(g.bias + half * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bias[j] = __ldg(b4 + j);
+    }
+    float4 qm[8];
+    if (MODE == 2) {
+      const float4* m4 = reinterpret_cast<const float4*>(g.qmul + half * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) qm[j] = __ldg(m4 + j);
+    }
+    const __half2 z2 = __float2half2_rn(0.f);
+    int it = 0;
+    for (int unit = blockIdx.x; unit < g.num_tiles; unit += gridDim.x) {
+      int img, pr0, pr1, strip;
+      unit_geom(unit, img, pr0, pr1, strip);
+      const int c = 120 * strip - 8 + m;                  // global convolution column
+      const bool col_ok = c >= 0 && c < g.ow;
+      const int q = kSpStrip * strip + u;                 // global pooled column of the reader role
+      const bool q_ok = u < kSpStrip && q < g.sp_ow;
+      __half2 acc_out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc_out[j] = z2;
+      uint4 acc8 = make_uint4(0u, 0u, 0u, 0u);
+      for (int r = 2 * pr0 - 1; r <= 2 * pr1 - 1; ++r, ++it) {
+        const int as = it % ACC;
+        ptx::mbar_wait(tfull_bar(as), ((uint32_t)(it / ACC)) & 1u);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + half * 32), v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        // ---- this thread's 32 channels of convolution pixel (r, c): + bias, fp16 + ReLU (or requantised u8); 0 outside the
+        // convolution's output
+        const bool ok = col_ok && r >= 0 && r < g.oh;
+        if (MODE == 0) {
+          const uint32_t xb = xch_base + (uint32_t)(it & 1) * kSpXchBytes + (uint32_t)m * 128u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 bl = bias[2 * j], bh = bias[2 * j + 1];
+            float x[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) x[t] = __uint_as_float(v[8 * j + t]);
+            ptx::add_f32x2(x[0], x[1], bl.x, bl.y); ptx::add_f32x2(x[2], x[3], bl.z, bl.w);
+            ptx::add_f32x2(x[4], x[5], bh.x, bh.y); ptx::add_f32x2(x[6], x[7], bh.z, bh.w);
+            uint4 o;
+            __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h[t] = ok ? __hmax2(__floats2half2_rn(x[2 * t], x[2 * t + 1]), z2) : z2;
+            const uint32_t addr = xb + (((uint32_t)(half * 4 + j) ^ msw) << 4);      // 16-byte groups XOR-swizzled by the row: conflict-free both ways
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+        } else {
+          // QLinearConv requantisation exactly as epilogue_tma's u8 path: r = clamp(rne((acc + b) * m), lo, hi), byte = r + zero point
+          const uint32_t xb = xch_base + (uint32_t)(it & 1) * kSpXchBytes + (uint32_t)m * 64u;
+          const float lo_out = g.relu ? fmaxf(g.q_lo, 0.f) : g.q_lo, hi1 = g.q_hi;
+          const uint32_t zout = (uint32_t)(int)(g.q_zmagic - kRneMagic);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {            // 16 channels -> one 16-byte group
+            uint32_t ow[4];
+#pragma unroll
+            for (int wq = 0; wq < 4; ++wq) {
+              const int c4 = 4 * j + wq;           // float4 index of these 4 channels
+              const float4 bf = bias[c4], mq = qm[c4];
+              float t0 = __uint_as_float(v[4 * c4 + 0]), t1 = __uint_as_float(v[4 * c4 + 1]), t2 = __uint_as_float(v[4 * c4 + 2]), t3 = __uint_as_float(v[4 * c4 + 3]);
+              ptx::add_f32x2(t0, t1, bf.x, bf.y); ptx::add_f32x2(t2, t3, bf.z, bf.w);
+              ptx::mul_f32x2(t0, t1, mq.x, mq.y); ptx::mul_f32x2(t2, t3, mq.z, mq.w);
+              t0 = fminf(fmaxf(t0, lo_out), hi1); t1 = fminf(fmaxf(t1, lo_out), hi1); t2 = fminf(fmaxf(t2, lo_out), hi1); t3 = fminf(fmaxf(t3, lo_out), hi1);
+              ptx::add_f32x2(t0, t1, kRneMagic, kRneMagic); ptx::add_f32x2(t2, t3, kRneMagic, kRneMagic);
+              const uint32_t b0 = __float_as_uint(t0) + zout, b1 = __float_as_uint(t1) + zout, b2 = __float_as_uint(t2) + zout, b3 = __float_as_uint(t3) + zout;
+              ow[wq] = ok ? __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410) : 0u;
+            }
+            const uint32_t addr = xb + (((uint32_t)(half * 2 + j) ^ (uint32_t)((m >> 1) & 3)) << 4);   // 64-byte rows: swizzle by the 128-byte line
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
+          }
+        }
+        ptx::named_bar_sync(1, kEpiWarps * 32);            // the whole row is in the exchange buffer (double-buffered: one barrier per row)
+        // ---- reader role: horizontal 3-max for pooled column u, channels [16 cg, 16 cg + 16)
+        if (MODE == 0) {
+          __half2 hmx[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hmx[j] = z2;
+          if (q_ok) {
+            const uint32_t rb = xch_base + (uint32_t)(it & 1) * kSpXchBytes;
+#pragma unroll
+            for (int dm = 0; dm < 3; ++dm) {
+              const int mm = 2 * u + 7 + dm;
+              const uint32_t rowp = rb + (uint32_t)mm * 128u;
+              const uint32_t sw = (uint32_t)(mm & 7);
+#pragma unroll
+              for (int gq = 0; gq < 2; ++gq) {
+                uint4 w4;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w4.x), "=r"(w4.y), "=r"(w4.z), "=r"(w4.w) : "r"(rowp + (((uint32_t)(2 * cg + gq) ^ sw) << 4)));
+                const __half2* hv = reinterpret_cast<const __half2*>(&w4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) hmx[4 * gq + t] = __hmax2(hmx[4 * gq + t], hv[t]);
+              }
+            }
+          }
+          // ---- vertical: pooled row p = max(H[2p - 1], H[2p], H[2p + 1]); H[2p + 1] is carried into row p + 1
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc_out[j] = __hmax2(acc_out[j], hmx[j]);
+          if (r & 1) {
+            const int p = (r - 1) >> 1;
+            if (r > 2 * pr0 - 1 && q_ok && p < g.sp_oh) {
+              uint4* dst = reinterpret_cast<uint4*>(g.out + ((((size_t)img * g.sp_oh + p) * g.sp_ow + q) * 64 + cg * 16));
+              uint4 o0, o1;
+              __half2* h0 = reinterpret_cast<__half2*>(&o0);
+              __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) { h0[t] = acc_out[t]; h1[t] = acc_out[4 + t]; }
+              dst[0] = o0; dst[1] = o1;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc_out[j] = hmx[j];
+          }
+        } else {
+          uint4 hm8 = make_uint4(0u, 0u, 0u, 0u);              // 0 is the identity of max on u8
+          if (q_ok) {
+            const uint32_t rb = xch_base + (uint32_t)(it & 1) * kSpXchBytes;
+#pragma unroll
+            for (int dm = 0; dm < 3; ++dm) {
+              const int mm = 2 * u + 7 + dm;
+              uint4 w4;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w4.x), "=r"(w4.y), "=r"(w4.z), "=r"(w4.w)
+                           : "r"(rb + (uint32_t)mm * 64u + (((uint32_t)cg ^ (uint32_t)((mm >> 1) & 3)) << 4)));
+              hm8 = make_uint4(__vmaxu4(hm8.x, w4.x), __vmaxu4(hm8.y, w4.y), __vmaxu4(hm8.z, w4.z), __vmaxu4(hm8.w, w4.w));
+            }
+          }
+          acc8 = make_uint4(__vmaxu4(acc8.x, hm8.x), __vmaxu4(acc8.y, hm8.y), __vmaxu4(acc8.z, hm8.z), __vmaxu4(acc8.w, hm8.w));
+          if (r & 1) {
+            const int p = (r - 1) >> 1;
+            if (r > 2 * pr0 - 1 && q_ok && p < g.sp_oh)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g.out) + ((((size_t)img * g.sp_oh + p) * g.sp_ow + q) * 64 + cg * 16)) = acc8;
+            acc8 = hm8;
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, ACC * BLOCK_N);
+  }
+}
+
 // Launch with programmatic stream serialization: the kernel may begin (prologue only, see grid_dep_wait) while the
 // previous kernel of the stream drains.  INFUR_B200_NO_PDL=1 turns it off.
 bool pdl_enabled() {
@@ -1482,6 +1759,7 @@ cudaError_t conv_tc_init() {
   opt_in(conv_halo_kernel<256, 0>, kSmemLimit); opt_in(conv_halo_kernel<256, 1>, kSmemLimit);
   opt_in(conv_tc_pair_kernel<0>, kSmemLimit); opt_in(conv_tc_pair_kernel<1>, kSmemLimit); opt_in(conv_tc_pair_kernel<3>, kSmemLimit);
   opt_in(conv_b2b_kernel<64>, B2BCfg<64>::kSmem); opt_in(conv_b2b_kernel<128>, B2BCfg<128>::kSmem);
+  opt_in(stem_pool_kernel<0>, kSpSmemBytes); opt_in(stem_pool_kernel<2>, kSpSmemBytes);
   return e;
 }
 
@@ -1496,6 +1774,13 @@ cudaError_t conv_tc_launch(int block_n, const ConvTcMaps& maps, const ConvTcGeom
     if (g.b2b_cmid == 64 && g.cchunks == 1) return launch_conv(conv_b2b_kernel<64>, grid, B2BCfg<64>::kSmem, stream, maps, g);
     if (g.b2b_cmid == 128 && g.cchunks == 2) return launch_conv(conv_b2b_kernel<128>, grid, B2BCfg<128>::kSmem, stream, maps, g);
     return cudaErrorInvalidValue;
+  }
+  if (g.stem && g.sp_fused) {
+    const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;
+    if (grid <= 0) return cudaSuccess;
+    if (block_n != 64 || (g.mode != 0 && g.mode != 2) || g.sp_rc < 1 || g.sp_strips < 1 || g.sp_chunks < 1) return cudaErrorInvalidValue;
+    if (g.mode == 2) return launch_conv(stem_pool_kernel<2>, grid, kSpSmemBytes, stream, maps, g);
+    return launch_conv(stem_pool_kernel<0>, grid, kSpSmemBytes, stream, maps, g);
   }
   if (g.stem) {
     const int grid = g.num_tiles < num_sms ? g.num_tiles : num_sms;

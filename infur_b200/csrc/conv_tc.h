@@ -38,6 +38,9 @@ struct ConvTcGeom {
   // above describe the 3x3 (maps.a / maps.b, bias, taps); maps.b2 / bias2 / residual / out / maps.c / maps.r the 1x1.
   int32_t b2b, b2b_cmid;
   const float* bias2;
+  // 1: stem_pool_kernel -- the 7x7/s2 stem fused with the 3x3/s2/p1 max-pool that follows it: `out` is the POOLED tensor
+  // [n][sp_oh][sp_ow][64]; oh / ow stay the convolution's output size.  Work unit = (image, sp_rc pooled rows, 60 pooled columns).
+  int32_t sp_fused, sp_oh, sp_ow, sp_rc, sp_chunks, sp_strips;
   int32_t stem;               // 1: 7x7/s2 RGB stem through stem_tc_kernel (maps.a[0] = row-group view of the padded NHWC4 input)
   const __half* stem_w;       // stem weights in smem order [7 ky][4 k-cores][64 cout][8], kStemWBytes
   const float* bias;          // [tiles_n * BLOCK_N]

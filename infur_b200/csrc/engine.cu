@@ -600,6 +600,103 @@ static Status fuse_b2b_pairs(infur_b200_handle* H, const DeviceModel& M, Plan& p
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stem + max-pool fusion (stem_pool_kernel): the 7x7/s2 stem followed by the 3x3/s2/p1 pool as one launch; the stem's output
+// (531 MB per 8 x 1080p frames) never reaches HBM.  Same bits as the two kernels; chosen by measurement like the other variants.
+static bool stem_pool_disabled_env() { const char* e = getenv("INFUR_B200_NO_STEM_POOL"); return e && e[0] == '1'; }
+static bool stem_pool_forced_env() { const char* e = getenv("INFUR_B200_STEM_POOL"); return e && e[0] == 'f'; }
+
+static Status fuse_stem_pool(infur_b200_handle* H, const DeviceModel& M, Plan& p, const std::vector<ConvIO>& ios) {
+  const LoweredModel& m = M.lm;
+  for (size_t k = 0; k + 1 < p.ops.size(); ++k) {
+    PlanOp &a = p.ops[k], &b = p.ops[k + 1];
+    if (!a.is_conv || b.is_conv || a.skip || b.skip || a.b2b) continue;
+    const LoweredOp &opa = m.ops[a.op], &opb = m.ops[b.op];
+    const DevConv& da = M.convs[a.op];
+    // the fp16 model's stem (ReLU in the epilogue) or the stem of an int8 plan (mode 2: requantised u8 output, pooled as bytes)
+    if (!(da.stem && da.tc_ok && ((da.mode == 0 && !da.quant && da.relu) || da.mode == 2) && da.cout == 64 && opa.conv.residual < 0)) continue;
+    if (!(opb.kind == OpKind::MaxPool && opb.pool_k == 3 && opb.pool_s == 2 && opb.pool_p == 1 && opb.in == opa.out)) continue;
+    int uses = 0;
+    for (size_t i = 0; i < m.ops.size(); ++i) {
+      if (!M.needed[i]) continue;
+      if (m.ops[i].in == opa.out) ++uses;
+      if (m.ops[i].kind == OpKind::Conv && (m.ops[i].conv.residual == opa.out || m.ops[i].conv.in2 == opa.out)) ++uses;
+    }
+    for (auto& hd : m.heads) if (hd.tensor == opa.out) ++uses;
+    if (uses != 1) continue;
+    const TensorInfo& ti = p.tensors[opb.in];
+    const TensorInfo& to = p.tensors[opb.out];
+    if (to.h != (ti.h - 1) / 2 + 1 || to.w != (ti.w - 1) / 2 + 1 || to.c != 64) continue;
+    PlanOp pf = a;
+    ConvTcGeom& g = pf.geom;
+    const int n = ios[k].n;
+    g.sp_fused = 1; g.sp_oh = to.h; g.sp_ow = to.w;
+    g.sp_strips = (to.w + 59) / 60;
+    // pooled rows per unit: a unit costs 2 rc + 1 convolution rows; pick the rc whose (waves over the SMs) x (rows per unit) is smallest
+    long best_cost = -1;
+    for (int rc = 4; rc <= to.h; ++rc) {
+      const int chunks = (to.h + rc - 1) / rc;
+      const long units = (long)n * g.sp_strips * chunks;
+      const long waves = (units + H->num_sms - 1) / H->num_sms;
+      const long cost = waves * (2 * rc + 1);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; g.sp_rc = rc; g.sp_chunks = chunks; }
+    }
+    if (best_cost < 0) { g.sp_rc = to.h; g.sp_chunks = 1; }
+    g.num_tiles = n * g.sp_strips * g.sp_chunks;
+    g.out = reinterpret_cast<__half*>(to.ptr);
+    const TuneKey key{3, 64, 7, 2, 1, 101 + da.mode, 0, 0, (int)lround(2.0 * log2(std::max(1.0, (double)n * to.h * to.w / 128.0)))};
+    bool fuse = true;
+    if (H->cfg.autotune && !stem_pool_forced_env()) {
+      auto it = H->tune_cache.find(key);
+      for (int delta = 1; delta <= 2 && it == H->tune_cache.end(); ++delta)
+        for (int sgn = -1; sgn <= 1 && it == H->tune_cache.end(); sgn += 2) { TuneKey k2 = key; k2.bucket += sgn * delta; it = H->tune_cache.find(k2); }
+      if (it != H->tune_cache.end()) fuse = it->second.variant == 1;
+      else {
+        H->last_build_tuned++;
+        cudaEvent_t e0, e1, e2;
+        CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1)); CU_TRY(cudaEventCreate(&e2));
+        float best_f = 1e30f, best_s = 1e30f;
+        cudaError_t e = cudaSuccess;
+        for (int round = 0; round < 3 && e == cudaSuccess; ++round) {
+          e = conv_tc_launch(pf.block_n, pf.maps, pf.geom, H->num_sms, H->stream);
+          cudaEventRecord(e0, H->stream);
+          for (int r = 0; r < 3 && e == cudaSuccess; ++r) e = conv_tc_launch(pf.block_n, pf.maps, pf.geom, H->num_sms, H->stream);
+          cudaEventRecord(e1, H->stream);
+          for (int r = 0; r < 3 && e == cudaSuccess; ++r) {
+            e = conv_tc_launch(a.block_n, a.maps, a.geom, H->num_sms, H->stream);
+            if (e == cudaSuccess)
+              e = M.i8 ? launch_maxpool3s2_u8(reinterpret_cast<const uint8_t*>(ti.ptr), reinterpret_cast<uint8_t*>(to.ptr), n, ti.h, ti.w, ti.c, to.h, to.w, H->stream)
+                       : launch_maxpool(reinterpret_cast<const __half*>(ti.ptr), reinterpret_cast<__half*>(to.ptr), n, ti.h, ti.w, ti.c, to.h, to.w, 3, 2, 1, H->stream);
+          }
+          cudaEventRecord(e2, H->stream);
+          if (e == cudaSuccess) e = cudaEventSynchronize(e2);
+          H->launches += 10;
+          float tf = 0.f, ts = 0.f;
+          if (e == cudaSuccess) { cudaEventElapsedTime(&tf, e0, e1); cudaEventElapsedTime(&ts, e1, e2); best_f = std::min(best_f, tf); best_s = std::min(best_s, ts); }
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        if (e != cudaSuccess) return Status::error(INFUR_E_RUNTIME, std::string("autotune (stem + pool): ") + cudaGetErrorString(e));
+        fuse = best_f < best_s * 0.98f;
+        H->tune_cache[key] = TuneChoice{64, fuse ? 1 : 0};
+        if (const char* dbg = getenv("INFUR_B200_DEBUG_TUNE"))
+          if (dbg[0] == '1' || dbg[0] == '2') fprintf(stderr, "[infur_b200] stem + pool, n %d conv out %dx%d: fused %.3f ms vs separate %.3f ms -> %s (rc %d, %d units)\n", n, ti.w, ti.h,
+                                     best_f / 3, best_s / 3, fuse ? "fused" : "separate", g.sp_rc, g.num_tiles);
+      }
+    }
+    if (!fuse) continue;
+    pf.flops = a.flops;
+    pf.bytes = a.bytes - (double)ti.bytes + (double)to.bytes;   // the stem's own output is never written; the pooled tensor is
+    pf.text = a.text.substr(0, a.text.find(" | ")) + " ++ " + opb.name + " 3x3/s2 -> [" + std::to_string(to.h) + "x" + std::to_string(to.w) + "] | tcgen05 fused stem + max-pool (stem_pool_kernel) units " +
+              std::to_string(g.num_tiles) + " rows/unit " + std::to_string(g.sp_rc) + " | GFLOP " + std::to_string(pf.flops * 1e-9) + " MB " + std::to_string(pf.bytes * 1e-6);
+    b.skip = true;
+    b.text = b.text.substr(0, b.text.find(" | ")) + " | (fused into previous) | MB 0";
+    b.flops = 0; b.bytes = 0;
+    p.ops[k] = pf;
+    break;
+  }
+  return Status();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Plan
 constexpr size_t kMaxPlans = 6;
 
@@ -815,6 +912,9 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
   }
   if (H->cfg.conv_impl == INFUR_CONV_TCGEN05 && !M->i8 && !m.quant && !b2b_disabled_env()) {
     if (!(st = fuse_b2b_pairs(H, *M, p, ios, last_use)).ok()) return st;
+  }
+  if (H->cfg.conv_impl == INFUR_CONV_TCGEN05 && (M->i8 || !m.quant) && !stem_pool_disabled_env()) {
+    if (!(st = fuse_stem_pool(H, *M, p, ios)).ok()) return st;
   }
   // ---- head / post
   const LoweredHead& hd = m.heads[M->out_head];

@@ -43,7 +43,39 @@ def test_b2b_bit_identical_to_separate_launches(fcn50, w, h, n):
     # FCN-ResNet50: layer1.1, layer1.2 (cmid 64) and layer2.1 .. layer2.3 (cmid 128); the first block of a layer carries the
     # projection shortcut in its 1x1 and is not a candidate, layer3 / layer4 (cmid 256 / 512) exceed the kernel's smem / TMEM budget
     assert len(fused) == 5 and sum("cmid 64" in ln for ln in fused) == 2 and sum("cmid 128" in ln for ln in fused) == 3, plan
-    assert plan.count("(fused into previous)") == 5
+    assert sum(1 for ln in plan.splitlines() if ln.startswith("conv ") and "(fused into previous)" in ln) == 5
     assert (low == low_ref).all(), f"low-res logits differ: max |diff| {np.abs(low - low_ref).max()}"
     for a, b in zip(got, ref):
+        assert (a["class_map"] == b["class_map"]).all() and (a["decoded_rgba"] == b["decoded_rgba"]).all()
+
+
+@pytest.mark.parametrize("kind", ["f16", "int8"])
+@pytest.mark.parametrize("w,h,n", [(320, 240, 2), (200, 136, 1), (97, 65, 3), (500, 34, 1), (8, 8, 1), (1, 1, 2)])
+def test_stem_pool_fusion_bit_identical(tiny, kind, w, h, n):
+    """stem_pool_kernel (7x7/s2 stem + 3x3/s2 max-pool in one launch) against the two separate kernels: several column strips,
+    odd convolution sizes (the last pooled row / column sees a clipped window), frames smaller than one strip; the fp16 model and
+    the stem of an int8 plan (requantised u8 output, pooled as bytes)."""
+    path, _ = tiny
+    if kind == "int8":
+        from infur_b200 import quantize
+        path = quantize.ensure_fixture("fcn_tiny_int8")
+    frames = np.stack([synth.synth_frame(w, h, 30 + i) for i in range(n)])
+    old = {k: os.environ.get(k) for k in ("INFUR_B200_NO_STEM_POOL", "INFUR_B200_STEM_POOL")}
+    res = {}
+    try:
+        for name, env in (("sep", {"INFUR_B200_NO_STEM_POOL": "1"}), ("fused", {"INFUR_B200_STEM_POOL": "force"})):
+            for k in old:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            with P.Handle(max_batch=n, autotune=False) as hd:
+                hd.model_load(path)
+                res[name] = (hd.advance_batch(frames, want=("class_map", "decoded_rgba")), hd.model_lowres(frames[0]), hd.plan_text(n, w, h))
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    assert "stem_pool_kernel" in res["fused"][2] and "stem_pool_kernel" not in res["sep"][2]
+    assert (res["fused"][1] == res["sep"][1]).all(), np.abs(res["fused"][1] - res["sep"][1]).max()
+    for a, b in zip(res["fused"][0], res["sep"][0]):
         assert (a["class_map"] == b["class_map"]).all() and (a["decoded_rgba"] == b["decoded_rgba"]).all()
