@@ -247,3 +247,29 @@ def test_class_legend(single, tiny):
     lut = oracle.color_lut()
     for i, _, rgb in leg:
         assert rgb == tuple(int(v) for v in lut[i % 20, 255, :3])   # COLORS_PALETTE[i % 20] (decode_predict.rs:9-34)
+
+
+def test_tune_table_export_import_skips_measurements(lib, tiny):
+    """infur_b200_tune_export / _import: a host can persist the autotune decisions next to the model; a fresh handle that imports
+    them builds the same plan without measuring anything (gui.rs:91-103 persists its settings the same way)."""
+    path, _ = tiny
+    frame = synth.synth_frame(320, 240, 3)
+    with P.Handle(device=0, max_batch=2) as h1:
+        h1.model_load(path)
+        ref = h1.advance(frame, 1)
+        ms1, tuned1 = h1.plan_build_stats()
+        table = h1.tune_export()
+        plan1 = h1.plan_text(1, 320, 240)
+    assert tuned1 > 0 and len(table.splitlines()) >= tuned1
+    with P.Handle(device=0, max_batch=2) as h2:
+        h2.tune_import(table)
+        h2.model_load(path)
+        got = h2.advance(frame, 1)
+        ms2, tuned2 = h2.plan_build_stats()
+        plan2 = h2.plan_text(1, 320, 240)
+        with pytest.raises(P.InfurError) as e:
+            h2.tune_import("64 256 1 1 1 0 1 0 20 100 0\n")        # block_n 100 is not a tile size
+        assert e.value.code == L.E_INVALID_ARG
+    assert tuned2 == 0 and ms2 < ms1
+    assert plan1 == plan2
+    assert (got["class_map"] == ref["class_map"]).all() and (got["decoded_rgba"] == ref["decoded_rgba"]).all()
