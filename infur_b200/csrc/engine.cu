@@ -421,7 +421,7 @@ static void setup_direct(const DevConv& d, const ConvIO& io, const __half* wv, D
 // accumulation order of every output element is the same for all choices (K blocks in sequence), so the
 // result is bit-identical whichever wins; only time differs: a narrower tile leaves room for more pipeline
 // stages (more HBM bytes in flight for the memory-bound 1x1 convs), a wider one halves the activation re-reads.
-static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO& io, PlanOp& po) {
+static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO& io, PlanOp& po, double flops) {
   struct Cand { int bn; int var; };
   static const Cand cands[8] = {{256, kVarPair}, {256, kVarPlain}, {128, kVarPlain}, {64, kVarPlain}, {256, kVarHalo}, {128, kVarHalo}, {64, kVarHalo}, {256, kVarPairDeep}};
   if (d.stem) return Status();
@@ -444,6 +444,9 @@ static Status tune_block_n(infur_b200_handle* H, const DevConv& d, const ConvIO&
       return Status();
     }
   }
+  // a layer of less than 2 GFLOP (~2 us of tensor-core time: small frames, the first 1x1 of layer1 at batch 1) is bound by launch
+  // latency whatever the tile shape: keep the default instead of spending ~80 launches on measuring it
+  if (flops < 2e9) return Status();
   H->last_build_tuned++;
   if (const char* dbg = getenv("INFUR_B200_DEBUG_TUNE"))
     if (dbg[0] == '1' || dbg[0] == '2') fprintf(stderr, "[infur_b200] autotune: %dx%d conv %d->%d s%d d%d mode %d res %d cin2 %d, n %d out %dx%d, bucket %d\n", d.kh, d.kw, d.cin, d.cout,
@@ -555,6 +558,7 @@ static Status fuse_b2b_pairs(infur_b200_handle* H, const DeviceModel& M, Plan& p
       for (int delta = 1; delta <= 2 && it == H->tune_cache.end(); ++delta)
         for (int sgn = -1; sgn <= 1 && it == H->tune_cache.end(); sgn += 2) { TuneKey k2 = key; k2.bucket += sgn * delta; it = H->tune_cache.find(k2); }
       if (it != H->tune_cache.end()) fuse = it->second.variant == 1;
+      else if (a.flops + b.flops < 2e9) fuse = true;   // too small to be worth measuring (see tune_block_n): one launch instead of two
       else {
         H->last_build_tuned++;
         cudaEvent_t e0, e1, e2;
@@ -650,6 +654,7 @@ static Status fuse_stem_pool(infur_b200_handle* H, const DeviceModel& M, Plan& p
       for (int delta = 1; delta <= 2 && it == H->tune_cache.end(); ++delta)
         for (int sgn = -1; sgn <= 1 && it == H->tune_cache.end(); sgn += 2) { TuneKey k2 = key; k2.bucket += sgn * delta; it = H->tune_cache.find(k2); }
       if (it != H->tune_cache.end()) fuse = it->second.variant == 1;
+      else if (a.flops < 2e9) fuse = true;             // small frames: one launch instead of two, unmeasured
       else {
         H->last_build_tuned++;
         cudaEvent_t e0, e1, e2;
@@ -886,11 +891,11 @@ Status build_plan(infur_b200_handle* H, int n, int w, int h, std::unique_ptr<Pla
       io.out_ld = to.ld;
       ios.back() = io;
       if (d.tc_ok) { if (!(st = setup_conv_tc(d, io, po, d.block_n)).ok()) return st; }
+      po.flops = 2.0 * n * to.h * to.w * (double)d.cout * (d.kh * d.kw * d.cin + d.cin2);
       if (d.tc_ok && !to.f32 && H->cfg.autotune && H->cfg.conv_impl == INFUR_CONV_TCGEN05) {
-        if (!(st = tune_block_n(H, d, io, po)).ok()) return st;
+        if (!(st = tune_block_n(H, d, io, po, po.flops)).ok()) return st;
       }
       setup_direct(d, io, reinterpret_cast<const __half*>(M->arena + d.wv_off), po.direct);
-      po.flops = 2.0 * n * to.h * to.w * (double)d.cout * (d.kh * d.kw * d.cin + d.cin2);
       const double xsz = d.mode == 3 ? 1.0 : 2.0, rsz = d.mode >= 2 ? 1.0 : 2.0;   // element sizes of the operands / of the residual
       po.bytes = (double)n * ti.h * ti.w * d.cin * xsz + (double)to.bytes + (io.residual ? (double)n * to.h * to.w * to.c * rsz : 0.0) +
                  (double)d.cout * (d.kh * d.kw * d.cin + d.cin2) * xsz + (io.x2 ? (double)n * io.h2 * io.w2 * d.cin2 * 2 : 0.0);
