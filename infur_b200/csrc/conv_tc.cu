@@ -31,6 +31,8 @@
 
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace infur {
@@ -216,6 +218,76 @@ __device__ __forceinline__ void epilogue_direct(const ConvTcGeom& g, uint32_t tm
   }
 }
 
+// Requantisation of 32 channels of one pixel to u8 (int8 plans), in f32 exactly as the fp16-carried form does it (requant /
+// requant_add above); what differs is getting integers in and out cheaply:
+//  * a residual byte b becomes the float 2^23 + b by placing it in the low mantissa byte of 0x4B000000 (PRMT), so b - zero_point
+//    is ONE add of -(2^23 + zero_point)  (exact);
+//  * rne(v) for |v| < 2^22 is v + 1.5 * 2^23 (one add): the low mantissa bits of the result hold rne(v) as a two's-complement
+//    integer.  (Adding the zero point before rounding would break ties differently whenever it is odd.)
+// VAR 0: generic -- the clamp happens in f32 before the rounding add (so that add is valid whatever the accumulator), the zero
+//        point is added to the mantissa bits and PRMT gathers the low bytes.
+// VAR 1: integer tail (ConvTcGeom::q_tail: the value that reaches the LAST rounding add is below 2^22 in magnitude whatever the
+//        input) -- no f32 clamp there: the integer rne(v) + zero_point saturates to [0, 255] inside the pack instruction
+//        (I2IP.SAT, two per four channels), then one byte-wise max with the lower bound when that is above 0.  Same result:
+//        clamp and rne commute (integer bounds), and q_hi + zero_point == 255 is checked where q_tail is set.
+// VAR 2: VAR 1 + small accumulators (MODE 3, |acc + bias| < 2^22 proven from the weights): int -> float is an integer add of the
+//        bit pattern of 1.5 * 2^23 (folded into the bias add, IADD3) and one packed float subtract instead of two I2F.
+// Multiplies that feed an add use mul_f32x2_sep: ptxas would otherwise fuse them into FFMA2 and drop a rounding (ptx.cuh).
+template <int MODE, bool HAS_RES, int VAR>
+__device__ __forceinline__ void requant_u8_pass(const ConvTcGeom& g, const uint32_t (&acc)[32], const uint32_t (&rw)[8], uint32_t (&ow)[8], int cofs,
+                                                float lo_out, float hi1, float lo2, float hi2, float res_bias, uint32_t zout, uint32_t lfloor) {
+  constexpr bool ITAIL = VAR >= 1, SMALL = VAR == 2;
+  constexpr int kMagicBits = 0x4B400000;          // bits of 1.5 * 2^23
+  const uint32_t zadj = ITAIL ? zout - (uint32_t)kMagicBits : zout;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {            // 4 channels -> one 32-bit word of u8
+    const float4 m = __ldg(reinterpret_cast<const float4*>(g.qmul + cofs) + j);
+    float t[4];
+    if (MODE == 3) {
+      const int4 bi = __ldg(reinterpret_cast<const int4*>(g.bias_i32 + cofs) + j);
+      if (SMALL) {
+        t[0] = __int_as_float((int)acc[4 * j + 0] + bi.x + kMagicBits); t[1] = __int_as_float((int)acc[4 * j + 1] + bi.y + kMagicBits);
+        t[2] = __int_as_float((int)acc[4 * j + 2] + bi.z + kMagicBits); t[3] = __int_as_float((int)acc[4 * j + 3] + bi.w + kMagicBits);
+        ptx::add_f32x2(t[0], t[1], -kRneMagic, -kRneMagic); ptx::add_f32x2(t[2], t[3], -kRneMagic, -kRneMagic);
+      } else {
+        t[0] = __int2float_rn((int)acc[4 * j + 0] + bi.x); t[1] = __int2float_rn((int)acc[4 * j + 1] + bi.y);
+        t[2] = __int2float_rn((int)acc[4 * j + 2] + bi.z); t[3] = __int2float_rn((int)acc[4 * j + 3] + bi.w);
+      }
+    } else {
+      const float4 bf = __ldg(reinterpret_cast<const float4*>(g.bias + cofs) + j);
+      t[0] = __uint_as_float(acc[4 * j + 0]); t[1] = __uint_as_float(acc[4 * j + 1]);
+      t[2] = __uint_as_float(acc[4 * j + 2]); t[3] = __uint_as_float(acc[4 * j + 3]);
+      ptx::add_f32x2(t[0], t[1], bf.x, bf.y); ptx::add_f32x2(t[2], t[3], bf.z, bf.w);
+    }
+    ptx::mul_f32x2_sep(t[0], t[1], m.x, m.y); ptx::mul_f32x2_sep(t[2], t[3], m.z, m.w);
+    uint32_t bits[4];
+#pragma unroll
+    for (int x = 0; x < 4; x += 2) {
+      float a0 = t[x], a1 = t[x + 1];
+      if (HAS_RES || !ITAIL) { a0 = fminf(fmaxf(a0, lo_out), hi1); a1 = fminf(fmaxf(a1, lo_out), hi1); }
+      ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);                       // rne(v) + 1.5 * 2^23
+      if (HAS_RES) {
+        ptx::add_f32x2(a0, a1, -kRneMagic, -kRneMagic);                   // rne(v) as a float
+        float b0 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x));        // 2^23 + residual byte
+        float b1 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x + 1));
+        ptx::add_f32x2(b0, b1, res_bias, res_bias);                         // residual - its zero point
+        ptx::mul_f32x2_sep(a0, a1, g.q_ra, g.q_ra);
+        ptx::mul_f32x2_sep(b0, b1, g.q_rb, g.q_rb);
+        ptx::add_f32x2(a0, a1, b0, b1);
+        if (!ITAIL) { a0 = fminf(fmaxf(a0, lo2), hi2); a1 = fminf(fmaxf(a1, lo2), hi2); }
+        ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);
+      }
+      bits[x] = __float_as_uint(a0) + zadj; bits[x + 1] = __float_as_uint(a1) + zadj;
+    }
+    if (ITAIL) {
+      ow[j] = ptx::pack_sat_u8x4((int)bits[0], (int)bits[1], (int)bits[2], (int)bits[3]);
+      if (lfloor) ow[j] = __vmaxu4(ow[j], lfloor);
+    } else {
+      ow[j] = __byte_perm(__byte_perm(bits[0], bits[1], 0x0040), __byte_perm(bits[2], bits[3], 0x0040), 0x5410);
+    }
+  }
+}
+
 // TMA-staged epilogue for NHWC outputs (fp16, or u8 in int8 plans: MODE >= 2).  The tile's output is produced in chunks
 // of CW channels (64 for fp16; 128 for u8 where the N tile has them); chunk q of this CTA (running count over all its
 // tiles) lives in smem buffer q % EB as 128 rows (pixels) x 128 B with the 128B swizzle the tensor maps expect
@@ -247,106 +319,84 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
     ptx::mbar_wait(tfull0 + 8u * as, aphase);
     ptx::tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + half * 32);
+    if constexpr (MODE >= 2 && CH >= 1) {
+      // ---- u8 outputs (int8 plan).  CW = 128: rows of 128 bytes, 128B-swizzled like the fp16 chunks, a thread owns 64 bytes of
+      // its row (two passes of 32 channels); CW = 64 (64-channel tiles): rows of 64 bytes, unswizzled, 32 bytes per thread.
+      // The passes of a tile are software-pipelined: the TMEM load of pass p + 1 is issued before the arithmetic of pass p, so
+      // its latency (and the L1 misses of the per-channel constants) hides behind ~400 instructions instead of stalling both
+      // warps of a scheduler -- with the instruction count of requant_u8_pass this loop was latency-bound, not issue-bound.
+      constexpr int PASSES = CW / 64;
+      constexpr int NP = CH * PASSES;             // passes per tile: 1, 2 or 4
+      constexpr uint32_t kChunk = CW == 128 ? kEpiBufBytes : kEpiBufBytes / 2;
+      const float lo1 = g.q_lo, hi1 = g.q_hi;
+      const float lo2 = g.relu ? fmaxf(g.q_lo2, 0.f) : g.q_lo2, hi2 = g.q_hi2;
+      const float lo_out = (!HAS_RES && g.relu) ? fmaxf(lo1, 0.f) : lo1;
+      const float res_bias = -(8388608.f + g.q_zres);
+      const uint32_t zout = (uint32_t)(int)(g.q_zmagic - kRneMagic);
+      const uint32_t lfloor = (uint32_t)g.q_floor * 0x01010101u;
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + half * (CW / 2));
+      auto pass = [&](auto pc, uint32_t (&acc)[32], uint32_t (&nxt)[32]) {
+        constexpr int p = decltype(pc)::value;
+        constexpr int c = p / PASSES, hh = p % PASSES;
+        ptx::tmem_ld_wait(acc);
+        if constexpr (p + 1 < NP) {
+          ptx::tmem_ld_32x32b_x32(t_acc + (uint32_t)(((p + 1) / PASSES) * CW + ((p + 1) % PASSES) * 32), nxt);
+        } else {                                 // accumulator stage fully read
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(tempty0 + 8u * as, 0));
+            else ptx::mbar_arrive(tempty0 + 8u * as);
+          }
+        }
+        const int qq = q + c;
+        const int b = qq % EB;
+        const uint32_t use = (uint32_t)(qq / EB);
+        const uint32_t rowb = epi_base + b * kChunk + (uint32_t)row * (uint32_t)CW;
+        const int cofs = n0 + c * CW + half * (CW / 2) + hh * 32;
+        uint32_t ga[2];                          // 16-byte group addresses of this pass
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+          ga[jj] = CW == 128 ? rowb + (((uint32_t)(half * 4 + hh * 2 + jj) ^ sw) << 4) : rowb + (uint32_t)(half * 32 + jj * 16);
+        uint32_t rw[8];
+        if (hh == 0) {
+          if (HAS_RES) ptx::mbar_wait(eb.res + 8u * b, use & 1u);
+          else if (use >= 1) ptx::mbar_wait(eb.free_ + 8u * b, (use - 1u) & 1u);
+        }
+        if (HAS_RES) {
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(ga[0]));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "r"(ga[1]));
+        }
+        uint32_t ow[8];
+        // uniform branches, not predicates: each variant is straight-line code of its own (a predicated-off instruction still
+        // takes its issue slot)
+        if (MODE == 3 && g.q_tail == 2) requant_u8_pass<MODE, HAS_RES, 2>(g, acc, rw, ow, cofs, lo_out, hi1, lo2, hi2, res_bias, zout, lfloor);
+        else if (g.q_tail == 1) requant_u8_pass<MODE, HAS_RES, 1>(g, acc, rw, ow, cofs, lo_out, hi1, lo2, hi2, res_bias, zout, lfloor);
+        else requant_u8_pass<MODE, HAS_RES, 0>(g, acc, rw, ow, cofs, lo_out, hi1, lo2, hi2, res_bias, zout, lfloor);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ga[0]), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ga[1]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
+        if constexpr (hh == PASSES - 1) {
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(eb.ready + 8u * b);
+        }
+      };
+      uint32_t accA[32], accB[32];
+      ptx::tmem_ld_32x32b_x32(t_acc, accA);
+      pass(std::integral_constant<int, 0>{}, accA, accB);
+      if constexpr (NP >= 2) pass(std::integral_constant<int, 1>{}, accB, accA);
+      if constexpr (NP >= 4) {
+        pass(std::integral_constant<int, 2>{}, accA, accB);
+        pass(std::integral_constant<int, 3>{}, accB, accA);
+      }
+      static_assert(NP == 1 || NP == 2 || NP == 4, "passes per tile");
+      q += CH;
+      continue;
+    }
 #pragma unroll 1
     for (int c = 0; c < CH; ++c, ++q) {
       const int b = q % EB;
       const uint32_t use = (uint32_t)(q / EB);
-      if (MODE >= 2) {
-        // ---- u8 outputs (int8 plan).  CW = 128: rows of 128 bytes, 128B-swizzled like the fp16 chunks, a thread owns 64 bytes of
-        // its row (two passes of 32 channels); CW = 64 (64-channel tiles): rows of 64 bytes, unswizzled, 32 bytes per thread.
-        constexpr int PASSES = CW / 64;
-        constexpr uint32_t kChunk = CW == 128 ? kEpiBufBytes : kEpiBufBytes / 2;
-        const uint32_t rowb = epi_base + b * kChunk + (uint32_t)row * (uint32_t)CW;
-        const float lo1 = g.q_lo, hi1 = g.q_hi;
-        const float lo2 = g.relu ? fmaxf(g.q_lo2, 0.f) : g.q_lo2, hi2 = g.q_hi2;
-        const float lo_out = (!HAS_RES && g.relu) ? fmaxf(lo1, 0.f) : lo1;
-        const float res_bias = -(8388608.f + g.q_zres);
-        const uint32_t zout = (uint32_t)(int)(g.q_zmagic - kRneMagic);
-#pragma unroll
-        for (int hh = 0; hh < PASSES; ++hh) {
-          const int cofs = n0 + c * CW + half * (CW / 2) + hh * 32;
-          // 16-byte group addresses of this pass
-          uint32_t ga[2];
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
-            ga[jj] = CW == 128 ? rowb + (((uint32_t)(half * 4 + hh * 2 + jj) ^ sw) << 4) : rowb + (uint32_t)(half * 32 + jj * 16);
-          uint32_t acc[32];
-          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c * CW + half * (CW / 2) + hh * 32), acc);
-          ptx::tmem_ld_wait();
-          if (c == CH - 1 && hh == PASSES - 1) {   // accumulator stage fully read
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (PAIR) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(tempty0 + 8u * as, 0));
-              else ptx::mbar_arrive(tempty0 + 8u * as);
-            }
-          }
-          uint32_t rw[8];
-          if (hh == 0) {
-            if (HAS_RES) ptx::mbar_wait(eb.res + 8u * b, use & 1u);
-            else if (use >= 1) ptx::mbar_wait(eb.free_ + 8u * b, (use - 1u) & 1u);
-          }
-          if (HAS_RES) {
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(ga[0]));
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]) : "r"(ga[1]));
-          }
-          // Requantisation in f32 exactly as in the fp16-carried form; what differs is getting integers in and out cheaply:
-          //  * a residual byte b becomes the float 2^23 + b by placing it in the low mantissa byte of 0x4B000000 (PRMT), so
-          //    b - zero_point is ONE add of -(2^23 + zero_point)  (exact);
-          //  * rne(v) for the clamped v is v + 1.5 * 2^23 (one add); the result's low mantissa bits hold rne(v) as an integer, the
-          //    output zero point is added to those bits with an integer add, and PRMT gathers the four low bytes of a word.
-          //    (Adding the zero point before rounding would break ties differently whenever it is odd.)
-          uint32_t ow[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {            // 4 channels -> one 32-bit word of u8
-            const float4 m = __ldg(reinterpret_cast<const float4*>(g.qmul + cofs) + j);
-            float t[4];
-            if (MODE == 3) {
-              const int4 bi = __ldg(reinterpret_cast<const int4*>(g.bias_i32 + cofs) + j);
-              if (g.q_small_acc) {   // |acc + bias| < 2^22 (ConvTcGeom::q_small_acc): f32(x) = as_float(x + bits(1.5 * 2^23)) - 1.5 * 2^23, exactly
-                constexpr int kMagicBits = 0x4B400000;
-                t[0] = __int_as_float((int)acc[4 * j + 0] + bi.x + kMagicBits); t[1] = __int_as_float((int)acc[4 * j + 1] + bi.y + kMagicBits);
-                t[2] = __int_as_float((int)acc[4 * j + 2] + bi.z + kMagicBits); t[3] = __int_as_float((int)acc[4 * j + 3] + bi.w + kMagicBits);
-                ptx::add_f32x2(t[0], t[1], -kRneMagic, -kRneMagic); ptx::add_f32x2(t[2], t[3], -kRneMagic, -kRneMagic);
-              } else {
-                t[0] = __int2float_rn((int)acc[4 * j + 0] + bi.x); t[1] = __int2float_rn((int)acc[4 * j + 1] + bi.y);
-                t[2] = __int2float_rn((int)acc[4 * j + 2] + bi.z); t[3] = __int2float_rn((int)acc[4 * j + 3] + bi.w);
-              }
-            } else {
-              const float4 bf = __ldg(reinterpret_cast<const float4*>(g.bias + cofs) + j);
-              t[0] = __uint_as_float(acc[4 * j + 0]); t[1] = __uint_as_float(acc[4 * j + 1]);
-              t[2] = __uint_as_float(acc[4 * j + 2]); t[3] = __uint_as_float(acc[4 * j + 3]);
-              ptx::add_f32x2(t[0], t[1], bf.x, bf.y); ptx::add_f32x2(t[2], t[3], bf.z, bf.w);
-            }
-            ptx::mul_f32x2(t[0], t[1], m.x, m.y); ptx::mul_f32x2(t[2], t[3], m.z, m.w);
-            uint32_t bits[4];
-#pragma unroll
-            for (int x = 0; x < 4; x += 2) {
-              float a0 = fminf(fmaxf(t[x], lo_out), hi1), a1 = fminf(fmaxf(t[x + 1], lo_out), hi1);
-              ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);                       // rne(v) + 1.5 * 2^23
-              if (HAS_RES) {
-                ptx::add_f32x2(a0, a1, -kRneMagic, -kRneMagic);                   // rne(v) as a float
-                float b0 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x));        // 2^23 + residual byte
-                float b1 = __uint_as_float(__byte_perm(rw[j], 0x4B000000u, 0x7650 + x + 1));
-                ptx::add_f32x2(b0, b1, res_bias, res_bias);                         // residual - its zero point
-                ptx::mul_f32x2(a0, a1, g.q_ra, g.q_ra);
-                ptx::mul_f32x2(b0, b1, g.q_rb, g.q_rb);
-                ptx::add_f32x2(a0, a1, b0, b1);
-                a0 = fminf(fmaxf(a0, lo2), hi2); a1 = fminf(fmaxf(a1, lo2), hi2);
-                ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);
-              }
-              bits[x] = __float_as_uint(a0) + zout; bits[x + 1] = __float_as_uint(a1) + zout;
-            }
-            ow[j] = __byte_perm(__byte_perm(bits[0], bits[1], 0x0040), __byte_perm(bits[2], bits[3], 0x0040), 0x5410);
-          }
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ga[0]), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ga[1]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
-        }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(eb.ready + 8u * b);
-        continue;
-      }
       const uint32_t rowp = epi_base + b * kEpiBufBytes + (uint32_t)row * 128u;
       float4 bias[8], qm[8];
       {
@@ -410,8 +460,8 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
             for (int t = 0; t < 4; ++t) {
               const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&rw[t]));
               float a0 = v[2 * t], a1 = v[2 * t + 1], b0 = r.x, b1 = r.y;
-              ptx::mul_f32x2(a0, a1, g.q_ra, g.q_ra);
-              ptx::mul_f32x2(b0, b1, g.q_rb, g.q_rb);
+              ptx::mul_f32x2_sep(a0, a1, g.q_ra, g.q_ra);
+              ptx::mul_f32x2_sep(b0, b1, g.q_rb, g.q_rb);
               ptx::add_f32x2(a0, a1, b0, b1);
               a0 = fminf(fmaxf(a0, g.q_lo2), g.q_hi2); a1 = fminf(fmaxf(a1, g.q_lo2), g.q_hi2);
               ptx::add_f32x2(a0, a1, kRneMagic, kRneMagic);

@@ -59,10 +59,15 @@ struct ConvTcGeom {
   int32_t mode;
   const int32_t* bias_i32;    // mode 3: [tiles_n * BLOCK_N]
   float q_zres, q_zmagic;
-  // mode 3: 1 when |accumulator + bias| < 2^22 for every output channel whatever the u8 input (proven from the weights at load:
-  // 255 * sum|w| + |b| per channel): int -> float is then an integer add of the bit pattern of 1.5 * 2^23 and one float subtract
-  // (both exact) instead of I2F, which issues at a quarter of the f32 rate and paced the HBM-bound +residual layers
-  int32_t q_small_acc;
+  // u8 outputs (mode >= 2): which form of the requantisation tail the epilogue runs (requant_u8_pass in conv_tc.cu) -- decided
+  // once per layer on the host from bounds that hold whatever the input:
+  //   0  generic;
+  //   1  integer tail: the value that reaches the final rounding add is below 2^22 in magnitude (with a residual:
+  //      max|q_lo, q_hi| * |q_ra| + 255 * |q_rb|), and the final bounds are [q_floor - zero_point, 255 - zero_point];
+  //   2  integer tail + small accumulators (mode 3): |accumulator + bias| < 2^22 for every output channel (255 * sum|w| + |b|),
+  //      and without a residual also max qmul <= 1 -- int -> float becomes an integer add and a float subtract instead of I2F.
+  // q_floor = lower bound of the stored byte (0 unless a ReLU follows a tensor with a non-zero zero point).
+  int32_t q_tail, q_floor;
   int8_t tap_view[kMaxTaps + 3];
   uint8_t tap_cc[kMaxTaps + 3];  // 64-channel chunks of each tap (a fused shortcut tap may differ from the main taps)
   int16_t tap_dx[kMaxTaps + 1];

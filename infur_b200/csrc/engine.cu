@@ -91,7 +91,7 @@ static bool i8_enabled_env() { const char* e = getenv("INFUR_B200_I8"); return !
 static bool pair_disabled_env() { const char* e = getenv("INFUR_B200_NO_CTA_PAIR"); return e && e[0] == '1'; }
 
 // 255 * sum|w| + |b| < 2^22 for every output channel: the s32 accumulator + bias of a u8 x s8 convolution then converts to f32 with
-// the magic-number add (ConvTcGeom::q_small_acc) whatever the input
+// the magic-number add (ConvTcGeom::q_tail == 2) whatever the input
 static bool small_acc_bound(const float* w, size_t k_per_out, int cout, const float* bias) {
   if (!w || k_per_out == 0) return false;
   for (int co = 0; co < cout; ++co) {
@@ -165,6 +165,7 @@ Status build_device_model(LoweredModel&& lm, const infur_b200_config& cfg, bool 
     classify_conv(c, m.ops[i].in == m.input_tensor, is_head_tensor[m.ops[i].out] != 0, d);
     if (i8) { d.mode = d.stem ? 2 : 3; d.res_zp = c.res_zp; d.out_zp = c.out_zp; }
     if (d.mode == 3) d.small_acc = small_acc_bound(c.weight.data(), c.weight.size() / (size_t)std::max(c.cout, 1), c.cout, c.bias.data());
+    for (float q : c.qmul) d.qmul_max = std::max(d.qmul_max, std::fabs(q));
     if (!d.tc_ok && cfg.conv_impl == INFUR_CONV_TCGEN05)
       return Status::error(INFUR_E_MODEL_LOAD, "convolution '" + m.ops[i].name + "' cannot run on the tcgen05 path: " + d.why_not);
     d.w_off = off; off = align_up(off + (size_t)d.cout_pad * d.kdim * 2, 256);
@@ -312,7 +313,20 @@ static Status setup_conv_tc(const DevConv& d, const ConvIO& io, PlanOp& po, int 
     g.q_lo = d.q_lo; g.q_hi = d.q_hi; g.q_ra = d.q_ra; g.q_rb = d.q_rb; g.q_lo2 = d.q_lo2; g.q_hi2 = d.q_hi2; g.q_deq = d.q_deq;
     g.mode = d.mode ? d.mode : 1;
     g.bias_i32 = io.bias_i32; g.q_zres = (float)d.res_zp; g.q_zmagic = (float)d.out_zp + 12582912.f;
-    g.q_small_acc = d.small_acc ? 1 : 0;
+    g.q_tail = 0; g.q_floor = 0;
+    if (g.mode >= 2 && !io.y_f32) {
+      // final bounds of the stored byte, and the bound on what reaches the last rounding add (ConvTcGeom::q_tail)
+      const bool has_res = io.residual != nullptr;
+      const float lo_f = has_res ? (d.relu ? std::max(d.q_lo2, 0.f) : d.q_lo2) : (d.relu ? std::max(d.q_lo, 0.f) : d.q_lo);
+      const float hi_f = has_res ? d.q_hi2 : d.q_hi;
+      const double lo_b = (double)lo_f + d.out_zp, hi_b = (double)hi_f + d.out_zp;
+      const bool range_ok = hi_b == 255.0 && lo_b >= 0.0 && lo_b <= 255.0 && lo_b == std::floor(lo_b);
+      const bool small = g.mode == 3 && d.small_acc;
+      bool bounded;
+      if (has_res) bounded = std::max(std::fabs((double)d.q_lo), std::fabs((double)d.q_hi)) * std::fabs((double)d.q_ra) + 255.0 * std::fabs((double)d.q_rb) + 1.0 < 4194304.0;
+      else bounded = small && d.qmul_max <= 1.f;          // |(acc + bias) * qmul| < 2^22
+      if (range_ok && bounded) { g.q_tail = small ? 2 : 1; g.q_floor = (int)lo_b; }
+    }
   }
   Status st;
   const uint32_t box[4] = {64, (uint32_t)(d.stem ? 128 : bw), (uint32_t)(d.stem ? 1 : bh), 1};
@@ -1130,6 +1144,7 @@ Status conv_test_impl(infur_b200_handle* H, const infur_b200_conv_desc* cd, cons
       std::vector<float> wf((size_t)c.cout * c.kh * c.kw * c.cin);
       for (size_t j = 0; j < wf.size(); ++j) wf[j] = __half2float(reinterpret_cast<const __half*>(wgt)[j]);
       d.small_acc = small_acc_bound(wf.data(), wf.size() / (size_t)c.cout, c.cout, bias);
+      for (int co = 0; co < c.cout; ++co) d.qmul_max = std::max(d.qmul_max, std::fabs(cd->qmul[co]));
     }
   }
   if (c.quant && !tc) return Status::error(INFUR_E_UNSUPPORTED, "conv_test: quantised layers run on the tcgen05 implementations only");

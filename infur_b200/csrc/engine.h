@@ -51,7 +51,8 @@ struct DevConv {
   int mode = 0;
   int res_zp = 0, out_zp = 0;
   size_t bi_off = 0;       // mode 3: int32 bias [cout_pad]
-  bool small_acc = false;  // mode 3: 255 * sum|w| + |bias| < 2^22 for every output channel (ConvTcGeom::q_small_acc)
+  bool small_acc = false;  // mode 3: 255 * sum|w| + |bias| < 2^22 for every output channel (ConvTcGeom::q_tail)
+  float qmul_max = 0.f;    // quantised layer: largest requantisation multiplier
 };
 
 struct DeviceModel {

@@ -42,13 +42,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// try_wait that may sleep in hardware for up to `ns` before reporting "not yet" (the suspend-time hint); it still returns as soon as
+// the phase completes.  Without the hint the instruction comes back within ~50 cycles, and a waiting thread then re-issues its
+// whole poll loop every ~50 cycles: measured on the int8 layers, the three single-thread role warps and the waiting epilogue
+// warps together spent a fifth of the SM's issue slots -- and, worse, of the half-rate ALU pipe the epilogue arithmetic needs --
+// on polling.
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return done != 0;
+}
 // Bounded wait: a protocol bug must trap, never hang the device (a hung GPU box is a lost round).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  const long long t0 = clock64();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 256; ++i)
+      if (mbar_try_wait_sleep(bar, parity, 2000u)) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 
@@ -115,6 +133,22 @@ __device__ __forceinline__ void mul_f32x2(float& a0, float& a1, float b0, float 
   asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tmul.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
       : "+f"(a0), "+f"(a1)
       : "f"(b0), "f"(b1));
+}
+// (a0, a1) *= (b0, b1), each lane rounded separately EVEN WHEN AN ADD FOLLOWS.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2
+// into one FFMA2 (a single rounding) in spite of the explicit rounding modifiers and of -fmad=false -- the scalar mul.rn.f32 /
+// add.rn.f32 pair is left alone, and so is the .ftz form used here (tools/instr_tput.cu notes; SASS checked).  Flushing subnormals
+// changes nothing for the callers: their products are integers below 2^24 times scale ratios nowhere near 2^-100, or exact zeros.
+__device__ __forceinline__ void mul_f32x2_sep(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tmul.rn.ftz.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+// four s32 -> four u8 with saturation to [0, 255], x0 in the low byte: two I2IP.U8.S32.SAT
+__device__ __forceinline__ uint32_t pack_sat_u8x4(int x0, int x1, int x2, int x3) {
+  uint32_t hi, w;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(x3), "r"(x2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(x1), "r"(x0), "r"(hi));
+  return w;
 }
 // c + float(h) in one FHADD (the fp16 operand is converted exactly, one rounding)
 __device__ __forceinline__ float add_f32_f16(float c, unsigned short h) {
@@ -183,6 +217,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, tied to the registers of an EARLIER tcgen05.ld: when other work sits between the load and the wait (software
+// pipelining), nothing but this data dependence stops the compiler from scheduling a consumer of r[] above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // ---- CTA pair (cta_group::2): two CTAs of a cluster drive one 256-row MMA ---------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {

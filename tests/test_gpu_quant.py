@@ -233,3 +233,96 @@ def test_golden_qlinear_on_gpu(handle):
         else:
             y = handle.conv_test(xc, wc, g["bias"].astype(np.float32), rc, 1, 2, 2, impl=impl, quant=quant)
             assert (y.astype(np.int32).transpose(0, 3, 1, 2) == g["q_add"]).all()
+
+
+def _fused_add_differs(ra, rb, a_c, b_c):
+    """Positions where a fused multiply-add (a * ra + round(b * rb), ONE rounding) would round differently from QLinearAdd's
+    three separately rounded f32 operations.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 although both carry
+    explicit rounding modifiers (csrc/ptx.cuh mul_f32x2_sep): this is what such a kernel would compute."""
+    F = np.float32
+    vb = (F(rb) * b_c.astype(F)).astype(F)
+    fused = np.rint((a_c.astype(np.float64) * np.float64(F(ra)) + vb.astype(np.float64)).astype(F))
+    unfused = np.rint(((F(ra) * a_c.astype(F)).astype(F) + vb).astype(F))
+    return fused != unfused
+
+
+def _scale_pairs_where_fusion_matters(count, a_c, b_c):
+    rng = np.random.default_rng(2024)
+    out = []
+    while len(out) < count:
+        ra, rb = np.float32(rng.uniform(0.2, 3.0)), np.float32(rng.uniform(0.2, 3.0))
+        if _fused_add_differs(ra, rb, a_c, b_c).sum() >= 3:
+            out.append((ra, rb))
+    return out
+
+
+# impl, relu, zero point of the sum, scale multiplier on (ra, rb)
+ADD_SWEEP = [
+    (L.CONV_TCGEN05, False, 0, 1.0),                  # fp16-carried tensors
+    (L.CONV_TCGEN05_I8, False, 0, 1.0),               # integer tail + small accumulators (ConvTcGeom::q_tail 2)
+    (L.CONV_TCGEN05_I8, True, 37, 1.0),               # ... with a ReLU above a non-zero zero point: the byte-wise floor
+    (L.CONV_TCGEN05_I8_PAIR, False, 3, 1.0),
+    (L.CONV_TCGEN05_I8_PAIR_DEEP, True, 0, 1.0),
+    (L.CONV_TCGEN05_I8, False, 0, 8192.0),            # 255 * (ra + rb) >= 2^22: the generic tail (f32 clamp before the rounding add)
+]
+
+
+@pytest.mark.parametrize("impl,relu,c_zp,mult", ADD_SWEEP, ids=lambda v: str(v))
+def test_qlinear_add_every_byte_pair(handle, impl, relu, c_zp, mult):
+    """QLinearConv -> QLinearAdd over EVERY (conv output byte, residual byte) pair, with scale pairs picked so that an
+    implementation that fuses the multiply into the add gets at least three of the 65 536 pairs wrong."""
+    n, h, w, cin, cout = 1, 16, 32, 64, 256
+    y_zp, r_zp = 128, 41
+    i8 = impl != L.CONV_TCGEN05
+    # x = 0 everywhere: accumulator + bias = bias[c] = c - 128 -> the conv output of channel c is the byte c at every pixel;
+    # the residual byte at pixel p, channel c is (p + 7 c) mod 256: all 256 values meet every channel
+    xq = np.zeros((n, cin, h, w), np.uint8)
+    wq = np.ones((cout, cin, 1, 1), np.int8)
+    bq = (np.arange(cout) - 128).astype(np.int32)
+    pix = np.arange(h * w).reshape(1, 1, h, w)
+    rq = ((pix + 7 * np.arange(cout).reshape(1, cout, 1, 1)) % 256).astype(np.uint8)
+    one = np.float32(1.0)
+    yq = qlinear.qlinear_conv(xq, one, np.uint8(0), wq, np.full(cout, one), np.zeros(cout, np.int8), one, np.uint8(y_zp), bq, 1, 0, 1, [])
+    assert (yq[0, :, 0, 0] == np.arange(cout)).all()
+    a_c = yq.astype(np.int32) - y_zp
+    b_c = rq.astype(np.int32) - r_zp
+    pairs = _scale_pairs_where_fusion_matters(3, a_c, b_c)
+    for ra, rb in pairs:
+        ra, rb = np.float32(ra * mult), np.float32(rb * mult)
+        cq = qlinear.qlinear_add(yq, ra, np.uint8(y_zp), rq, rb, np.uint8(r_zp), one, np.uint8(c_zp))
+        if relu:
+            cq = np.maximum(cq, np.uint8(c_zp))
+        quant = {"qmul": np.full(cout, one), "q_lo": -y_zp, "q_hi": 255 - y_zp, "q_ra": ra, "q_rb": rb, "q_lo2": -c_zp, "q_hi2": 255 - c_zp,
+                 "q_zres": r_zp, "q_zout": c_zp}
+        xc = xq.astype(np.int32).transpose(0, 2, 3, 1)
+        wc = wq.astype(np.int32).transpose(0, 2, 3, 1)
+        rc = b_c.transpose(0, 2, 3, 1)
+        y = handle.conv_test(xc, wc, bq.astype(np.float32), rc, 1, 0, 1, relu=relu, impl=impl, quant=quant)
+        got = y.astype(np.int32).transpose(0, 3, 1, 2) + c_zp
+        bad = got != cq.astype(np.int32)
+        assert not bad.any(), f"ra {ra} rb {rb}: {bad.sum()} outputs differ; first at {np.argwhere(bad)[0]}: got {got[bad][0]} want {cq[bad][0]}"
+        if mult == 1.0:   # the case discriminates: a kernel with the fused form differs from the oracle on these inputs
+            assert _fused_add_differs(ra, rb, a_c, b_c).sum() >= 3
+    assert len(pairs) == 3
+
+
+@pytest.mark.parametrize("cin,impl", [(64, L.CONV_TCGEN05_I8), (1024, L.CONV_TCGEN05_I8), (64, L.CONV_TCGEN05_I8_PAIR)],
+                         ids=["small_acc_int_tail", "generic_tail", "pair_int_tail"])
+def test_qlinear_conv_relu_over_nonzero_zero_point(handle, cin, impl):
+    """QLinearConv + ReLU whose output tensor has a non-zero zero point (no residual): the stored byte is floored at the zero
+    point -- in the integer tail that is the byte-wise max after the saturating pack (ConvTcGeom::q_floor)."""
+    n, h, w, cout, y_zp = 2, 17, 23, 256, 23
+    rng = np.random.default_rng(cin)
+    xq = rng.integers(0, 256, size=(n, cin, h, w), dtype=np.uint8)
+    wq = rng.integers(-127, 128, size=(cout, cin, 1, 1), dtype=np.int8)
+    bq = rng.integers(-20000, 20000, size=cout, dtype=np.int32)
+    x_scale, y_scale = np.float32(0.021), np.float32(0.043)
+    w_scale = (rng.random(cout).astype(np.float32) + np.float32(0.5)) * np.float32(y_scale / x_scale / (25.0 * np.sqrt(cin)))
+    yq = qlinear.qlinear_conv(xq, x_scale, np.uint8(0), wq, w_scale, np.zeros(cout, np.int8), y_scale, np.uint8(y_zp), bq, 1, 0, 1, [])
+    expect = np.maximum(yq, np.uint8(y_zp)).astype(np.int32)
+    assert (yq < y_zp).mean() > 0.1 and (yq == 255).any() and len(np.unique(yq)) > 200          # both ends of the range are exercised
+    quant = {"qmul": (x_scale * w_scale) / y_scale, "q_lo": -y_zp, "q_hi": 255 - y_zp, "q_zout": y_zp}
+    y = handle.conv_test(xq.astype(np.int32).transpose(0, 2, 3, 1), wq.astype(np.int32).transpose(0, 2, 3, 1), bq.astype(np.float32), None, 1, 0, 1,
+                         relu=True, impl=impl, quant=quant)
+    got = y.astype(np.int32).transpose(0, 3, 1, 2) + y_zp
+    assert (got == expect).all()
