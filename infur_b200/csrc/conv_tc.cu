@@ -393,10 +393,12 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
       q += CH;
       continue;
     }
-#pragma unroll 1
-    for (int c = 0; c < CH; ++c, ++q) {
-      const int b = q % EB;
-      const uint32_t use = (uint32_t)(q / EB);
+    // fp16 outputs: one 64-channel chunk after the other, software-pipelined like the u8 passes above -- the TMEM load of chunk
+    // c + 1 is in flight during the arithmetic of chunk c, and the per-channel constants are requested before the wait.
+    auto chunk = [&](auto cc, uint32_t (&acc)[32], uint32_t (&nxt)[32]) {
+      constexpr int c = decltype(cc)::value;
+      const int b = (q + c) % EB;
+      const uint32_t use = (uint32_t)((q + c) / EB);
       const uint32_t rowp = epi_base + b * kEpiBufBytes + (uint32_t)row * 128u;
       float4 bias[8], qm[8];
       {
@@ -409,10 +411,10 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
 #pragma unroll
         for (int j = 0; j < 8; ++j) qm[j] = __ldg(m4 + j);
       }
-      uint32_t acc[32];
-      ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), acc);
-      ptx::tmem_ld_wait();
-      if (c == CH - 1) {   // accumulator stage fully read: hand it back to the MMA warp (of the leader CTA in a pair)
+      ptx::tmem_ld_wait(acc);
+      if constexpr (c + 1 < CH) {
+        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)((c + 1) * 64), nxt);
+      } else {             // accumulator stage fully read: hand it back to the MMA warp (of the leader CTA in a pair)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -491,6 +493,18 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
       ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA store
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(eb.ready + 8u * b);
+    };
+    {
+      uint32_t accA[32], accB[32];
+      ptx::tmem_ld_32x32b_x32(t_row, accA);
+      chunk(std::integral_constant<int, 0>{}, accA, accB);
+      if constexpr (CH >= 2) chunk(std::integral_constant<int, 1>{}, accB, accA);
+      if constexpr (CH >= 4) {
+        chunk(std::integral_constant<int, 2>{}, accA, accB);
+        chunk(std::integral_constant<int, 3>{}, accB, accA);
+      }
+      static_assert(CH == 1 || CH == 2 || CH == 4, "chunks per tile");
+      q += CH;
     }
   }
 }
@@ -1284,19 +1298,20 @@ conv_b2b_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__
         const int as2 = v & 1;
         ptx::mbar_wait(tfull2(as2), ((uint32_t)(v >> 1)) & 1u);
         ptx::tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c, ++q) {
-          const int b = q & 3;
-          const uint32_t use = (uint32_t)(q >> 2);
+        // the two 64-channel chunks of the tile, software-pipelined (see epilogue_tma): chunk 1's TMEM load flies during chunk 0's arithmetic
+        auto chunk = [&](auto cc, uint32_t (&acc)[32], uint32_t (&nxt)[32]) {
+          constexpr int c = decltype(cc)::value;
+          const int b = (q + c) & 3;
+          const uint32_t use = (uint32_t)((q + c) >> 2);
           const uint32_t rowp = epi_base + b * kEpiBufBytes + (uint32_t)row * 128u;
           float4 bias[8];
           const float4* b4 = reinterpret_cast<const float4*>(g.bias2 + j * N2 + c * 64 + half * 32);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) bias[jj] = __ldg(b4 + jj);
-          uint32_t acc[32];
-          ptx::tmem_ld_32x32b_x32(lane_base + (uint32_t)(C::kAcc2Col0 + as2 * N2 + c * 64 + half * 32), acc);
-          ptx::tmem_ld_wait();
-          if (c == 1) {
+          ptx::tmem_ld_wait(acc);
+          if constexpr (c == 0) {
+            ptx::tmem_ld_32x32b_x32(lane_base + (uint32_t)(C::kAcc2Col0 + as2 * N2 + 64 + half * 32), nxt);
+          } else {
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty2(as2));
@@ -1337,7 +1352,12 @@ conv_b2b_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant__
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(eb.ready + 8u * b);
-        }
+        };
+        uint32_t accA[32], accB[32];
+        ptx::tmem_ld_32x32b_x32(lane_base + (uint32_t)(C::kAcc2Col0 + as2 * N2 + half * 32), accA);
+        chunk(std::integral_constant<int, 0>{}, accA, accB);
+        chunk(std::integral_constant<int, 1>{}, accB, accA);
+        q += 2;
       }
     }
   }
@@ -1613,7 +1633,21 @@ stem_pool_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
       for (int j = 0; j < 8; ++j) qm[j] = __ldg(m4 + j);
     }
     const __half2 z2 = __float2half2_rn(0.f);
-    int it = 0;
+    int it = 0, n_it = 0;                                 // convolution rows of this CTA: done / in all
+    for (int unit = blockIdx.x; unit < g.num_tiles; unit += gridDim.x) {
+      int img, pr0, pr1, strip;
+      unit_geom(unit, img, pr0, pr1, strip);
+      n_it += 2 * (pr1 - pr0) + 1;
+    }
+    // The accumulator row of iteration it + 1 is requested from TMEM as soon as row it has been converted (v is dead then), so the
+    // load's latency hides behind the exchange barrier and the pooling reads instead of heading every row.
+    uint32_t v[32];
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32);
+    if (n_it > 0) {
+      ptx::mbar_wait(tfull_bar(0), 0u);
+      ptx::tc_fence_after();
+      ptx::tmem_ld_32x32b_x32(t_lane, v);
+    }
     for (int unit = blockIdx.x; unit < g.num_tiles; unit += gridDim.x) {
       int img, pr0, pr1, strip;
       unit_geom(unit, img, pr0, pr1, strip);
@@ -1627,11 +1661,7 @@ stem_pool_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
       uint4 acc8 = make_uint4(0u, 0u, 0u, 0u);
       for (int r = 2 * pr0 - 1; r <= 2 * pr1 - 1; ++r, ++it) {
         const int as = it % ACC;
-        ptx::mbar_wait(tfull_bar(as), ((uint32_t)(it / ACC)) & 1u);
-        ptx::tc_fence_after();
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + half * 32), v);
-        ptx::tmem_ld_wait();
+        ptx::tmem_ld_wait(v);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
@@ -1678,6 +1708,12 @@ stem_pool_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
             const uint32_t addr = xb + (((uint32_t)(half * 2 + j) ^ (uint32_t)((m >> 1) & 3)) << 4);   // 64-byte rows: swizzle by the 128-byte line
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
           }
+        }
+        if (it + 1 < n_it) {                               // v has been consumed: start the next row's load
+          const int as1 = (it + 1) % ACC;
+          ptx::mbar_wait(tfull_bar(as1), ((uint32_t)((it + 1) / ACC)) & 1u);
+          ptx::tc_fence_after();
+          ptx::tmem_ld_32x32b_x32(t_lane + (uint32_t)(as1 * BLOCK_N), v);
         }
         ptx::named_bar_sync(1, kEpiWarps * 32);            // the whole row is in the exchange buffer (double-buffered: one barrier per row)
         // ---- reader role: horizontal 3-max for pooled column u, channels [16 cg, 16 cg + 16)

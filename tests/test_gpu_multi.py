@@ -270,6 +270,6 @@ def test_tune_table_export_import_skips_measurements(lib, tiny):
         with pytest.raises(P.InfurError) as e:
             h2.tune_import("64 256 1 1 1 0 1 0 20 100 0\n")        # block_n 100 is not a tile size
         assert e.value.code == L.E_INVALID_ARG
-    assert tuned2 == 0 and ms2 < ms1
+    assert tuned2 == 0          # nothing measured (ms2 < ms1 as a rule, but a wall-clock comparison of two ~10 ms builds is not an invariant)
     assert plan1 == plan2
     assert (got["class_map"] == ref["class_map"]).all() and (got["decoded_rgba"] == ref["decoded_rgba"]).all()
