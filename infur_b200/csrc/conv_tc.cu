@@ -322,9 +322,6 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
     if constexpr (MODE >= 2 && CH >= 1) {
       // ---- u8 outputs (int8 plan).  CW = 128: rows of 128 bytes, 128B-swizzled like the fp16 chunks, a thread owns 64 bytes of
       // its row (two passes of 32 channels); CW = 64 (64-channel tiles): rows of 64 bytes, unswizzled, 32 bytes per thread.
-      // The passes of a tile are software-pipelined: the TMEM load of pass p + 1 is issued before the arithmetic of pass p, so
-      // its latency (and the L1 misses of the per-channel constants) hides behind ~400 instructions instead of stalling both
-      // warps of a scheduler -- with the instruction count of requant_u8_pass this loop was latency-bound, not issue-bound.
       constexpr int PASSES = CW / 64;
       constexpr int NP = CH * PASSES;             // passes per tile: 1, 2 or 4
       constexpr uint32_t kChunk = CW == 128 ? kEpiBufBytes : kEpiBufBytes / 2;
@@ -335,13 +332,15 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
       const uint32_t zout = (uint32_t)(int)(g.q_zmagic - kRneMagic);
       const uint32_t lfloor = (uint32_t)g.q_floor * 0x01010101u;
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + half * (CW / 2));
-      auto pass = [&](auto pc, uint32_t (&acc)[32], uint32_t (&nxt)[32]) {
-        constexpr int p = decltype(pc)::value;
-        constexpr int c = p / PASSES, hh = p % PASSES;
-        ptx::tmem_ld_wait(acc);
-        if constexpr (p + 1 < NP) {
-          ptx::tmem_ld_32x32b_x32(t_acc + (uint32_t)(((p + 1) / PASSES) * CW + ((p + 1) % PASSES) * 32), nxt);
-        } else {                                 // accumulator stage fully read
+      // ONE pass body in a rolled loop: four unrolled copies (with the next pass's TMEM load in flight) were tried and measured no
+      // faster -- tools/epi_tput.cu: TMEM delivers 800 B/clk/SM, the load is 1 % of a pass -- while quadrupling the loop's code.
+      uint32_t acc[32];
+#pragma unroll 1
+      for (int p = 0; p < NP; ++p) {
+        const int c = p / PASSES, hh = p % PASSES;
+        ptx::tmem_ld_32x32b_x32(t_acc + (uint32_t)(c * CW + hh * 32), acc);
+        ptx::tmem_ld_wait();
+        if (p == NP - 1) {                       // accumulator stage fully read
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -375,19 +374,11 @@ __device__ __forceinline__ void epilogue_tma(const ConvTcGeom& g, const Sched sc
         else requant_u8_pass<MODE, HAS_RES, 0>(g, acc, rw, ow, cofs, lo_out, hi1, lo2, hi2, res_bias, zout, lfloor);
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ga[0]), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ga[1]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
-        if constexpr (hh == PASSES - 1) {
+        if (hh == PASSES - 1) {
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(eb.ready + 8u * b);
         }
-      };
-      uint32_t accA[32], accB[32];
-      ptx::tmem_ld_32x32b_x32(t_acc, accA);
-      pass(std::integral_constant<int, 0>{}, accA, accB);
-      if constexpr (NP >= 2) pass(std::integral_constant<int, 1>{}, accB, accA);
-      if constexpr (NP >= 4) {
-        pass(std::integral_constant<int, 2>{}, accA, accB);
-        pass(std::integral_constant<int, 3>{}, accB, accA);
       }
       static_assert(NP == 1 || NP == 2 || NP == 4, "passes per tile");
       q += CH;

@@ -50,6 +50,77 @@ __device__ __forceinline__ void pass(const uint32_t (&acc)[32], const uint32_t (
   }
 }
 
+// TMEM variants (8 or 16 warps: warp w reads lane quadrant w % 4, 32 columns at a time, of 512 allocated columns -- their content is
+// whatever the last kernel left, which is all the arithmetic needs): T = 1 loads only, 2 load -> wait -> arithmetic, 3 the load of
+// pass p + 1 in flight during the arithmetic of pass p
+template <int T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) kt(unsigned* out, const float* qmul, const int* bias, int passes, float lo, float hi, float ra, float rb, unsigned seed,
+                                                    long long* cycles) {
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(&tmem_ptr), 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t base = tmem_ptr + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t accA[32], accB[32], rw[8], ow[8], x = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { rw[i] = seed ^ (threadIdx.x * 2654435761u + i); ow[i] = 0; }
+  const int col0 = (warp >> 2) * 32;
+  const long long t0 = clock64();
+  if (T == 3) ptx::tmem_ld_32x32b_x32(base + (uint32_t)col0, accA);
+  for (int p = 0; p < passes; p += 2) {
+    if (T == 1) {
+      ptx::tmem_ld_32x32b_x32(base + (uint32_t)((col0 + p * 32) & 511 & ~31), accA);
+      ptx::tmem_ld_32x32b_x32(base + (uint32_t)((col0 + p * 32 + 32) & 511 & ~31), accB);
+      ptx::tmem_ld_wait(accA); ptx::tmem_ld_wait(accB);
+      x ^= accA[0] ^ accA[31] ^ accB[5] ^ accB[17];
+    } else if (T == 2) {
+      ptx::tmem_ld_32x32b_x32(base + (uint32_t)((col0 + p * 32) & 511 & ~31), accA);
+      ptx::tmem_ld_wait(accA);
+      pass<true>(accA, rw, ow, qmul, bias, (p & 7) * 32, lo, hi, -(8388608.f + 37.f), ra, rb, 3u - 0x4B400000u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x ^= ow[i]; rw[i] += ow[i]; }
+      ptx::tmem_ld_32x32b_x32(base + (uint32_t)((col0 + p * 32 + 32) & 511 & ~31), accB);
+      ptx::tmem_ld_wait(accB);
+      pass<true>(accB, rw, ow, qmul, bias, ((p + 1) & 7) * 32, lo, hi, -(8388608.f + 37.f), ra, rb, 3u - 0x4B400000u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x ^= ow[i]; rw[i] += ow[i]; }
+    } else {
+      ptx::tmem_ld_wait(accA);
+      ptx::tmem_ld_32x32b_x32(base + (uint32_t)((col0 + p * 32 + 32) & 511 & ~31), accB);
+      pass<true>(accA, rw, ow, qmul, bias, (p & 7) * 32, lo, hi, -(8388608.f + 37.f), ra, rb, 3u - 0x4B400000u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x ^= ow[i]; rw[i] += ow[i]; }
+      ptx::tmem_ld_wait(accB);
+      ptx::tmem_ld_32x32b_x32(base + (uint32_t)((col0 + p * 32 + 64) & 511 & ~31), accA);
+      pass<true>(accB, rw, ow, qmul, bias, ((p + 1) & 7) * 32, lo, hi, -(8388608.f + 37.f), ra, rb, 3u - 0x4B400000u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x ^= ow[i]; rw[i] += ow[i]; }
+    }
+  }
+  if (T == 3) ptx::tmem_ld_wait(accA);
+  const long long t1 = clock64();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_ptr, 512); }
+  if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+  if (x == 0x12345678u) out[0] = x + accA[0];
+}
+
+template <int T, int WARPS>
+void runt(int sms, unsigned* d, const float* qmul, const int* bias, long long* dcyc) {
+  const int passes = 2048, warps = WARPS;
+  for (int rep = 0; rep < 2; ++rep) kt<T, WARPS><<<sms, warps * 32>>>(d, qmul, bias, passes, -128.f, 127.f, 1.37f, 0.55f, 12345u, dcyc);
+  cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost);
+  const char* names[4] = {"", "tmem loads only          ", "load -> wait -> arithmetic", "pipelined load + arithmetic"};
+  printf("%s warps/CTA %2d: %9lld cycles, %6.1f scheduler-cycles per warp-pass; %6.2f outputs (= 4-byte TMEM words)/clk/SM = %6.1f B/clk/SM of TMEM reads  [%s]\n",
+         names[T], warps, cyc, (double)cyc / passes / (warps / 4.0), 32.0 * 32.0 * warps * passes / (double)cyc, 4.0 * 32.0 * 32.0 * warps * passes / (double)cyc,
+         cudaGetErrorString(cudaGetLastError()));
+}
+
 template <bool LDG, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k(unsigned* out, const float* qmul, const int* bias, int passes, float lo, float hi, float ra, float rb, unsigned seed,
                                              long long* cycles) {
@@ -102,5 +173,8 @@ int main() {
   run<false, 16>(sms, d, qmul, bias, dcyc); run<false, 32>(sms, d, qmul, bias, dcyc);
   run<true, 4>(sms, d, qmul, bias, dcyc); run<true, 8>(sms, d, qmul, bias, dcyc); run<true, 12>(sms, d, qmul, bias, dcyc);
   run<true, 16>(sms, d, qmul, bias, dcyc); run<true, 32>(sms, d, qmul, bias, dcyc);
+  runt<1, 4>(sms, d, qmul, bias, dcyc); runt<1, 8>(sms, d, qmul, bias, dcyc); runt<1, 16>(sms, d, qmul, bias, dcyc);
+  runt<2, 8>(sms, d, qmul, bias, dcyc); runt<3, 8>(sms, d, qmul, bias, dcyc);
+  runt<2, 16>(sms, d, qmul, bias, dcyc); runt<3, 16>(sms, d, qmul, bias, dcyc);
   return 0;
 }
