@@ -242,7 +242,7 @@ def workload_name(args) -> str:
 
 # ------------------------------------------------------------------------------------------------ ncu evidence under profiles/
 def conv_traffic_from_profiles(kind: str):
-    """DRAM bytes per conv launch from the newest ncu launch list of one step kept under profiles/ (``tools/profile_step.py`` under
+    """((DRAM bytes of all conv-layer kernels, their launch count), file) from the newest ncu launch list of one step kept under profiles/ (``tools/profile_step.py`` under
     ``ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum``); None when there is none."""
     tag = "int8" if kind == "int8" else "f16"
     cands = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_launches_step_{tag}_b8_1080p.csv")), key=lambda p: (os.path.basename(p).split("_")[0], os.path.getmtime(p)))
@@ -266,12 +266,12 @@ def conv_traffic_from_profiles(kind: str):
         if not d["Metric Name"].startswith("dram__bytes"):
             continue
         name = d["Kernel Name"]
-        if "conv_tc" not in name and "stem_tc" not in name and "conv_halo" not in name:
+        if not any(t in name for t in ("conv_tc", "stem_tc", "conv_halo", "conv_b2b", "stem_pool")):   # every kernel a conv layer runs in
             continue
         per_launch[d["ID"]] = per_launch.get(d["ID"], 0.0) + float(d["Metric Value"].replace(",", "")) * scale.get(d["Metric Unit"], 0.0)
     if not per_launch:
         return None, None
-    return sum(per_launch.values()) / len(per_launch), os.path.relpath(path, ROOT)
+    return (sum(per_launch.values()), len(per_launch)), os.path.relpath(path, ROOT)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -397,15 +397,18 @@ def roofline_block(kind, plan_lines, op_ms, prof_steps, B, flops_per_frame, pk, 
     # (tools/ubench_mma.cu, profiles/r1_ubench_mma.txt), so the denominator is twice the measured sustained bf16 peak
     mult = 2.0 if kind == "int8" else 1.0
     peak = pk["bf16_tflops_sustained"] * mult
-    traffic, traffic_src = conv_traffic_from_profiles(kind)
+    # both per conv LAYER of the plan (fused layers share a launch: the same denominator keeps the ratio meaningful)
+    traffic_tot, traffic_src = conv_traffic_from_profiles(kind)
+    traffic = traffic_tot[0] / n_conv if traffic_tot else None
     algo_bytes = 1e6 * sum(float(ln.split(" MB ")[1]) for ln in op_lines if ln.startswith("conv ")) / n_conv
+    n_launched = sum(1 for ln in op_lines if ln.startswith("conv ") and "(fused into previous)" not in ln)
     roof = {
-        "kernel": "conv_tc_* / stem_tc (tcgen05 implicit-GEMM conv+bias+ReLU(+residual)), all %d conv launches of one step" % n_conv,
+        "kernel": "conv_tc_* / stem_tc (tcgen05 implicit-GEMM conv+bias+ReLU(+residual)), all %d conv layers of one step (%d launches: fused bottleneck tails share one)" % (n_conv, n_launched),
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s" if kind == "int8" else "TFLOP/s", "frac": achieved / peak,
         "basis": "conv launches timed with CUDA events INSIDE the sustained loop (every %dth step, %d steps averaged) / sustained peak" % (PROFILE_EVERY, prof_steps),
         "frac_vs_burst_peak": achieved / (pk["bf16_tflops"] * mult),
         "frac_whole_step": flops / (ms_per_step * 1e-3) / 1e12 / peak,
-        "traffic": traffic, "traffic_source": traffic_src,
+        "traffic": traffic, "traffic_source": traffic_src, "traffic_launches_in_profile": traffic_tot[1] if traffic_tot else None,
         "algorithmic_bytes_per_launch": algo_bytes,
         "traffic_over_algorithmic": (traffic / algo_bytes) if traffic else None,
         "flops_per_launch_avg": flops / n_conv, "ms_per_launch_avg": conv_ms / n_conv, "ms_all_conv_launches": conv_ms,
@@ -419,7 +422,7 @@ def roofline_block(kind, plan_lines, op_ms, prof_steps, B, flops_per_frame, pk, 
     esz = 1 if kind == "int8" else 2
     other = [hbm("pre kernel (Scale 1.0 + u8->fp16 normalise, NHWC4)", 6.2208 + 16.5888, pre_ms),
              hbm("post kernel (bilinear x8 upsample + argmax + colour)", 2.7216 + 8.2944 + 2.0736, post_ms)]
-    if pool_ms > 0:
+    if pool_ms > 0.02:      # a fused stem + pool leaves only the event overhead of the skipped op
         other.insert(1, hbm("maxpool3s2 kernel (3x3/s2, NHWC)", (66.3552 + 16.5888) * esz / 2, pool_ms))
     return roof, other
 
