@@ -147,3 +147,19 @@ def test_rust_ffi_matches_header(lib):
     # status codes
     for k, v in re.findall(r"pub const (E_[A-Z_]+): i32 = (\d+);", src):
         assert getattr(L, k) == int(v), k
+
+
+def test_no_contracted_packed_fma_in_the_library(lib):
+    """ptxas 12.9 fuses ``mul.rn.f32x2`` + ``add.rn.f32x2`` into one FFMA2 in spite of the explicit rounding modifiers (csrc/ptx.cuh,
+    ``mul_f32x2_sep``), which silently drops a rounding of QLinearAdd.  No kernel of the library wants a packed FMA, so its SASS must not
+    contain one; the tcgen05 / TMA / TMEM mnemonics the hot path is built on must be there."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", L.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "FFMA2" not in sass
+    for mnemonic in ("UTCHMMA", "UTCIMMA", "UTMALDG", "UTMASTG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert not re.search(r"\s(HMMA|IMMA)\.", sass)              # no legacy mma.sync path (UTCHMMA / UTCIMMA are the tcgen05 forms)
