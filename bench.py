@@ -24,7 +24,8 @@ Printed by rank 0 as ONE JSON line:
                 against the fp16-emulating oracle, largest oracle top-2 margin over mismatching pixels, RGBA max |diff|
   roofline      the tcgen05 implicit-GEMM conv kernels: algorithmic conv FLOPs / summed CUDA-event time of the conv launches,
                 timed INSIDE the sustained loop (every 8th step carries an event after each kernel), against the measured
-                sustained bf16 peak; `traffic` = DRAM bytes per launch from the newest ncu launch list under profiles/
+                sustained bf16 peak; `traffic` = DRAM bytes per conv layer from the newest ncu launch list under profiles/;
+                `layerwise_floor_ms` = sum over the launches of max(tensor-core time, HBM time) at the measured peaks
   int8          the same measurements for the QOperator-quantised network (the kind of file configs[0] names), same run
   cpu_baseline  the oracle pipeline (PyTorch-CPU fp32 + numpy) on the box's host cores, bounded sample (N = 1 only)
 ``--impl reference`` times that CPU pipeline alone (the reference's onnxruntime path cannot be built here: no Rust, no
@@ -402,12 +403,21 @@ def roofline_block(kind, plan_lines, op_ms, prof_steps, B, flops_per_frame, pk, 
     traffic = traffic_tot[0] / n_conv if traffic_tot else None
     algo_bytes = 1e6 * sum(float(ln.split(" MB ")[1]) for ln in op_lines if ln.startswith("conv ")) / n_conv
     n_launched = sum(1 for ln in op_lines if ln.startswith("conv ") and "(fused into previous)" not in ln)
+    # layer-wise roofline: every launch at the better of its tensor-core time and its HBM time (algorithmic FLOPs and bytes of the plan,
+    # measured peaks) -- what this layer-by-layer algorithm could reach at best; only cross-layer fusion moves it
+    floor_ms = 0.0
+    for ln in op_lines:
+        if ln.startswith("conv ") and " MB " in ln:
+            gf = float(ln.split("GFLOP ")[1].split()[0]) if "GFLOP " in ln else 0.0
+            mb = float(ln.split(" MB ")[1].split()[0])
+            floor_ms += max(gf / (peak * 1e3) * 1e3, mb * 1e6 / (pk["hbm_gbs"] * 1e9) * 1e3)
     roof = {
         "kernel": "conv_tc_* / stem_tc (tcgen05 implicit-GEMM conv+bias+ReLU(+residual)), all %d conv layers of one step (%d launches: fused bottleneck tails share one)" % (n_conv, n_launched),
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s" if kind == "int8" else "TFLOP/s", "frac": achieved / peak,
         "basis": "conv launches timed with CUDA events INSIDE the sustained loop (every %dth step, %d steps averaged) / sustained peak" % (PROFILE_EVERY, prof_steps),
         "frac_vs_burst_peak": achieved / (pk["bf16_tflops"] * mult),
         "frac_whole_step": flops / (ms_per_step * 1e-3) / 1e12 / peak,
+        "layerwise_floor_ms": floor_ms, "frac_of_layerwise_floor": floor_ms / conv_ms if conv_ms > 0 else None,
         "traffic": traffic, "traffic_source": traffic_src, "traffic_launches_in_profile": traffic_tot[1] if traffic_tot else None,
         "algorithmic_bytes_per_launch": algo_bytes,
         "traffic_over_algorithmic": (traffic / algo_bytes) if traffic else None,
