@@ -1678,7 +1678,9 @@ stem_pool_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
           }
         } else {
           // QLinearConv requantisation exactly as epilogue_tma's u8 path: r = clamp(rne((acc + b) * m), lo, hi), byte = r + zero point
-          const uint32_t xb = xch_base + (uint32_t)(it & 1) * kSpXchBytes + (uint32_t)m * 64u;
+          // 64-byte rows: odd row pairs are stored swapped (row m at slot m ^ ((m >> 1) & 1)) so that rows two apart -- what the lanes of
+          // a quarter-warp read in the pooling pass -- sit in different halves of the bank space
+          const uint32_t xb = xch_base + (uint32_t)(it & 1) * kSpXchBytes + (uint32_t)(m ^ ((m >> 1) & 1)) * 64u;
           const float lo_out = g.relu ? fmaxf(g.q_lo, 0.f) : g.q_lo, hi1 = g.q_hi;
           const uint32_t zout = (uint32_t)(int)(g.q_zmagic - kRneMagic);
 #pragma unroll
@@ -1722,7 +1724,11 @@ stem_pool_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
 #pragma unroll
               for (int gq = 0; gq < 2; ++gq) {
                 uint4 w4;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w4.x), "=r"(w4.y), "=r"(w4.z), "=r"(w4.w) : "r"(rowp + (((uint32_t)(2 * cg + gq) ^ sw) << 4)));
+                // which of its two 16-byte groups a thread reads first alternates with the pooled column: the rows of neighbouring
+                // columns are two apart (same swizzle parity), so reading the same group in both would put the eight lanes of a
+                // quarter-warp on four bank groups -- a 2-way conflict on every load of a kernel that is shared-memory-bound
+                // (ncu: LSU + tensor-core wavefronts = 96 % of the pipe, 9.9 M of 16.2 M load wavefronts were conflicts)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w4.x), "=r"(w4.y), "=r"(w4.z), "=r"(w4.w) : "r"(rowp + (((uint32_t)(2 * cg + (gq ^ (u & 1))) ^ sw) << 4)));
                 const __half2* hv = reinterpret_cast<const __half2*>(&w4);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) hmx[4 * gq + t] = __hmax2(hmx[4 * gq + t], hv[t]);
@@ -1741,7 +1747,7 @@ stem_pool_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
               __half2* h1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
               for (int t = 0; t < 4; ++t) { h0[t] = acc_out[t]; h1[t] = acc_out[4 + t]; }
-              dst[0] = o0; dst[1] = o1;
+              dst[u & 1] = o0; dst[(u & 1) ^ 1] = o1;      // acc_out[0..3] holds the group that was read first (see the loads above)
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc_out[j] = hmx[j];
@@ -1755,7 +1761,7 @@ stem_pool_kernel(const __grid_constant__ ConvTcMaps maps, const __grid_constant_
               const int mm = 2 * u + 7 + dm;
               uint4 w4;
               asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w4.x), "=r"(w4.y), "=r"(w4.z), "=r"(w4.w)
-                           : "r"(rb + (uint32_t)mm * 64u + (((uint32_t)cg ^ (uint32_t)((mm >> 1) & 3)) << 4)));
+                           : "r"(rb + (uint32_t)(mm ^ ((mm >> 1) & 1)) * 64u + (((uint32_t)cg ^ (uint32_t)((mm >> 1) & 3)) << 4)));
               hm8 = make_uint4(__vmaxu4(hm8.x, w4.x), __vmaxu4(hm8.y, w4.y), __vmaxu4(hm8.z, w4.z), __vmaxu4(hm8.w, w4.w));
             }
           }
