@@ -108,6 +108,74 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kt(unsigned* out, const float* 
   if (x == 0x12345678u) out[0] = x + accA[0];
 }
 
+// Chunk hand-over variants (8 warps): every pass = TMEM load + arithmetic + two 16-byte shared-memory stores; every second pass ends a
+// chunk: F = 0 nothing more, 1 fence.proxy.async + __syncwarp + mbarrier arrive right after the stores (what the kernels do), 2 the same
+// but one pass later (the stores have long drained when the fence executes)
+template <int F>
+__global__ void __launch_bounds__(256, 1) kf(unsigned* out, const float* qmul, const int* bias, int passes, float lo, float hi, float ra, float rb, unsigned seed,
+                                            long long* cycles) {
+  __shared__ uint32_t tmem_ptr;
+  __shared__ __align__(16) uint8_t buf[2][128 * 128];
+  __shared__ __align__(8) unsigned long long bar[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(&tmem_ptr), 512); ptx::tmem_relinquish(); }
+  if (threadIdx.x == 0) { ptx::mbar_init(ptx::smem_u32(&bar[0]), 1u << 19); ptx::mbar_init(ptx::smem_u32(&bar[1]), 1u << 19); ptx::fence_mbar_init(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t base = tmem_ptr + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc[32], rw[8], ow[8], x = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { rw[i] = seed ^ (threadIdx.x * 2654435761u + i); ow[i] = 0; }
+  const int half = warp >> 2, row = (warp & 3) * 32 + lane;
+  const uint32_t sw = (uint32_t)(row & 7);
+  const long long t0 = clock64();
+  int pending = -1;
+  for (int p = 0; p < passes; ++p) {
+    const int b = (p >> 1) & 1, hh = p & 1;
+    ptx::tmem_ld_32x32b_x32(base + (uint32_t)(((half * 64 + hh * 32) + (p & 3) * 128) & 511 & ~31), acc);
+    ptx::tmem_ld_wait();
+    pass<true>(acc, rw, ow, qmul, bias, (p & 7) * 32, lo, hi, -(8388608.f + 37.f), ra, rb, 3u - 0x4B400000u);
+    const uint32_t rowb = ptx::smem_u32(&buf[b][0]) + (uint32_t)row * 128u;
+    const uint32_t g0 = rowb + (((uint32_t)(half * 4 + hh * 2) ^ sw) << 4), g1 = rowb + (((uint32_t)(half * 4 + hh * 2 + 1) ^ sw) << 4);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(g0), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(g1), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7]) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x ^= ow[i]; rw[i] += ow[i]; }
+    if (F == 2 && pending >= 0 && hh == 0) {     // hand over the PREVIOUS chunk now
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar[pending]));
+      pending = -1;
+    }
+    if (hh == 1) {
+      if (F == 1) {
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar[b]));
+      } else if (F == 2) pending = b;
+    }
+  }
+  const long long t1 = clock64();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_ptr, 512); }
+  if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+  if (x == 0x12345678u) out[0] = x + buf[0][threadIdx.x];
+}
+
+template <int F>
+void runf(int sms, unsigned* d, const float* qmul, const int* bias, long long* dcyc) {
+  const int passes = 2048;
+  for (int rep = 0; rep < 2; ++rep) kf<F><<<sms, 256>>>(d, qmul, bias, passes, -128.f, 127.f, 1.37f, 0.55f, 12345u, dcyc);
+  cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost);
+  const char* names[3] = {"stores only", "fence + arrive right after the stores", "fence + arrive one pass later"};
+  printf("chunk hand-over, 8 warps: %9lld cycles, %6.1f scheduler-cycles per warp-pass  [%s; %s]\n", cyc, (double)cyc / passes / 2.0, names[F],
+         cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int T, int WARPS>
 void runt(int sms, unsigned* d, const float* qmul, const int* bias, long long* dcyc) {
   const int passes = 2048, warps = WARPS;
@@ -176,5 +244,6 @@ int main() {
   runt<1, 4>(sms, d, qmul, bias, dcyc); runt<1, 8>(sms, d, qmul, bias, dcyc); runt<1, 16>(sms, d, qmul, bias, dcyc);
   runt<2, 8>(sms, d, qmul, bias, dcyc); runt<3, 8>(sms, d, qmul, bias, dcyc);
   runt<2, 16>(sms, d, qmul, bias, dcyc); runt<3, 16>(sms, d, qmul, bias, dcyc);
+  runf<0>(sms, d, qmul, bias, dcyc); runf<1>(sms, d, qmul, bias, dcyc); runf<2>(sms, d, qmul, bias, dcyc);
   return 0;
 }
